@@ -279,7 +279,8 @@ static int next_combo(int* c, int k, int n) {   /* lexicographic successor == st
 }
 static void make_time_prop_btable(mceo* e, mceo_term* term) {
   const int m = term->m, d = term->d;
-  if (m < d) { int n = 1 << (m - 1); for (int i = 0; i < n; i++) term->enc_B[i] = i; return; }
+  if (m < d) { int n = 1 << (m - 1); for (int i = 0; i < n; i++) term->enc_B[i] = i; return; }   /* cells_gtable keeps its stale value (ce:681-687) */
+  if (m == d) { term->cells_gtable = 0; return; }   /* combo_counts[m] = 0 for m <= d (ce:454-459): the serial path yields an EMPTY table */
   const int phc = term->phc;
   double Ac[d * d], work[d * d], bc[d], vertex[d]; int P[d], combo[d];
   const double* b_pert = e->b_pert; const double* A = term->A;
