@@ -1,0 +1,74 @@
+"""ctypes binding of include/mce_b200.h (libmce_b200.so).  No compute lives here: every call crosses the C ABI."""
+import ctypes as ct
+import os
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libmce_b200.so")
+MAXM = 32
+
+
+class MceOptions(ct.Structure):
+    _fields_ = [("device", ct.c_int), ("tr_search_order", ct.c_int * 12), ("print_basic_info", ct.c_int),
+                ("fast_moments", ct.c_int), ("reserved", ct.c_int * 7)]
+
+
+class MceMoments(ct.Structure):
+    _fields_ = [("fz", ct.c_double * 2), ("fz_after_mu", ct.c_double * 2), ("mean", ct.c_double * 32), ("cov", ct.c_double * 512),
+                ("g_scale_factor", ct.c_double), ("numeric_moment_errors", ct.c_int), ("Nt", ct.c_int), ("Nt_after_muc", ct.c_int),
+                ("master_step", ct.c_int), ("skip_post_mu", ct.c_int)]
+
+
+class MceStepStats(ct.Structure):
+    _fields_ = [(n, ct.c_double) for n in ("ms_total", "ms_tp", "ms_mu", "ms_moments", "ms_regroup", "ms_ftr", "ms_gtable", "ms_compact")] + \
+               [(n, ct.c_longlong) for n in ("parents", "slots", "terms_after_muc", "groups", "survivors", "bytes_gtable_algorithmic",
+                                             "bytes_step_algorithmic", "kernel_launches")] + \
+               [(n, ct.c_int) for n in ("ftr_rounds_max", "diag_unmodelled_alias", "diag_hash_overflow")]
+
+
+# every symbol include/mce_b200.h declares
+SYMBOLS = ["mce_default_options", "mce_create", "mce_destroy", "mce_step", "mce_get_moments", "mce_shape_range",
+           "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_shift_b",
+           "mce_deterministic_time_prop", "mce_export_shape", "mce_get_step_stats", "mce_debug_capture", "mce_debug_muc_shape",
+           "mce_last_error", "mce_version"]
+
+
+def bind(lib):
+    dp, ip = ct.POINTER(ct.c_double), ct.POINTER(ct.c_int)
+    lib.mce_create.restype = ct.c_void_p
+    lib.mce_create.argtypes = [ct.c_int] * 5 + [dp] * 5 + [ct.POINTER(MceOptions)]
+    lib.mce_destroy.argtypes = [ct.c_void_p]
+    lib.mce_destroy.restype = None
+    lib.mce_step.restype = ct.c_int
+    lib.mce_step.argtypes = [ct.c_void_p, ct.c_double, dp, dp, dp, dp, ct.c_double, dp, dp]
+    lib.mce_get_moments.argtypes = [ct.c_void_p, ct.POINTER(MceMoments)]
+    lib.mce_shape_range.argtypes = [ct.c_void_p]
+    lib.mce_get_terms_per_shape.argtypes = [ct.c_void_p, ip, ct.c_int]
+    lib.mce_set_master_step.argtypes = [ct.c_void_p, ct.c_int]
+    lib.mce_set_master_step.restype = None
+    lib.mce_reset.argtypes = [ct.c_void_p]
+    lib.mce_reinitialize_start_statistics.argtypes = [ct.c_void_p, dp, dp, dp]
+    lib.mce_shift_b.argtypes = [ct.c_void_p, dp, ct.c_double]
+    lib.mce_deterministic_time_prop.argtypes = [ct.c_void_p, dp, dp, dp]
+    lib.mce_export_shape.argtypes = [ct.c_void_p, ct.c_int, ip, ct.POINTER(ct.c_longlong), dp, dp, dp, ip, ct.POINTER(ct.c_uint32), dp]
+    lib.mce_get_step_stats.argtypes = [ct.c_void_p, ct.POINTER(MceStepStats)]
+    lib.mce_debug_capture.argtypes = [ct.c_void_p, ct.c_int]
+    lib.mce_debug_muc_shape.argtypes = [ct.c_void_p, ct.c_int, ip, dp, dp, dp, dp, dp, ip, ct.POINTER(ct.c_uint8), ct.POINTER(ct.c_int8), ip]
+    lib.mce_last_error.restype = ct.c_char_p
+    lib.mce_version.restype = ct.c_char_p
+    lib.mce_default_options.argtypes = [ct.POINTER(MceOptions)]
+    lib.mce_default_options.restype = None
+    return lib
+
+
+_LIB = None
+
+
+def load():
+    """Loads libmce_b200.so. Raises when the CUDA extension has not been built: there is no fallback."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("cauchyfriendly_b200: %s is missing; build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)" % LIB_PATH)
+        _LIB = bind(ct.CDLL(LIB_PATH))
+    return _LIB

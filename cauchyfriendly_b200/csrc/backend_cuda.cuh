@@ -1,0 +1,117 @@
+// backend_cuda.cuh -- the CUDA (sm_100a) backend of the MCE engine: device memory, one stream, kernel launch
+// of the functors in mce_kern_*.h, and the two library primitives the path uses (CUB radix sort of the
+// FTR axis keys / reduction-group keys, CUB exclusive scan).  Everything else is hand-written kernels.
+#ifndef MCE_BACKEND_CUDA_CUH_
+#define MCE_BACKEND_CUDA_CUH_
+
+#include <cuda_runtime.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <stdexcept>
+#include <string>
+
+#include "mce_exec.h"
+
+namespace mce {
+
+#define MCE_CUDA_CHECK(expr)                                                                              \
+  do {                                                                                                    \
+    cudaError_t e__ = (expr);                                                                             \
+    if (e__ != cudaSuccess)                                                                               \
+      throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+template <class K>
+__global__ void mce_kernel_entry(const __grid_constant__ K k) {
+  extern __shared__ __align__(16) unsigned char mce_dyn_smem[];
+  DevCtx c;
+  c.smem_ = mce_dyn_smem;
+  k.run(c);
+}
+
+struct CudaBackend {
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  long long launch_count = 0;
+  void* cub_tmp = nullptr;
+  size_t cub_tmp_bytes = 0;
+  size_t bytes_allocated = 0;
+
+  static bool available(int dev, std::string* why) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { *why = std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); libmce_b200 has no CPU fallback"; return false; }
+    if (dev >= n) { *why = "device ordinal out of range"; return false; }
+    return true;
+  }
+  bool init(int dev, std::string* why) {
+    try {
+      if (dev >= 0) MCE_CUDA_CHECK(cudaSetDevice(dev));
+      MCE_CUDA_CHECK(cudaGetDevice(&device));
+      MCE_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    } catch (const std::exception& ex) { *why = ex.what(); return false; }
+    return true;
+  }
+  void shutdown() {
+    if (cub_tmp) cudaFree(cub_tmp);
+    cub_tmp = nullptr; cub_tmp_bytes = 0;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+  void* alloc(size_t n) {
+    void* p = nullptr;
+    MCE_CUDA_CHECK(cudaSetDevice(device));
+    MCE_CUDA_CHECK(cudaMalloc(&p, n ? n : 1));
+    bytes_allocated += n;
+    return p;
+  }
+  void free(void* p) {
+    cudaStreamSynchronize(stream);
+    cudaFree(p);
+  }
+  void h2d(void* d, const void* s, size_t n) { MCE_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream)); MCE_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void d2h(void* d, const void* s, size_t n) { MCE_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream)); MCE_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void memset(void* p, int v, size_t n) { MCE_CUDA_CHECK(cudaMemsetAsync(p, v, n, stream)); }
+  void sync() { MCE_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  double tic() {
+    MCE_CUDA_CHECK(cudaStreamSynchronize(stream));
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  }
+  double toc(double t0) { return tic() - t0; }
+
+  template <class K>
+  void launch(const K& k, int nblocks, int nthreads, size_t smem) {
+    if (nblocks <= 0) return;
+    static_assert(sizeof(K) <= 32000, "kernel functor exceeds the 32 KB parameter space (CUDA >= 12.1, sm_70+)");
+    if (smem > 48 * 1024) MCE_CUDA_CHECK(cudaFuncSetAttribute(mce_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    mce_kernel_entry<K><<<nblocks, nthreads, smem, stream>>>(k);
+    MCE_CUDA_CHECK(cudaGetLastError());
+    launch_count++;
+  }
+  void ensure_tmp(size_t bytes) {
+    if (bytes > cub_tmp_bytes) {
+      if (cub_tmp) { cudaStreamSynchronize(stream); cudaFree(cub_tmp); }
+      MCE_CUDA_CHECK(cudaMalloc(&cub_tmp, bytes + bytes / 2 + 256));
+      cub_tmp_bytes = bytes + bytes / 2 + 256;
+    }
+  }
+  void sort_pairs(const unsigned long long* kin, unsigned long long* kout, const int* vin, int* vout, int n) {
+    size_t bytes = 0;
+    MCE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, kin, kout, vin, vout, n, 0, 64, stream));
+    ensure_tmp(bytes);
+    MCE_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, kin, kout, vin, vout, n, 0, 64, stream));
+    launch_count++;
+  }
+  void exclusive_scan(const int* in, int* out, int n) {
+    size_t bytes = 0;
+    MCE_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, in, out, n, stream));
+    ensure_tmp(bytes);
+    MCE_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cub_tmp, bytes, in, out, n, stream));
+    launch_count++;
+  }
+};
+
+}  // namespace mce
+#endif

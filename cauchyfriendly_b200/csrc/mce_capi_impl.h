@@ -1,0 +1,129 @@
+// mce_capi_impl.h -- extern "C" entry points of include/mce_b200.h over Engine<MCE_BACKEND>.
+// Included exactly once by mce_capi.cu (CUDA backend -> libmce_b200.so).
+#ifndef MCE_CAPI_IMPL_H_
+#define MCE_CAPI_IMPL_H_
+
+#include <new>
+#include <string>
+
+#include "../../include/mce_b200.h"
+#include "mce_engine.h"
+
+using EngineT = mce::Engine<MCE_BACKEND>;
+struct mce_handle { EngineT* e; };
+static thread_local std::string g_mce_error;
+
+extern "C" {
+
+void mce_default_options(mce_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->device = -1;
+  for (int i = 0; i < 12; i++) o->tr_search_order[i] = i;
+}
+
+mce_handle* mce_create(int d, int cmcc, int pncc, int p, int steps, const double* A0, const double* p0, const double* b0,
+                       const double* root_point, const double* b_pert, const mce_options* opts) {
+  mce_options def; mce_default_options(&def);
+  if (!opts) opts = &def;
+  if (!A0 || !p0 || !b0 || !root_point || !b_pert || p < 1 || steps < 1 || pncc < 0 || cmcc < 0) { g_mce_error = "mce_create: bad argument"; return nullptr; }
+  const int max_shape = d > 1 ? (steps - 1) * pncc + d : d + pncc;
+  std::string why;
+  if (!EngineT::supported(d, max_shape, pncc, &why)) { g_mce_error = "mce_create: " + why; return nullptr; }
+  std::string berr;
+  if (!MCE_BACKEND::available(opts->device, &berr)) { g_mce_error = "mce_create: " + berr; return nullptr; }
+  EngineT* e = new (std::nothrow) EngineT(d, cmcc, pncc, p, steps, A0, p0, b0, root_point, b_pert, opts->tr_search_order, opts->print_basic_info);
+  if (!e) { g_mce_error = "mce_create: out of memory"; return nullptr; }
+  e->fast_moments = opts->fast_moments != 0;
+  if (!e->be.init(opts->device, &berr)) { g_mce_error = "mce_create: " + berr; delete e; return nullptr; }
+  mce_handle* h = new mce_handle; h->e = e;
+  return h;
+}
+
+void mce_destroy(mce_handle* h) {
+  if (!h) return;
+  h->e->be.shutdown();
+  delete h->e; delete h;
+}
+
+int mce_step(mce_handle* h, double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
+             const double* B, const double* u) {
+  if (!h || !H) { g_mce_error = "mce_step: bad argument"; return MCE_ERR_BAD_ARG; }
+  EngineT* e = h->e;
+  if (e->master_step > 0 && (e->master_step % e->p) == 0 && (!Phi || (e->pncc > 0 && (!Gamma || !beta)))) { g_mce_error = "mce_step: Phi/Gamma/beta required on a time-propagation step"; return MCE_ERR_BAD_ARG; }
+  int rc;
+  try { rc = e->step(msmt, Phi, Gamma, beta, H, gamma, B, u); }
+  catch (const std::exception& ex) { g_mce_error = std::string("mce_step: ") + ex.what(); return MCE_ERR_CUDA; }
+  if (rc < 0) g_mce_error = "mce_step: " + e->error;
+  return rc;
+}
+
+int mce_get_moments(mce_handle* h, mce_moments* out) {
+  if (!h || !out) return MCE_ERR_BAD_ARG;
+  EngineT* e = h->e;
+  memset(out, 0, sizeof(*out));
+  out->fz[0] = e->fz.re; out->fz[1] = e->fz.im; out->fz_after_mu[0] = e->fz_mu.re; out->fz_after_mu[1] = e->fz_mu.im;
+  for (int i = 0; i < e->d; i++) { out->mean[2 * i] = e->mean[i].re; out->mean[2 * i + 1] = e->mean[i].im; }
+  for (int i = 0; i < e->d * e->d; i++) { out->cov[2 * i] = e->var[i].re; out->cov[2 * i + 1] = e->var[i].im; }
+  out->g_scale_factor = e->G_SCALE_FACTOR; out->numeric_moment_errors = e->numeric_moment_errors;
+  out->Nt = e->Nt; out->Nt_after_muc = e->Nt_muc; out->master_step = e->master_step; out->skip_post_mu = e->skip_post_mu;
+  return 0;
+}
+int mce_shape_range(mce_handle* h) { return h ? h->e->shape_range : MCE_ERR_BAD_ARG; }
+int mce_get_terms_per_shape(mce_handle* h, int* counts, int after_muc) {
+  if (!h || !counts) return MCE_ERR_BAD_ARG;
+  const std::vector<int>& v = after_muc ? h->e->muc_per_shape : h->e->terms_per_shape;
+  for (int i = 0; i < h->e->shape_range; i++) counts[i] = v[i];
+  return 0;
+}
+void mce_set_master_step(mce_handle* h, int master_step) { if (h) h->e->master_step = master_step; }
+int mce_reset(mce_handle* h) { if (!h) return MCE_ERR_BAD_ARG; h->e->reset(); return 0; }
+int mce_reinitialize_start_statistics(mce_handle* h, const double* A0, const double* p0, const double* b0) {
+  if (!h || !A0 || !p0 || !b0) return MCE_ERR_BAD_ARG;
+  EngineT* e = h->e;
+  e->A0.assign(A0, A0 + e->d * e->d); e->p0.assign(p0, p0 + e->d); e->b0.assign(b0, b0 + e->d);
+  return 0;
+}
+int mce_shift_b(mce_handle* h, const double* delta, double sign) {
+  if (!h || !delta) return MCE_ERR_BAD_ARG;
+  try { return h->e->shift_b(delta, sign); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
+int mce_deterministic_time_prop(mce_handle* h, const double* Phi, const double* B, const double* u) {
+  if (!h || !Phi) return MCE_ERR_BAD_ARG;
+  if ((B == nullptr) != (u == nullptr)) { g_mce_error = "mce_deterministic_time_prop: set both B and u or neither (est:1336-1344)"; return MCE_ERR_BAD_ARG; }
+  try { return h->e->det_time_prop(Phi, B, u); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
+int mce_export_shape(mce_handle* h, int m, int* n_terms, long long* n_cells_total, double* A, double* p, double* b, int* cells, uint32_t* keys, double* G) {
+  if (!h || !n_terms || !n_cells_total) return MCE_ERR_BAD_ARG;
+  try { return h->e->export_shape(m, n_terms, n_cells_total, A, p, b, cells, keys, G); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
+int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
+  if (!h || !out) return MCE_ERR_BAD_ARG;
+  const mce::StepStats& s = h->e->stats;
+  memset(out, 0, sizeof(*out));
+  out->ms_total = s.ms_total; out->ms_tp = s.ms_tp; out->ms_mu = s.ms_mu; out->ms_moments = s.ms_moments; out->ms_regroup = s.ms_regroup;
+  out->ms_ftr = s.ms_ftr; out->ms_gtable = s.ms_gtable; out->ms_compact = s.ms_compact;
+  out->parents = s.parents; out->slots = s.slots; out->terms_after_muc = s.terms_after_muc; out->groups = s.groups; out->survivors = s.survivors;
+  out->bytes_gtable_algorithmic = s.bytes_gtable; out->bytes_step_algorithmic = s.bytes_step; out->kernel_launches = s.launches;
+  out->ftr_rounds_max = s.ftr_rounds_max; out->diag_unmodelled_alias = s.diag_alias; out->diag_hash_overflow = s.diag_hash;
+  return 0;
+}
+int mce_debug_capture(mce_handle* h, int enable) { if (!h) return MCE_ERR_BAD_ARG; h->e->capture = enable != 0; return 0; }
+int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd, int* meta, uint8_t* cmap, int8_t* csmap, int* F) {
+  if (!h || !n_terms) return MCE_ERR_BAD_ARG;
+  *n_terms = 0;
+  for (auto& cs : h->e->cap) {
+    if (cs.m != m) continue;
+    *n_terms = cs.n;
+    if (A) {
+      memcpy(A, cs.A.data(), cs.A.size() * 8); memcpy(p, cs.p.data(), cs.p.size() * 8); memcpy(q, cs.q.data(), cs.q.size() * 8);
+      memcpy(b, cs.b.data(), cs.b.size() * 8); memcpy(cd, cs.cd.data(), cs.cd.size() * 8); memcpy(meta, cs.meta.data(), cs.meta.size() * 4);
+      memcpy(cmap, cs.cmap.data(), cs.cmap.size()); memcpy(csmap, cs.csmap.data(), cs.csmap.size()); memcpy(F, cs.F.data(), cs.F.size() * 4);
+    }
+  }
+  return 0;
+}
+const char* mce_last_error(void) { return g_mce_error.c_str(); }
+const char* mce_version(void) { return MCE_VERSION_STRING; }
+
+}  // extern "C"
+#endif

@@ -1,0 +1,638 @@
+// mce_engine.h -- host-side step driver of the B200 MCE path: owns the device-resident term store and
+// sequences the kernels of mce_kern_*.h for CauchyEstimator::step() (cauchy_estimator.hpp:1211-1245).
+// The driver is written against a Backend policy (allocation, copies, kernel launch, sort/scan primitives);
+// libmce_b200.so instantiates it with the CUDA backend only (backend_cuda.cuh).
+#ifndef MCE_ENGINE_H_
+#define MCE_ENGINE_H_
+
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "mce_kern_ftr.h"
+#include "mce_kern_group.h"
+#include "mce_kern_prop.h"
+
+namespace mce {
+
+// reference error bits, cauchy_constants.hpp:104-116
+enum { ERROR_COVARIANCE_UNSTABLE_ANY_STEP = 0, ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT = 1,
+       ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT = 2, ERROR_COVARIANCE_AT_CURRENT_STEP_DNE = 3,
+       ERROR_MEAN_UNSTABLE_ANY_STEP = 4, ERROR_MEAN_UNSTABLE_CURRENT_STEP_FINAL_MSMT = 5,
+       ERROR_MEAN_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT = 6, ERROR_MEAN_AT_CURRENT_STEP_DNE = 7,
+       ERROR_FZ_UNSTABLE = 8, ERROR_FZ_NEGATIVE = 9 };
+
+struct StepStats {
+  double ms_total = 0, ms_tp = 0, ms_mu = 0, ms_moments = 0, ms_regroup = 0, ms_ftr = 0, ms_gtable = 0, ms_compact = 0;
+  long long parents = 0, slots = 0, terms_after_muc = 0, groups = 0, survivors = 0;
+  long long bytes_gtable = 0, bytes_step = 0, launches = 0;
+  int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
+};
+
+template <class BE>
+struct DevBuf {           // grow-only device buffer; contents are not preserved across growth
+  BE* be = nullptr; void* p = nullptr; size_t cap = 0;
+  void* ensure(size_t bytes) {
+    if (bytes > cap) {
+      if (p) be->free(p);
+      size_t want = bytes + bytes / 4 + 256;
+      p = be->alloc(want); cap = want;
+    }
+    return p;
+  }
+  template <class T> T* as() const { return (T*)p; }
+  void release() { if (p) be->free(p); p = nullptr; cap = 0; }
+};
+
+// Host-side covariance checks (cauchy_util.hpp:1882-2004); eigenvalues of the lower triangle by cyclic Jacobi
+// (the reference's NR tred2/tqli also reads the lower triangle, eig_solve.hpp:263-404).
+inline void sym_eigvals(const double* A, double* ev, int n) {
+  std::vector<double> a(n * n);
+  for (int i = 0; i < n; i++) for (int j = 0; j <= i; j++) a[i * n + j] = a[j * n + i] = A[i * n + j];
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0;
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++) off += a[i * n + j] * a[i * n + j];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n - 1; p++) for (int q = p + 1; q < n; q++) {
+      if (fabs(a[p * n + q]) < 1e-300) continue;
+      double theta = (a[q * n + q] - a[p * n + p]) / (2.0 * a[p * n + q]);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      for (int k = 0; k < n; k++) { double akp = a[k * n + p], akq = a[k * n + q]; a[k * n + p] = c * akp - s * akq; a[k * n + q] = s * akp + c * akq; }
+      for (int k = 0; k < n; k++) { double apk = a[p * n + k], aqk = a[q * n + k]; a[p * n + k] = c * apk - s * aqk; a[q * n + k] = s * apk + c * aqk; }
+    }
+  }
+  for (int i = 0; i < n; i++) ev[i] = a[i * n + i];
+}
+inline int covariance_checker(const cplx* cov, int d) {
+  int flags = 0; std::vector<double> cr(d * d), ci(d * d), eig(d);
+  for (int i = 0; i < d * d; i++) { cr[i] = cov[i].re; ci[i] = cov[i].im; }
+  sym_eigvals(cr.data(), eig.data(), d);
+  for (int i = 0; i < d; i++) if (eig[i] < -1e-5) flags |= 1 << 0;
+  for (int i = 0; i < d - 1; i++) {
+    double sig_ii = sqrt(cr[i * d + i]);
+    for (int j = i + 1; j < d; j++) { double corr = cr[i * d + j] / (sig_ii * sqrt(cr[j * d + j])); if (fabs(corr) > 1) flags |= 1 << 1; }
+  }
+  for (int i = 0; i < d; i++) for (int j = i; j < d; j++) { double ratio = fabs(ci[i * d + j]) / (fabs(cr[i * d + j]) + 1e-15); if (ratio > 10) flags |= 1 << 2; }
+  for (int i = 0; i < d * d; i++) if (fabs(ci[i]) > 2000) flags |= 1 << 3;
+  return flags;
+}
+
+template <class BE>
+class Engine {
+ public:
+  BE be;
+  int d, cmcc, pncc, p, steps, num_estimation_steps, max_shape, shape_range;
+  int master_step = 0, Nt = 1, Nt_muc = 1, numeric_moment_errors = 0, skip_post_mu = 0, print_basic_info = 0;
+  int tr_order[12];
+  std::vector<double> A0, p0, b0, root_point, b_pert;
+  double G_SCALE_FACTOR = 0;
+  cplx fz, last_fz, fz_mu; std::vector<cplx> mean, var, last_mean, last_var;
+  std::vector<int> terms_per_shape, muc_per_shape;
+  StepStats stats;
+  std::string error;
+  bool finished = false;     // the window's last step has run: only reset() is valid now
+  bool fast_moments = false; // mean/covariance by a two-level tree instead of the reference's serial order (fz stays serial)
+
+  // ---- device state ----
+  struct GenStore {
+    GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G;
+    std::vector<int> alive_per_shape;   // survivors per shape
+  } gen[2];
+  int cur = 0;
+  DevBuf<BE> wsA, wsp, wsb, wsm, wsSgn, wsXor, wsTpB, wsTpBc;
+  DevBuf<BE> slA, slp, slq, slb, slmeta, slcmap, slg, sly;
+  DevBuf<BE> tvA, tvp, tvq, tvb, tvmeta, tvcmap, slotOfTerm;
+  DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
+  DevBuf<BE> ftrF, ftrWide, grpOrder, grpStart, aliveFlag, diagBuf, unkBuf, initBuf;
+  // debug capture
+  bool capture = false;
+  struct CapShape { int m = 0, n = 0; std::vector<double> A, p, q, b, cd; std::vector<int> meta, F; std::vector<unsigned char> cmap; std::vector<signed char> csmap; };
+  std::vector<CapShape> cap;
+
+  Engine(int d_, int cmcc_, int pncc_, int p_, int steps_, const double* A0_, const double* p0_, const double* b0_,
+         const double* root_point_, const double* b_pert_, const int* tr_order_, int print_info)
+      : d(d_), cmcc(cmcc_), pncc(pncc_), p(p_), steps(steps_) {
+    num_estimation_steps = p * steps;
+    max_shape = d > 1 ? (steps - 1) * pncc + d : d + pncc;     // est:97
+    shape_range = max_shape + 1;
+    print_basic_info = print_info;
+    for (int i = 0; i < 12; i++) tr_order[i] = tr_order_ ? tr_order_[i] : i;
+    A0.assign(A0_, A0_ + d * d); p0.assign(p0_, p0_ + d); b0.assign(b0_, b0_ + d);
+    root_point.assign(root_point_, root_point_ + d);
+    b_pert.assign(MAXM, 0.0);
+    for (int i = 0; i < max_shape && i < MAXM; i++) b_pert[i] = b_pert_[i];
+    mean.assign(d, make_cplx(0, 0)); var.assign(d * d, make_cplx(0, 0)); last_mean = mean; last_var = var;
+    fz = last_fz = make_cplx(0, 0);
+    terms_per_shape.assign(shape_range, 0); muc_per_shape.assign(shape_range, 0);
+    terms_per_shape[d] = 1;
+    DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G,
+                         &gen[1].g_m, &gen[1].cells, &gen[1].alive, &gen[1].A, &gen[1].p, &gen[1].b, &gen[1].keys, &gen[1].G,
+                         &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
+                         &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
+                         &scratchI0, &scratchI1, &scratchI2, &scratchI3, &scratchK0, &scratchK1, &ftrF, &ftrWide, &grpOrder, &grpStart,
+                         &aliveFlag, &diagBuf, &unkBuf, &initBuf};
+    for (auto* b : all) b->be = &be;
+    gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0);
+  }
+  ~Engine() {}
+
+  static bool supported(int d, int max_shape, int pncc, std::string* why) {
+    if (d < 2 || d > MAXD) { *why = "state dimension must be in [2, 8]"; return false; }
+    if (max_shape > MAXM - 1) { *why = "max hyperplane count exceeds 31 (reference cap, est:231-235)"; return false; }
+    if (pncc > MAXPN) { *why = "pncc > 4 not supported"; return false; }
+    return true;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  void fill_gen_layout(GenStore& g, const std::vector<int>& groups_per_shape) {
+    GenView& v = g.v;
+    long long gA = 0, gp = 0, gt = 0; int gid = 0;
+    for (int m = 0; m < NSHAPE; m++) {
+      v.gid_begin[m] = gid; v.A_base[m] = gA; v.p_base[m] = gp; v.tab_base[m] = gt;
+      const int n = m < (int)groups_per_shape.size() ? groups_per_shape[m] : 0;
+      const int stride = m >= 1 ? cell_count_central_half(m, d) : 0;
+      v.tab_stride[m] = stride;
+      gid += n; gA += (long long)n * m * d; gp += (long long)n * m; gt += (long long)n * stride;
+    }
+    v.gid_begin[NSHAPE] = gid; v.n_groups = gid;
+    v.g_m = (unsigned char*)g.g_m.ensure((size_t)gid + 16);
+    v.cells = (int*)g.cells.ensure(sizeof(int) * ((size_t)gid + 4));
+    v.alive = (int*)g.alive.ensure(sizeof(int) * ((size_t)gid + 4));
+    v.A = (double*)g.A.ensure(sizeof(double) * (size_t)(gA + 8));
+    v.p = (double*)g.p.ensure(sizeof(double) * (size_t)(gp + 8));
+    v.b = (double*)g.b.ensure(sizeof(double) * ((size_t)gid * d + 8));
+    v.keys = (unsigned*)g.keys.ensure(sizeof(unsigned) * (size_t)(gt + 8));
+    v.G = (cplx*)g.G.ensure(sizeof(cplx) * (size_t)(gt + 8));
+  }
+
+  StepParams make_params(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
+                         const double* B, const double* u, bool with_tp) {
+    StepParams sp; memset(&sp, 0, sizeof(sp));
+    sp.d = d; sp.with_tp = with_tp; sp.skip_post_mu = skip_post_mu; sp.max_shape = max_shape;
+    for (int i = 0; i < 12; i++) sp.tr_order[i] = tr_order[i];
+    for (int i = 0; i < d; i++) { sp.H[i] = H[i]; sp.root_point[i] = root_point[i]; }
+    for (int i = 0; i < MAXM; i++) sp.b_pert[i] = b_pert[i];
+    sp.msmt = msmt; sp.gamma = gamma; sp.gscale = G_SCALE_FACTOR;
+    if (with_tp) {
+      for (int i = 0; i < d * d; i++) sp.Phi[i] = Phi[i];
+      // precoalign_Gamma_beta, cauchy_util.hpp:128-210 (host: pncc x d values)
+      double tG[MAXPN * MAXD], tb[MAXPN]; int cm = pncc;
+      for (int i = 0; i < cm; i++) { for (int j = 0; j < d; j++) tG[i * d + j] = Gamma[j * cm + i]; tb[i] = beta[i]; }
+      for (int i = 0; i < cm; i++) {
+        double nf = 0; for (int j = 0; j < d; j++) nf += fabs(tG[i * d + j]);
+        for (int j = 0; j < d; j++) tG[i * d + j] /= nf;
+        tb[i] *= nf;
+      }
+      bool F[MAXPN]; for (int i = 0; i < cm; i++) F[i] = true;
+      for (int i = 0; i < cm - 1; i++) if (F[i])
+        for (int j = i + 1; j < cm; j++) if (F[j]) {
+          bool pos, neg; coalign_gates(tG + i * d, tG + j * d, d, &pos, &neg);
+          if (pos || neg) { F[j] = false; tb[i] += tb[j]; }
+        }
+      int n = 0;
+      for (int i = 0; i < cm; i++) if (F[i]) { for (int j = 0; j < d; j++) sp.GammaT[n * d + j] = tG[i * d + j]; sp.beta[n] = tb[i]; n++; }
+      sp.npn = n;
+      if (cmcc > 0 && B && u) {
+        sp.has_bu = 1;
+        for (int i = 0; i < d; i++) { double sum = 0.0; for (int j = 0; j < cmcc; j++) sum += B[i * cmcc + j] * u[j]; sp.bu[i] = sum; }
+      }
+    }
+    return sp;
+  }
+
+  // finalize_cached_moments (est:340-357) on the raw sums; `check` adds moments_numerical_check (est:359-461)
+  void finalize_moments(const double* raw /*2*(1+d+d*d)*/, bool check) {
+    fz = make_cplx(raw[0], raw[1]);
+    for (int i = 0; i < d; i++) mean[i] = make_cplx(raw[2 + 2 * i], raw[3 + 2 * i]);
+    for (int i = 0; i < d * d; i++) var[i] = make_cplx(raw[2 + 2 * d + 2 * i], raw[3 + 2 * d + 2 * i]);
+    G_SCALE_FACTOR = (1.0 / (2.0 * M_PI)) / fz.re;
+    const cplx Ifz = make_cplx(0, fz.re);
+    for (int i = 0; i < d; i++) mean[i] = cdiv(mean[i], Ifz);
+    for (int i = 0; i < d; i++) for (int j = 0; j < d; j++) var[i * d + j] = csub(cdiv(var[i * d + j], fz), cmul(mean[i], mean[j]));
+    fz_mu = fz;
+    if (!check) return;
+    const bool first_msmt = (master_step % p) == 0, not_last = (master_step % p) != (p - 1), last = (master_step % p) == (p - 1);
+    if (first_msmt) {
+      numeric_moment_errors |= (1 << ERROR_MEAN_AT_CURRENT_STEP_DNE) | (1 << ERROR_COVARIANCE_AT_CURRENT_STEP_DNE);
+      numeric_moment_errors &= ~((1 << ERROR_MEAN_UNSTABLE_CURRENT_STEP_FINAL_MSMT) | (1 << ERROR_MEAN_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT) |
+                                 (1 << ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT) | (1 << ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT));
+    }
+    int nw = 0;
+    if (fz.re <= 0) nw |= (1 << ERROR_FZ_NEGATIVE);
+    if (fabs(fz.im / (1e-15 + fz.re)) > 1e-3) nw |= (1 << ERROR_FZ_UNSTABLE);
+    bool mean_okay = true;
+    for (int i = 0; i < d; i++) {
+      double mr = fabs(mean[i].re), mi = fabs(mean[i].im), ratio = mi / (1e-15 + mr);
+      if ((ratio > 1e-1) || (mi > 0.001)) {
+        nw |= (1 << ERROR_MEAN_UNSTABLE_ANY_STEP);
+        if (not_last) nw |= (1 << ERROR_MEAN_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT);
+        if (last) nw |= (1 << ERROR_MEAN_UNSTABLE_CURRENT_STEP_FINAL_MSMT);
+        mean_okay = false;
+      }
+    }
+    bool cov_okay = true;
+    if (covariance_checker(var.data(), d)) {
+      nw |= (1 << ERROR_COVARIANCE_UNSTABLE_ANY_STEP);
+      if (not_last) nw |= (1 << ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_NOT_FINAL_MSMT);
+      if (last) nw |= (1 << ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT);
+      cov_okay = false;
+    }
+    numeric_moment_errors |= nw;
+    if (mean_okay) numeric_moment_errors &= ~(1 << ERROR_MEAN_AT_CURRENT_STEP_DNE);
+    if (cov_okay) numeric_moment_errors &= ~(1 << ERROR_COVARIANCE_AT_CURRENT_STEP_DNE);
+    if (mean_okay) last_mean = mean; else mean = last_mean;
+    if (cov_okay) last_var = var; else var = last_var;
+    if (!mean_okay && !cov_okay) fz = last_fz; else last_fz = fz;
+    fz_mu = fz;
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int step(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
+           const double* B, const double* u) {
+    if (numeric_moment_errors & (1 << ERROR_FZ_NEGATIVE)) return numeric_moment_errors;     // est:1214-1219
+    if (master_step == num_estimation_steps || finished) { error = "master_step == num_estimation_steps: reset() the estimator first (est:1220-1225)"; return -4; }
+    skip_post_mu = (master_step == num_estimation_steps - 1);                               // SKIP_LAST_STEP, est:1229
+    stats = StepStats();
+    double t0 = be.tic();
+    int rc = (master_step == 0) ? step_first(msmt, H, gamma) : step_general(msmt, Phi, Gamma, beta, H, gamma, B, u);
+    if (rc < 0) return rc;
+    stats.ms_total = be.toc(t0);
+    stats.launches = be.launch_count; be.launch_count = 0;
+    master_step++;
+    return numeric_moment_errors;
+  }
+
+  int step_first(double msmt, const double* H, double gamma) {
+    StepParams sp = make_params(msmt, nullptr, nullptr, nullptr, H, gamma, nullptr, nullptr, false);
+    GenStore& ng = gen[cur];
+    std::vector<int> groups(NSHAPE, 0); groups[d] = d + 1;
+    fill_gen_layout(ng, groups);
+    double* init = (double*)initBuf.ensure(sizeof(double) * (d * d + 2 * d));
+    be.h2d(init, A0.data(), sizeof(double) * d * d);
+    be.h2d(init + d * d, p0.data(), sizeof(double) * d);
+    be.h2d(init + d * d + d, b0.data(), sizeof(double) * d);
+    const int nq = 1 + d + d * d;
+    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    int* cnt = (int*)unkBuf.ensure(64);
+    KFirstStep k{sp, init, init + d * d, init + d * d + d, ng.v, mom, cnt};
+    size_t smem = sizeof(double) * ((d + 1) * (2 + 2 * d) + 4) + sizeof(int) * (d + 4);
+    be.launch(k, 1, 32, smem);
+    std::vector<double> raw(2 * nq); int nt = 0;
+    be.d2h(raw.data(), mom, sizeof(double) * 2 * nq); be.d2h(&nt, cnt, sizeof(int));
+    finalize_moments(raw.data(), false);        // compute_moments(true): no numerical check on the first step (quirk A.9 iv)
+    ng.v.n_alive = nt;
+    std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0); ng.alive_per_shape[d] = nt;
+    Nt = nt; Nt_muc = nt;
+    std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = nt; muc_per_shape = terms_per_shape;
+    if (!print_basic_info) fz = make_cplx(1, 0);       // est:1198-1204
+    last_mean = mean; last_var = var; last_fz = fz;
+    stats.parents = 1; stats.slots = d + 1; stats.terms_after_muc = nt; stats.groups = nt; stats.survivors = nt;
+    return 0;
+  }
+
+  int step_general(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
+                   const double* B, const double* u) {
+    const bool with_tp = (master_step % p) == 0;
+    StepParams sp = make_params(msmt, Phi, Gamma, beta, H, gamma, B, u, with_tp);
+    GenStore& pg = gen[cur]; GenStore& ng = gen[1 - cur];
+    const int n_alive = pg.v.n_alive;
+    const int nq = 1 + d + d * d;
+    stats.parents = n_alive;
+    int* diag = (int*)diagBuf.ensure(64); be.memset(diag, 0, 64);
+    double tph = be.tic();
+
+    // ---- K1/K2: time propagation, Gamma coalignment, B^{k|k-1} ----
+    ParentWs ws; memset(&ws, 0, sizeof(ws));
+    ws.sgnmask = (unsigned*)wsSgn.ensure(sizeof(unsigned) * (n_alive + 4));
+    ws.bxor = (unsigned*)wsXor.ensure(sizeof(unsigned) * (n_alive + 4));
+    const int Hcap = cell_count_central_half(max_shape, d);
+    if (with_tp) {
+      ws.A = (double*)wsA.ensure(sizeof(double) * (size_t)n_alive * max_shape * d);
+      ws.p = (double*)wsp.ensure(sizeof(double) * (size_t)n_alive * max_shape);
+      ws.b = (double*)wsb.ensure(sizeof(double) * (size_t)n_alive * d);
+      ws.m_tp = (unsigned char*)wsm.ensure((size_t)n_alive + 16);
+      be.launch(KTimeProp{sp, pg.v, ws}, (n_alive + 127) / 128, 128, 0);
+      if (!skip_post_mu) {
+        ws.tpB_stride = Hcap;
+        ws.tpB = (unsigned*)wsTpB.ensure(sizeof(unsigned) * (size_t)n_alive * Hcap);
+        ws.tpB_cells = (int*)wsTpBc.ensure(sizeof(int) * (n_alive + 4));
+        int max_mtp = 0;
+        for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) max_mtp = m + sp.npn;
+        if (max_mtp > max_shape) max_mtp = max_shape;
+        const int cgen = cell_count_general(max_mtp, d);
+        const int acc_cap = next_pow2(cgen + 1), vis_cap = next_pow2(DCE_STORAGE_MULT * cgen);
+        const int nth = 128;
+        be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag}, n_alive, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
+      }
+    }
+    stats.ms_tp = be.toc(tph); tph = be.tic();
+
+    // ---- K3/K4: measurement update, moment contributions, MU coalignment ----
+    SlotView sl; memset(&sl, 0, sizeof(sl));
+    long long nslots = 0, offA = 0, offpq = 0; int rank = 0;
+    for (int m = 0; m < NSHAPE; m++) {
+      sl.par_begin[m] = rank; sl.slot_begin[m] = nslots; sl.A_off[m] = offA; sl.pq_off[m] = offpq;
+      const int n = pg.alive_per_shape[m];
+      int MT = m + (with_tp ? sp.npn : 0);
+      if (MT > max_shape) MT = max_shape;
+      sl.MT[m] = MT;
+      rank += n; nslots += (long long)n * (MT + 1); offA += (long long)n * (MT + 1) * MT * d; offpq += (long long)n * (MT + 1) * MT;
+    }
+    sl.par_begin[NSHAPE] = rank; sl.slot_begin[NSHAPE] = nslots; sl.n_slots = nslots;
+    stats.slots = nslots;
+    sl.meta = (SlotMeta*)slmeta.ensure(sizeof(SlotMeta) * (size_t)(nslots + 1));
+    sl.g = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(nslots + 8));
+    sl.y = (double*)sly.ensure(sizeof(double) * (size_t)(nslots + 1) * 2 * d);
+    sl.cmap = (unsigned char*)slcmap.ensure(skip_post_mu ? 64 : (size_t)(nslots + 1) * MAXM);
+    if (!skip_post_mu) {
+      sl.A = (double*)slA.ensure(sizeof(double) * (size_t)(offA + 8));
+      sl.p = (double*)slp.ensure(sizeof(double) * (size_t)(offpq + 8));
+      sl.q = (double*)slq.ensure(sizeof(double) * (size_t)(offpq + 8));
+      sl.b = (double*)slb.ensure(sizeof(double) * (size_t)(nslots + 1) * d);
+    }
+    for (int m = 1; m < NSHAPE; m++) {
+      const long long n = (long long)pg.alive_per_shape[m] * (sl.MT[m] + 1);
+      if (n > 0) be.launch(KMsmtUpdate{sp, pg.v, ws, sl, m}, (int)((n + 127) / 128), 128, 0);
+    }
+    stats.ms_mu = be.toc(tph); tph = be.tic();
+
+    // ---- moments (K3 tail): serial-order fz, two-level mean/covariance sums ----
+    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    if (fast_moments) {
+      const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
+      double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
+      be.launch(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 32, 0);     // d = 0: only fz, in serial order
+      be.launch(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
+      be.launch(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
+    } else {
+      be.launch(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, 1, ((2 * nq + 31) / 32) * 32, 0);
+    }
+
+    // ---- canonical ranks of the new terms inside their new shapes ----
+    const int nchunks = (int)((nslots + RANK_CHUNK - 1) / RANK_CHUNK);
+    int* counts = (int*)rankCounts.ensure(sizeof(int) * (size_t)nchunks * 2 * NSHAPE + 64);
+    int* totals = (int*)rankTotals.ensure(sizeof(int) * 2 * NSHAPE + 64);
+    be.launch(KRankCount{sl, nchunks, counts}, nchunks, RANK_CHUNK, sizeof(int) * 2 * NSHAPE);
+    be.launch(KRankScan{nchunks, counts, totals}, 2 * NSHAPE, 32, 0);
+    std::vector<double> raw(2 * nq); std::vector<int> tot(2 * NSHAPE);
+    be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
+    be.d2h(tot.data(), totals, sizeof(int) * 2 * NSHAPE);
+    finalize_moments(raw.data(), true);
+    sp.gscale = G_SCALE_FACTOR;
+    stats.ms_moments = be.toc(tph); tph = be.tic();
+
+    TermView tv; memset(&tv, 0, sizeof(tv));
+    long long nterms = 0, tA = 0, tpq = 0;
+    std::fill(muc_per_shape.begin(), muc_per_shape.end(), 0);
+    for (int m = 0; m < NSHAPE; m++) {
+      tv.n_old[m] = tot[m]; tv.n[m] = tot[m] + tot[NSHAPE + m];
+      tv.t_begin[m] = nterms; tv.A_base[m] = tA; tv.pq_base[m] = tpq;
+      nterms += tv.n[m]; tA += (long long)tv.n[m] * m * d; tpq += (long long)tv.n[m] * m;
+      if (m < shape_range) muc_per_shape[m] = tv.n[m];
+    }
+    tv.t_begin[NSHAPE] = nterms;
+    Nt_muc = (int)nterms; stats.terms_after_muc = nterms;
+    if (skip_post_mu) {          // est:732-733, 806-828: only the counts change on the window's last step
+      terms_per_shape = muc_per_shape; Nt = (int)nterms; finished = true;
+      return 0;
+    }
+
+    tv.A = (double*)tvA.ensure(sizeof(double) * (size_t)(tA + 8));
+    tv.p = (double*)tvp.ensure(sizeof(double) * (size_t)(tpq + 8));
+    tv.q = (double*)tvq.ensure(sizeof(double) * (size_t)(tpq + 8));
+    tv.b = (double*)tvb.ensure(sizeof(double) * (size_t)(nterms + 1) * d);
+    tv.meta = (SlotMeta*)tvmeta.ensure(sizeof(SlotMeta) * (size_t)(nterms + 1));
+    tv.cmap = (unsigned char*)tvcmap.ensure((size_t)(nterms + 1) * MAXM);
+    long long* sot = (long long*)slotOfTerm.ensure(sizeof(long long) * (size_t)(nterms + 1));
+    be.launch(KRegroup{sp, sl, tv, nchunks, counts, sot}, nchunks, RANK_CHUNK, sizeof(int) * RANK_CHUNK);
+    stats.ms_regroup = be.toc(tph); tph = be.tic();
+
+    // ---- K5/K6: fast term reduction per new shape, reduction groups ----
+    int* F_all = (int*)ftrF.ensure(sizeof(int) * (size_t)(nterms + 4));
+    unsigned char* wide_all = (unsigned char*)ftrWide.ensure((size_t)nterms + 16);
+    int* order_all = (int*)grpOrder.ensure(sizeof(int) * (size_t)(nterms + 4));
+    int* gstart_all = (int*)grpStart.ensure(sizeof(int) * (size_t)(nterms + NSHAPE + 4));
+    int max_n = 0;
+    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > max_n) max_n = tv.n[m];
+    unsigned long long* k0 = (unsigned long long*)scratchK0.ensure(sizeof(unsigned long long) * (size_t)(max_n + 4));
+    unsigned long long* k1 = (unsigned long long*)scratchK1.ensure(sizeof(unsigned long long) * (size_t)(max_n + 4));
+    int* i0 = (int*)scratchI0.ensure(sizeof(int) * (size_t)(max_n + 4));
+    int* i1 = (int*)scratchI1.ensure(sizeof(int) * (size_t)(max_n + 4));
+    int* i2 = (int*)scratchI2.ensure(sizeof(int) * (size_t)(max_n + 4));
+    int* i3 = (int*)scratchI3.ensure(sizeof(int) * (size_t)(max_n + 4));
+    int* unk = (int*)unkBuf.ensure(64);
+    std::vector<int> n_groups(NSHAPE, 0), n_phase1(NSHAPE, 0), gstart_off(NSHAPE, 0);
+    int goff = 0;
+    if (capture) cap.clear();
+    for (int m = 1; m < NSHAPE; m++) {
+      const int n = tv.n[m];
+      if (n == 0) continue;
+      int* F = F_all + tv.t_begin[m]; unsigned char* wide = wide_all + tv.t_begin[m];
+      int* order = order_all + tv.t_begin[m]; int* gstart = gstart_all + goff;
+      gstart_off[m] = goff;
+      const int nb = (n + 127) / 128;
+      be.launch(KFtrKeys{tv, m, d, tr_order[0], k0, i0, F}, nb, 128, 0);
+      be.sort_pairs(k0, k1, i0, i1, n);                     // k1 = sorted keys, i1 = term index at each sorted position
+      be.launch(KFtrWide{tv, m, d, tr_order[0], k1, wide}, nb, 128, 0);
+      int rounds = 0;
+      for (;;) {
+        be.memset(unk, 0, sizeof(int));
+        be.launch(KFtrRound{tv, sp, m, k1, i1, wide, F, unk}, nb, 128, 0);
+        int nu = 0; be.d2h(&nu, unk, sizeof(int));
+        rounds++;
+        if (nu == 0) break;
+        if (rounds > n + 2) { error = "FTR resolution did not converge"; return -3; }
+      }
+      if (rounds > stats.ftr_rounds_max) stats.ftr_rounds_max = rounds;
+      be.launch(KRootKeys{n, F, k0, i0}, nb, 128, 0);
+      be.sort_pairs(k0, k1, i0, order, n);
+      be.launch(KGroupHeads{n, F, order, i2}, nb, 128, 0);
+      be.exclusive_scan(i2, i3, n);
+      int last_rank = 0, last_head = 0;
+      be.d2h(&last_rank, i3 + (n - 1), sizeof(int)); be.d2h(&last_head, i2 + (n - 1), sizeof(int));
+      const int ng_m = last_rank + last_head;
+      n_groups[m] = ng_m;
+      be.launch(KGroupFill{n, i2, i3, gstart, ng_m}, nb, 128, 0);
+      // groups whose root is an old term come first (roots ascend): their count = rank of the first head at order position >= ... root >= n_old
+      // roots are sorted ascending, so count roots < n_old: F[j]==j for j < n_old  <=> heads among the first positions; use the scan of heads over F order
+      {
+        // number of roots with index < n_old = number of j < n_old with F[j] == j; computed from a scan over term order
+        be.launch(KRootFlags{tv.n_old[m], F, i2}, (tv.n_old[m] + 127) / 128 + 1, 128, 0);
+        int np1 = 0;
+        if (tv.n_old[m] > 0) {
+          be.exclusive_scan(i2, i3, tv.n_old[m]);
+          int a = 0, b2 = 0; be.d2h(&a, i3 + (tv.n_old[m] - 1), sizeof(int)); be.d2h(&b2, i2 + (tv.n_old[m] - 1), sizeof(int));
+          np1 = a + b2;
+        }
+        n_phase1[m] = np1;
+      }
+      goff += ng_m + 1;
+      if (capture) capture_shape(tv, m, F, ws, with_tp);
+    }
+    stats.ms_ftr = be.toc(tph); tph = be.tic();
+
+    // ---- K7/K8: child B-tables and G-tables, one CTA per reduction group ----
+    fill_gen_layout(ng, n_groups);
+    unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
+    const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
+    const size_t gsm = KGTable::smem_bytes(HC2);
+    long long total_groups = 0;
+    for (int phase = 0; phase < 2; phase++)
+      for (int m = 1; m < NSHAPE; m++) {
+        if (n_groups[m] == 0) continue;
+        const int g0 = phase == 0 ? 0 : n_phase1[m], g1 = phase == 0 ? n_phase1[m] : n_groups[m];
+        if (g1 <= g0) continue;
+        total_groups += g1 - g0;
+        const int Hm = cell_count_central_half(m, d);
+        int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
+        KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
+        be.launch(k, g1 - g0, nth, gsm);
+      }
+    stats.groups = total_groups;
+    stats.ms_gtable = be.toc(tph); tph = be.tic();
+
+    // ---- K9: survivor list of the new generation, parent/child generation swap (util:895) ----
+    const int ngr = ng.v.n_groups;
+    int n_surv = 0;
+    std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0);
+    if (ngr > 0) {
+      int* fi = (int*)scratchI0.ensure(sizeof(int) * (size_t)(ngr + 4));
+      int* fr = (int*)scratchI1.ensure(sizeof(int) * (size_t)(ngr + 4));
+      be.launch(KFlagsToInt{ngr, aflag, fi}, (ngr + 127) / 128, 128, 0);
+      be.exclusive_scan(fi, fr, ngr);
+      be.launch(KAliveCompact{ngr, aflag, fr, ng.v.alive}, (ngr + 127) / 128, 128, 0);
+      std::vector<int> bounds(NSHAPE + 1, 0);
+      for (int m = 1; m <= NSHAPE; m++) {
+        const int g = ng.v.gid_begin[m];
+        if (g >= ngr) { int a = 0, b2 = 0; be.d2h(&a, fr + (ngr - 1), sizeof(int)); be.d2h(&b2, fi + (ngr - 1), sizeof(int)); bounds[m] = a + b2; }
+        else be.d2h(&bounds[m], fr + g, sizeof(int));
+      }
+      for (int m = 1; m < NSHAPE; m++) ng.alive_per_shape[m] = bounds[m + 1] - bounds[m];
+      n_surv = bounds[NSHAPE];
+    }
+    ng.v.n_alive = n_surv;
+    int hd[16]; be.d2h(hd, diag, sizeof(int) * 4);
+    stats.diag_alias = hd[0]; stats.diag_hash = hd[1];
+    stats.survivors = n_surv;
+    std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0);
+    for (int m = 1; m < shape_range; m++) terms_per_shape[m] = ng.alive_per_shape[m];
+    Nt = n_surv;
+    cur = 1 - cur;
+    if (!print_basic_info) fz = make_cplx(1, 0);           // est:1172-1176
+    stats.ms_compact = be.toc(tph);
+    // algorithmic bytes: parents (term + G/B tables), post-MUC payload written + read, survivors written
+    {
+      long long bytes = 0, bg = 0;
+      for (int m = 1; m < NSHAPE; m++) {
+        const long long H = cell_count_central_half(m, d);
+        bytes += (long long)pg.alive_per_shape[m] * (8LL * (m * d + m + d) + 28LL * H);
+        bytes += 2LL * tv.n[m] * (8LL * (m * d + 2 * m + d) + 2 * m);
+        bytes += (long long)ng.alive_per_shape[m] * (28LL * H + 8LL * (m * d + m + d));
+        bg += (long long)pg.alive_per_shape[m] * 28LL * H + (long long)tv.n[m] * (8LL * (m * d + 2 * m + d) + 2 * m) +
+              (long long)ng.alive_per_shape[m] * (28LL * H + 8LL * (m * d + m + d));
+      }
+      stats.bytes_step = bytes; stats.bytes_gtable = bg;
+    }
+    return 0;
+  }
+
+  struct KRootFlags {       // flags[j] = (F[j] == j) for j < n
+    int n; const int* F; int* flags;
+    template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+      c.par([&](int tid) { const int j = c.block() * c.nthreads() + tid; if (j < n) flags[j] = (F[j] == j) ? 1 : 0; });
+    }
+  };
+
+  void capture_shape(const TermView& tv, int m, const int* F, const ParentWs& ws, bool with_tp) {
+    CapShape cs; cs.m = m; cs.n = tv.n[m];
+    const int n = cs.n;
+    cs.A.resize((size_t)n * m * d); cs.p.resize((size_t)n * m); cs.q.resize((size_t)n * m); cs.b.resize((size_t)n * d); cs.cd.resize((size_t)n * 2);
+    cs.meta.resize((size_t)n * 8); cs.F.resize(n); cs.cmap.resize((size_t)n * MAXM); cs.csmap.resize((size_t)n * MAXM);
+    std::vector<SlotMeta> me(n);
+    be.d2h(cs.A.data(), term_A(tv, m, 0, d), sizeof(double) * cs.A.size());
+    be.d2h(cs.p.data(), term_p(tv, m, 0), sizeof(double) * cs.p.size());
+    be.d2h(cs.q.data(), term_q(tv, m, 0), sizeof(double) * cs.q.size());
+    be.d2h(cs.b.data(), term_b(tv, m, 0, d), sizeof(double) * cs.b.size());
+    be.d2h(me.data(), tv.meta + tv.t_begin[m], sizeof(SlotMeta) * n);
+    be.d2h(cs.cmap.data(), tv.cmap + tv.t_begin[m] * MAXM, (size_t)n * MAXM);
+    be.d2h(cs.F.data(), F, sizeof(int) * n);
+    GenStore& pg = gen[cur];
+    std::vector<int> alive(pg.v.n_alive), cells(pg.v.n_groups); std::vector<unsigned char> gm(pg.v.n_groups);
+    be.d2h(alive.data(), pg.v.alive, sizeof(int) * alive.size());
+    be.d2h(cells.data(), pg.v.cells, sizeof(int) * cells.size());
+    be.d2h(gm.data(), pg.v.g_m, gm.size());
+    std::vector<int> tpc(pg.v.n_alive, 0);
+    if (with_tp) be.d2h(tpc.data(), ws.tpB_cells, sizeof(int) * tpc.size());
+    for (int i = 0; i < n; i++) {
+      const SlotMeta& s = me[i];
+      cs.cd[2 * i] = s.c_val; cs.cd[2 * i + 1] = s.d_val;
+      int* o = &cs.meta[(size_t)i * 8];
+      o[0] = gm[alive[s.parent]]; o[1] = s.pbc; o[2] = s.z; o[3] = (int)s.enc_lhp; o[4] = (int)s.hflag; o[5] = s.flags & 1; o[6] = with_tp ? tpc[s.parent] : cells[alive[s.parent]]; o[7] = (s.flags >> 1) & 1;
+      for (int l = 0; l < MAXM; l++) {
+        const bool has = ((s.flags >> 1) & 1) && l < s.pbc;
+        cs.csmap[(size_t)i * MAXM + l] = has ? (((s.csneg >> l) & 1u) ? -1 : 1) : 0;
+        if (!has) cs.cmap[(size_t)i * MAXM + l] = 255;
+      }
+    }
+    cap.push_back(std::move(cs));
+  }
+
+  // ------------------------------------------------------------------------------------------
+  int shift_b(const double* delta, double sign) {
+    if (skip_post_mu) return 0;                 // est:1314, 1365
+    GenStore& g = gen[cur];
+    if (g.v.n_alive == 0) return 0;
+    KShiftB k; k.gen = g.v; k.d = d; k.sign = sign;
+    for (int i = 0; i < d; i++) k.delta[i] = delta[i];
+    be.launch(k, (g.v.n_alive + 127) / 128, 128, 0);
+    return 0;
+  }
+  int det_time_prop(const double* T, const double* B, const double* u) {
+    GenStore& g = gen[cur];
+    if (g.v.n_alive == 0 || master_step == 0) return 0;
+    KDetTimeProp k; memset(&k, 0, sizeof(k)); k.gen = g.v; k.d = d;
+    for (int i = 0; i < d * d; i++) k.T[i] = T[i];
+    if (B && u && cmcc > 0) { k.has_bu = 1; for (int i = 0; i < d; i++) { double s = 0.0; for (int j = 0; j < cmcc; j++) s += B[i * cmcc + j] * u[j]; k.bu[i] = s; } }
+    be.launch(k, (g.v.n_alive + 127) / 128, 128, 0);
+    return 0;
+  }
+  void reset() {                                 // est:1247-1300
+    master_step = 0; Nt = 1; numeric_moment_errors = 0; finished = false; skip_post_mu = 0;
+    std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = 1;
+    gen[0].v.n_alive = 0; gen[1].v.n_alive = 0;
+  }
+
+  // Host copy of the parents of shape m (canonical order).
+  int export_shape(int m, int* n_terms, long long* n_cells_total, double* A, double* pp, double* b, int* cells, uint32_t* keys, double* G) {
+    GenStore& g = gen[cur];
+    if (m < 1 || m >= NSHAPE || master_step == 0) { *n_terms = 0; *n_cells_total = 0; return 0; }
+    const int n = g.alive_per_shape[m];
+    *n_terms = n;
+    if (n == 0) { *n_cells_total = 0; return 0; }
+    int rank0 = 0; for (int k = 1; k < m; k++) rank0 += g.alive_per_shape[k];
+    std::vector<int> alive(n), hc(n);
+    be.d2h(alive.data(), g.v.alive + rank0, sizeof(int) * n);
+    long long tot = 0;
+    for (int i = 0; i < n; i++) { be.d2h(&hc[i], g.v.cells + alive[i], sizeof(int)); tot += hc[i]; }
+    *n_cells_total = tot;
+    if (!A) return 0;
+    long long o = 0;
+    for (int i = 0; i < n; i++) {
+      const int gid = alive[i];
+      be.d2h(A + (size_t)i * m * d, gen_A(g.v, gid, m, d), sizeof(double) * m * d);
+      be.d2h(pp + (size_t)i * m, gen_p(g.v, gid, m), sizeof(double) * m);
+      be.d2h(b + (size_t)i * d, gen_b(g.v, gid, d), sizeof(double) * d);
+      cells[i] = hc[i];
+      be.d2h(keys + o, gen_keys(g.v, gid, m), sizeof(unsigned) * hc[i]);
+      be.d2h(G + 2 * o, gen_G(g.v, gid, m), sizeof(cplx) * hc[i]);
+      o += hc[i];
+    }
+    return 0;
+  }
+};
+
+}  // namespace mce
+#endif

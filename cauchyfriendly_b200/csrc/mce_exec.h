@@ -1,0 +1,51 @@
+// mce_exec.h -- execution contexts for the MCE kernels.
+//
+// Every kernel body in mce_kernels.h is written against a small "Ctx" interface in bulk-synchronous
+// style: block-uniform control flow outside `ctx.par(...)`, per-thread work inside it, one barrier at the
+// end of every `par`.  DevCtx (below) is the CUDA implementation: par(f) runs f(threadIdx.x) followed by
+// __syncthreads().  tests/emu/emu_backend.h provides a sequential implementation of the same interface
+// that exists only to unit-test kernel logic on machines without a GPU; it is never part of libmce_b200.so.
+#ifndef MCE_EXEC_H_
+#define MCE_EXEC_H_
+
+#include "mce_math.h"
+
+namespace mce {
+
+#if defined(__CUDACC__)
+struct DevCtx {
+  unsigned char* smem_;
+  __device__ __forceinline__ int block() const { return (int)blockIdx.x; }
+  __device__ __forceinline__ int nblocks() const { return (int)gridDim.x; }
+  __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
+  __device__ __forceinline__ unsigned char* smem() const { return smem_; }
+  template <class F>
+  __device__ __forceinline__ void par(F&& f) {
+    f((int)threadIdx.x);
+    __syncthreads();
+  }
+  // Reads a block-uniform value from shared memory for use in control flow; the trailing barrier keeps a
+  // fast thread from overwriting it (in a later phase) before a slow thread has read it.
+  template <class T>
+  __device__ __forceinline__ T uniform(const T& v) {
+    T r = v;
+    __syncthreads();
+    return r;
+  }
+  __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
+  __device__ __forceinline__ unsigned atomic_xor(unsigned* p, unsigned v) { return atomicXor(p, v); }
+  __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
+  __device__ __forceinline__ unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
+  __device__ __forceinline__ int load_relaxed(const int* p) { return *(const volatile int*)p; }
+};
+#endif
+
+// Kernel functors expose: template <class Ctx> void run(Ctx&) const.
+#if defined(__CUDACC__)
+#define MCE_KERNEL_FN __device__
+#else
+#define MCE_KERNEL_FN
+#endif
+
+}  // namespace mce
+#endif

@@ -1,0 +1,152 @@
+// mce_kern_ftr.h -- kernels K5/K6: fast term reduction (global deduplication) and reduction groups.
+// Reference loops replaced: term_reduction.hpp:30-80 (per-axis ordered maps), 89-276 (fast_term_reduction),
+// cauchy_util.hpp:349-408 (ForwardFlagArray).
+//
+// The reference elects roots greedily in index order: i ascending, every still-unreduced j > i inside
+// i's epsilon-box that passes the p / A checks gets F[j] = i.  Equivalently: j's root is the smallest
+// matching i < j that is itself a root; j is a root when there is none.  That is a "lexicographically
+// first" fixed point, evaluated here by rounds: a term is decided once every matching lower-index term
+// below its would-be root is decided.  Results are identical to the serial loop (parity: bit-exact F).
+#ifndef MCE_KERN_FTR_H_
+#define MCE_KERN_FTR_H_
+
+#include "mce_exec.h"
+#include "mce_types.h"
+
+namespace mce {
+
+// Order-preserving image of an fp64 value (sort key for the primary search axis).
+MCE_HD unsigned long long f64_sort_key(double x) {
+  union { double d; unsigned long long u; } v; v.d = x;
+  return (v.u & 0x8000000000000000ull) ? ~v.u : (v.u | 0x8000000000000000ull);
+}
+
+// match(i -> j): would root i absorb term j?  (term_reduction.hpp:108-157 window semantics: on every axis
+// fl(b_i - eps) < b_j <= fl(b_i + eps); then |p_j - p_i|_inf <= eps (tr:223-236) and the A check exactly
+// as written in tr:238-263, which compares the first m scalars of A, d times each -- quirk A.9(i).)
+MCE_HD bool ftr_match(const double* bi, const double* bj, const double* pi, const double* pj, const double* Ai, const double* Aj,
+                      int m, int d, const int* order) {
+  const double ep = REDUCTION_EPS;
+  for (int a = 0; a < d; a++) {
+    const int ax = order[a];
+    const double lo = bi[ax] - ep, hi = bi[ax] + ep, v = bj[ax];
+    if (!(lo < v && v <= hi)) return false;
+  }
+  for (int k = 0; k < m; k++) if (fabs(pj[k] - pi[k]) > ep) return false;
+  for (int k = 0; k < m; k++) {
+    const double ar = Ai[k], ac = Aj[k];
+    const bool pos = fabs(ar - ac) < ep, neg = fabs(ar + ac) < ep;
+    if (!(pos || neg)) return false;
+  }
+  return true;
+}
+
+// sort keys of the primary axis for one shape
+struct KFtrKeys {
+  TermView tv; int m, d, axis0; unsigned long long* keys; int* idx; int* F;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int i = c.block() * c.nthreads() + tid;
+      if (i >= tv.n[m]) return;
+      keys[i] = f64_sort_key(term_b(tv, m, i, d)[axis0]);
+      idx[i] = i; F[i] = -1;
+    });
+  }
+};
+
+// wide[i]: the root's own axis-0 window holds at least two points (the `(gti - lti) > 2` gate, tr:121)
+struct KFtrWide {
+  TermView tv; int m, d, axis0; const unsigned long long* skeys; unsigned char* wide;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int i = c.block() * c.nthreads() + tid;
+      const int n = tv.n[m];
+      if (i >= n) return;
+      const double qp = term_b(tv, m, i, d)[axis0];
+      const unsigned long long klo = f64_sort_key(qp - REDUCTION_EPS), khi = f64_sort_key(qp + REDUCTION_EPS);
+      // lti = last index with value <= lo ; gti = first index with value > hi   (tr:89-106)
+      int lo = 0, hi = n;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= klo) lo = mid + 1; else hi = mid; }
+      const int lti = lo - 1;
+      lo = 0; hi = n;
+      while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= khi) lo = mid + 1; else hi = mid; }
+      const int gti = lo;
+      wide[i] = (gti - lti) > 2;
+    });
+  }
+};
+
+// One resolution round; `n_unknown` counts terms still undecided after the round.
+struct KFtrRound {
+  TermView tv; StepParams sp; int m; const unsigned long long* skeys; const int* sidx; const unsigned char* wide; int* F; int* n_unknown;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int pos = c.block() * c.nthreads() + tid;
+      const int n = tv.n[m], d = sp.d;
+      if (pos >= n) return;
+      const int j = sidx[pos];
+      if (c.load_relaxed(F + j) != -1) return;
+      const double* bj = term_b(tv, m, j, d); const double* pj = term_p(tv, m, j); const double* Aj = term_A(tv, m, j, d);
+      const int ax0 = sp.tr_order[0];
+      // conservative scan bounds around b_j on the primary axis; ftr_match applies the exact interval test
+      const double slack = 4.0 * REDUCTION_EPS + 8.0 * fabs(bj[ax0]) * 2.3e-16;
+      const unsigned long long klo = f64_sort_key(bj[ax0] - slack), khi = f64_sort_key(bj[ax0] + slack);
+      int min_root = 0x7fffffff, min_unknown = 0x7fffffff;
+      for (int dir = 0; dir < 2; dir++) {
+        int q = dir ? pos + 1 : pos - 1;
+        while (q >= 0 && q < n) {
+          const unsigned long long kq = skeys[q];
+          if (dir ? (kq > khi) : (kq < klo)) break;
+          const int i = sidx[q];
+          if (i < j && i < min_root && wide[i]) {
+            const int Fi = c.load_relaxed(F + i);
+            if ((Fi == i || Fi == -1) && ftr_match(term_b(tv, m, i, d), bj, term_p(tv, m, i), pj, term_A(tv, m, i, d), Aj, m, d, sp.tr_order)) {
+              if (Fi == i) { if (i < min_root) min_root = i; }
+              else if (i < min_unknown) min_unknown = i;
+            }
+          }
+          q += dir ? 1 : -1;
+        }
+      }
+      if (min_unknown < min_root) { c.atomic_add(n_unknown, 1); return; }   // an undecided lower term could still claim j
+      F[j] = (min_root != 0x7fffffff) ? min_root : j;
+    });
+  }
+};
+
+// After sorting term indices by (F, index): group heads and sizes. order[] holds term indices sorted by root.
+struct KGroupHeads {
+  int n; const int* F; const int* order; int* is_head;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int k = c.block() * c.nthreads() + tid;
+      if (k >= n) return;
+      is_head[k] = (F[order[k]] == order[k]) ? 1 : 0;
+    });
+  }
+};
+struct KGroupFill {     // head_rank = exclusive scan of is_head; grp_start[rank] = position of the head in order[]
+  int n; const int* is_head; const int* head_rank; int* grp_start; int n_groups;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int k = c.block() * c.nthreads() + tid;
+      if (k >= n) return;
+      if (is_head[k]) grp_start[head_rank[k]] = k;
+      if (k == 0) grp_start[n_groups] = n;
+    });
+  }
+};
+struct KRootKeys {      // sort key for grouping: (root index << 32) | term index
+  int n; const int* F; unsigned long long* keys; int* vals;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int j = c.block() * c.nthreads() + tid;
+      if (j >= n) return;
+      keys[j] = ((unsigned long long)(unsigned)F[j] << 32) | (unsigned)j;
+      vals[j] = j;
+    });
+  }
+};
+
+}  // namespace mce
+#endif

@@ -1,0 +1,567 @@
+// mce_kern_prop.h -- kernels K1/K3/K4 (+K10, step_first): time propagation, measurement update,
+// moment contributions, MU coalignment and the regroup-by-shape of the child terms.
+// Reference loops replaced: cauchy_term.hpp:84-310 (msmt_update), 312-401 (eval_g_yei), 435-531
+// (time_prop, tp_coalign), 458-472 (normalize_hps), 533-745 (mu_coalign); cauchy_estimator.hpp:307-338
+// (cache_moments), 744-779 (regroup), 1179-1208 (step_first), 1312-1394 (shift / deterministic TP).
+#ifndef MCE_KERN_PROP_H_
+#define MCE_KERN_PROP_H_
+
+#include "mce_exec.h"
+#include "mce_types.h"
+
+namespace mce {
+
+// ---------------------------------------------------------------------------------------------
+// Per-thread building blocks (straight restatements; dot products left to right, no FMA).
+// ---------------------------------------------------------------------------------------------
+MCE_HD double dot_lr(const double* x, const double* y, int n) {
+  double z = 0.0;
+  for (int i = 0; i < n; i++) z += x[i] * y[i];
+  return z;
+}
+
+// normalize_hps, cauchy_term.hpp:458-472
+MCE_HD void normalize_rows(double* A, double* p, double* q, int m, int d, bool set_q) {
+  if (set_q) for (int i = 0; i < m; i++) q[i] = p[i];
+  for (int i = 0; i < m; i++) {
+    double norm1 = 0;
+    for (int j = 0; j < d; j++) norm1 += fabs(A[i * d + j]);
+    p[i] *= norm1;
+    for (int j = 0; j < d; j++) A[i * d + j] /= norm1;
+  }
+}
+
+// (anti)parallel test of two L1-normalised rows, cauchy_term.hpp:494-504 / 563-575
+MCE_HD void coalign_gates(const double* r, const double* c, int d, bool* pos, bool* neg) {
+  bool pg = true, ng = true;
+  for (int l = 0; l < d; l++) {
+    if (pg) pg = fabs(r[l] - c[l]) < COALIGN_EPS;
+    if (ng) ng = fabs(r[l] + c[l]) < COALIGN_EPS;
+    if (!(pg || ng)) break;
+  }
+  *pos = pg; *neg = ng;
+}
+
+// mu_coalign, cauchy_term.hpp:533-745.  Rows are compacted in place; returns the new shape.
+MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsigned* hflag_io, unsigned char* cmap, unsigned* csneg_out) {
+  normalize_rows(A, p, q, m, d, true);
+  unsigned F = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);   // bit set: row still unique
+  unsigned hf = *hflag_io, csneg = 0;
+  const bool any_h = hf != 0;
+  for (int j = 0; j < m; j++) cmap[j] = 255;
+  int unique_count = 0;
+  for (int j = 0; j < m - 1; j++) {
+    if (!((F >> j) & 1u)) continue;
+    cmap[j] = (unsigned char)unique_count;
+    for (int k = j + 1; k < m; k++) {
+      if (!((F >> k) & 1u)) continue;
+      bool pos, neg;
+      coalign_gates(A + j * d, A + k * d, d, &pos, &neg);
+      if (pos) {
+        if (any_h) {
+          const bool hj = (hf >> j) & 1u, hk = (hf >> k) & 1u;
+          if (!hj && !hk) q[j] += q[k];
+          else if (hj && !hk) { q[j] = q[k]; hf &= ~(1u << j); }
+          else if (!hj && hk) hf &= ~(1u << k);
+          else { hf &= ~(1u << k); q[j] += q[k]; }
+        } else q[j] += q[k];
+        F &= ~(1u << k); p[j] += p[k]; cmap[k] = (unsigned char)unique_count;
+      }
+      if (neg) {
+        if (any_h) {
+          const bool hj = (hf >> j) & 1u, hk = (hf >> k) & 1u;
+          if (!hj && !hk) q[j] -= q[k];
+          else if (hj && !hk) { q[j] = -q[k]; hf &= ~(1u << j); }
+          else if (!hj && hk) hf &= ~(1u << k);
+          // both H-orthogonal and anti-parallel: the reference exit(1)s here (term:674-691); the flag survives
+        } else q[j] -= q[k];
+        F &= ~(1u << k); p[j] += p[k]; cmap[k] = (unsigned char)unique_count; csneg |= (1u << k);
+      }
+    }
+    unique_count += 1;
+  }
+  if ((F >> (m - 1)) & 1u) cmap[m - 1] = (unsigned char)unique_count;
+  int new_shape = 0;
+  for (int i = 0; i < m; i++) new_shape += (F >> i) & 1u;
+  if (new_shape != m) {
+    unique_count = 1;
+    for (int j = 1; j < m; j++) {
+      if ((F >> j) & 1u) {
+        if (unique_count < j) {
+          for (int l = 0; l < d; l++) A[unique_count * d + l] = A[j * d + l];
+          p[unique_count] = p[j]; q[unique_count] = q[j];
+        }
+        unique_count++;
+      }
+    }
+    if (any_h) {
+      unsigned nf = 0; unique_count = 0;
+      for (int j = 0; j < m; j++) if ((F >> j) & 1u) nf |= (((hf >> j) & 1u) << unique_count++);
+      hf = nf;
+    }
+  }
+  *hflag_io = hf; *csneg_out = csneg;
+  return new_shape;
+}
+
+// eval_g_yei, cauchy_term.hpp:312-401, for a term that has not been L1-normalised yet.
+// y gets 2d doubles: (re_j, im_j) = (-sum_l p_l s_l a_lj, b_j).
+MCE_HD cplx eval_g_yei(const double* A, const double* p, const double* b, int m, int d, unsigned hflag, double c_val, double d_val,
+                       const double* root_point, bool first_update, int phc, int z, unsigned enc_lhp,
+                       const unsigned* pkeys, const cplx* pG, int pcells, double* y) {
+  double tmp[MAXD];
+  for (int j = 0; j < d; j++) tmp[j] = 0;
+  unsigned signs = 0;
+  double ygi = 0;
+  for (int l = 0; l < m; l++) {
+    const double s = dot_lr(A + l * d, root_point, d) > 0 ? 1.0 : -1.0;
+    if (s < 0) signs |= (1u << l);
+    const double sc = p[l] * s;
+    for (int j = 0; j < d; j++) tmp[j] += sc * A[l * d + j];
+    if (!((hflag >> l) & 1u)) ygi += p[l] * s;
+  }
+  cplx gp, gm;
+  if (first_update) { gp = make_cplx(1, 0); gm = make_cplx(1, 0); }
+  else {
+    int lp, lm;
+    parent_keys(signs, m, phc, z, true, nullptr, 0, &lp, &lm);   // the old term has z = m >= phc: no inserted bit
+    gp = g_lookup(lp ^ (int)enc_lhp, phc, pkeys, pG, pcells);
+    gm = g_lookup(lm ^ (int)enc_lhp, phc, pkeys, pG, pcells);
+  }
+  cplx g = csub(cdiv(gp, make_cplx(ygi + d_val, c_val)), cdiv(gm, make_cplx(ygi - d_val, c_val)));
+  g = cscale(g, 1.0 / (2.0 * M_PI));
+  for (int j = 0; j < d; j++) { y[2 * j] = -tmp[j]; y[2 * j + 1] = b[j]; }
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: time propagation + Gamma coalignment, one thread per parent (TP steps only).
+// ---------------------------------------------------------------------------------------------
+struct KTimeProp {
+  StepParams sp; GenView gen; ParentWs ws;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int r = c.block() * c.nthreads() + tid;
+      if (r >= gen.n_alive) return;
+      const int d = sp.d, gid = gen.alive[r], m0 = gen_m(gen, gid), MS = sp.max_shape;
+      const double* A0 = gen_A(gen, gid, m0, d); const double* p0 = gen_p(gen, gid, m0); const double* b0 = gen_b(gen, gid, d);
+      double* A = ws.A + (long long)r * MS * d; double* p = ws.p + (long long)r * MS; double* b = ws.b + (long long)r * d;
+      // time_prop, cauchy_term.hpp:435-456: A <- A Phi^T, b <- Phi b (+ B u)
+      for (int i = 0; i < m0; i++)
+        for (int j = 0; j < d; j++) {
+          double sum = 0.0;
+          for (int k = 0; k < d; k++) sum += A0[i * d + k] * sp.Phi[k + j * d];
+          A[i * d + j] = sum;
+        }
+      for (int i = 0; i < d; i++) {
+        double sum = 0.0;
+        for (int j = 0; j < d; j++) sum += sp.Phi[i * d + j] * b0[j];
+        b[i] = sum;
+      }
+      if (sp.has_bu) for (int i = 0; i < d; i++) b[i] += 1.0 * sp.bu[i];
+      for (int i = 0; i < m0; i++) p[i] = p0[i];
+      // tp_coalign, cauchy_term.hpp:475-531
+      normalize_rows(A, p, nullptr, m0, d, false);
+      int m = m0; unsigned Fg = (1u << sp.npn) - 1u;
+      for (int j = 0; j < sp.npn; j++) {
+        const double* gr = sp.GammaT + j * d;
+        for (int k = 0; k < m0; k++) {
+          if (!((Fg >> j) & 1u)) break;
+          bool pos, neg;
+          coalign_gates(gr, A + k * d, d, &pos, &neg);
+          if (pos || neg) { Fg &= ~(1u << j); p[k] += sp.beta[j]; }
+        }
+      }
+      for (int i = 0; i < sp.npn; i++)
+        if ((Fg >> i) & 1u) {
+          for (int l = 0; l < d; l++) A[m * d + l] = sp.GammaT[i * d + l];
+          p[m++] = sp.beta[i];
+        }
+      ws.m_tp[r] = (unsigned char)m;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4: measurement update, moment contribution and MU coalignment; one thread per (parent, slot).
+// Launched once per old shape `ms` (all parents of a region share MT = ms + npn).
+// ---------------------------------------------------------------------------------------------
+struct KMsmtUpdate {
+  StepParams sp; GenView gen; ParentWs ws; SlotView sl; int ms;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int MT = sl.MT[ms], spp = MT + 1;
+      const long long ls = (long long)c.block() * c.nthreads() + tid;
+      const int npar = sl.par_begin[ms + 1] - sl.par_begin[ms];
+      if (ls >= (long long)npar * spp) return;
+      const int r = sl.par_begin[ms] + (int)(ls / spp), s = (int)(ls % spp);
+      const long long slot = sl.slot_begin[ms] + ls;
+      const int d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid);
+      int m; const double *Ap, *pp, *bp;
+      if (sp.with_tp) { m = ws.m_tp[r]; Ap = ws.A + (long long)r * sp.max_shape * d; pp = ws.p + (long long)r * sp.max_shape; bp = ws.b + (long long)r * d; }
+      else { m = phc; Ap = gen_A(gen, gid, phc, d); pp = gen_p(gen, gid, phc); bp = gen_b(gen, gid, d); }
+      SlotMeta me; me.newm = 0; me.pbc = (unsigned char)m; me.z = 0; me.flags = 0; me.hflag = 0; me.enc_lhp = 0; me.csneg = 0; me.parent = r; me.pad_ = 0; me.c_val = 0; me.d_val = 0;
+      double* yout = sl.y + slot * 2 * d;
+      const int t = (s == 0) ? m : s - 1;
+      // --- msmt_update, cauchy_term.hpp:104-134: mu_l = a_l / (H a_l), rho_l = p_l |H a_l| ---
+      double mu[(MAXM + 1) * MAXD], rho[MAXM + 1];
+      unsigned F_int = 0, sgn = 0;
+      if (t <= m) {
+        for (int l = 0; l < m; l++) {
+          double* mu_l = mu + l * d;
+          for (int i = 0; i < d; i++) mu_l[i] = Ap[l * d + i];
+          const double H_mu = dot_lr(sp.H, mu_l, d), a = fabs(H_mu);
+          if (a < MU_EPS) rho[l] = pp[l];
+          else {
+            const double sc = 1.0 / H_mu;
+            for (int i = 0; i < d; i++) mu_l[i] *= sc;
+            rho[l] = pp[l] * a; F_int |= (1u << l);
+            if (!(H_mu > 0)) sgn |= (1u << l);
+          }
+        }
+        rho[m] = sp.gamma; for (int i = 0; i < d; i++) mu[m * d + i] = 0; F_int |= (1u << m);
+      }
+      if (t > m || (s != 0 && t >= m) || !((F_int >> t) & 1u)) {        // no such child (row H-orthogonal, or parent has fewer rows than MT)
+        sl.g[slot] = make_cplx(0, 0);
+        for (int j = 0; j < 2 * d; j++) yout[j] = 0;
+        sl.meta[slot] = me;
+        return;
+      }
+      const double zeta = sp.msmt - dot_lr(sp.H, bp, d);
+      // --- child t, cauchy_term.hpp:158-211 ---
+      double cA[MAXM * MAXD], cp[MAXM], cq[MAXM], cb[MAXD];
+      const double* mu_t = mu + t * d;
+      for (int i = 0; i < d; i++) cb[i] = bp[i] + zeta * mu_t[i];
+      unsigned hofs = 0; int l = 0;
+      for (int _l = 0; _l < m + 1; _l++) {
+        if (_l == t) continue;
+        const double* mu_l = mu + _l * d;
+        cp[l] = rho[_l];
+        if ((F_int >> _l) & 1u) for (int i = 0; i < d; i++) cA[l * d + i] = mu_l[i] - mu_t[i];
+        else { for (int i = 0; i < d; i++) cA[l * d + i] = mu_l[i]; hofs |= (1u << l); }
+        l++;
+      }
+      // enc_lhp, cauchy_term.hpp:217-228
+      unsigned enc_lhp = sgn;
+      if (phc < m) enc_lhp &= (1u << phc) - 1u;
+      me.z = (unsigned char)t; me.flags = (s == 0) ? 0 : 1; me.hflag = hofs; me.enc_lhp = enc_lhp; me.c_val = zeta; me.d_val = rho[t];
+      // --- moment contribution, cauchy_estimator.hpp:307-338 (summed by KMoments) ---
+      const unsigned* pkeys = gen_keys(gen, gid, phc); const cplx* pG = gen_G(gen, gid, phc);
+      sl.g[slot] = eval_g_yei(cA, cp, cb, m, d, hofs, zeta, rho[t], sp.root_point, false, phc, t, enc_lhp, pkeys, pG, gen.cells[gid], yout);
+      if (s == 0) {
+        unsigned e = sgn;                                   // parent B ^= enc_sgn_AH, half-normalised (term:229-250)
+        if (e & (1u << (m - 1))) e ^= (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
+        ws.sgnmask[r] = e; ws.bxor[r] = 0;
+      }
+      if (sp.skip_post_mu) { me.newm = (unsigned char)m; sl.meta[slot] = me; return; }
+      // --- normalise / coalign (cauchy_estimator.hpp:719-731) and store the slot ---
+      int newm = m; unsigned csneg = 0;
+      unsigned char* cmap = sl.cmap + slot * MAXM;
+      if (s == 0) normalize_rows(cA, cp, cq, m, d, true);
+      else {
+        newm = mu_coalign_rows(cA, cp, cq, m, d, &hofs, cmap, &csneg);
+        if (newm < m) me.flags |= 2;
+      }
+      me.newm = (unsigned char)newm; me.hflag = hofs; me.csneg = csneg;
+      double* Ao = sl.A + sl.A_off[ms] + ls * (long long)MT * d; double* po = sl.p + sl.pq_off[ms] + ls * MT; double* qo = sl.q + sl.pq_off[ms] + ls * MT;
+      double* bo = sl.b + slot * d;
+      for (int i = 0; i < newm * d; i++) Ao[i] = cA[i];
+      for (int i = 0; i < newm; i++) { po[i] = cp[i]; qo[i] = cq[i]; }
+      for (int i = 0; i < d; i++) bo[i] = cb[i];
+      sl.meta[slot] = me;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Moments: fz is summed in the reference's serial order (bit-identical to NUM_CPUS=1: the running
+// normaliser 1/(2 pi Re fz) scales every new G and hence every term-approximation decision);
+// mean / covariance sums use a fixed-shape two-level reduction (deterministic; parity bar 1e-9).
+// ---------------------------------------------------------------------------------------------
+// Serial-order sums of all 1 + d + d*d complex moment accumulators: real accumulator q2 = 2*q + part is owned
+// by thread q2 and adds its addend for slot 0, 1, 2, ... in slot order, which is the order of the reference's
+// cache_moments loop (parents in shape/index order, each followed by its children).  The addends are computed
+// exactly as est:318-325 does: fz += g; mean_j += g*y_j; cov_jk -= (g*y_j)*y_k.  Unused slots hold g = y = 0
+// and leave every accumulator unchanged, so the sums are bit-identical to the NUM_CPUS = 1 reference.
+struct KMomentsSerial {
+  const cplx* g; const double* y; long long n; int d; double* out /*[2*(1+d+d*d)]*/;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int nq = 1 + d + d * d;
+      if (tid >= 2 * nq || c.block() != 0) return;
+      const int q = tid >> 1, part = tid & 1;
+      const int j = q == 0 ? 0 : (q <= d ? q - 1 : (q - 1 - d) / d), k = q <= d ? 0 : (q - 1 - d) % d;
+      double acc = 0;
+      for (long long i = 0; i < n; i++) {
+        const cplx gv = g[i];
+        double v;
+        if (q == 0) v = part ? gv.im : gv.re;
+        else {
+          const double* yy = y + i * 2 * d;
+          cplx w = cmul(gv, make_cplx(yy[2 * j], yy[2 * j + 1]));
+          if (q > d) w = cmul(w, make_cplx(yy[2 * k], yy[2 * k + 1]));
+          v = part ? w.im : w.re;
+        }
+        if (q > d) acc -= v; else acc += v;
+      }
+      out[tid] = acc;
+    });
+  }
+};
+
+constexpr int MOM_CHUNK = 4096;   // slots per block of the partial-moment reduction
+struct KMomentsPartial {          // partial[block][2*(d + d*d)] = sum over the block's slots of (g*y_j, -g*y_j*y_k)
+  const cplx* g; const double* y; long long n; int d; double* partial;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int nq = d + d * d;
+    double* sm = (double*)c.smem();                 // [nthreads][2] scratch per quantity
+    const long long lo = (long long)c.block() * MOM_CHUNK;
+    const long long hi = lo + MOM_CHUNK < n ? lo + MOM_CHUNK : n;
+    for (int qn = 0; qn < nq; qn++) {
+      c.par([&](int tid) {
+        double ar = 0, ai = 0;
+        for (long long i = lo + tid; i < hi; i += c.nthreads()) {
+          const cplx gv = g[i];
+          const double* yy = y + i * 2 * d;
+          cplx v;
+          if (qn < d) v = cmul(gv, make_cplx(yy[2 * qn], yy[2 * qn + 1]));
+          else {
+            const int j = (qn - d) / d, k = (qn - d) % d;
+            v = cmul(cmul(gv, make_cplx(yy[2 * j], yy[2 * j + 1])), make_cplx(yy[2 * k], yy[2 * k + 1]));
+            v.re = -v.re; v.im = -v.im;
+          }
+          ar += v.re; ai += v.im;
+        }
+        sm[2 * tid] = ar; sm[2 * tid + 1] = ai;
+      });
+      for (int stride = c.nthreads() / 2; stride > 0; stride >>= 1)
+        c.par([&](int tid) { if (tid < stride) { sm[2 * tid] += sm[2 * (tid + stride)]; sm[2 * tid + 1] += sm[2 * (tid + stride) + 1]; } });
+      c.par([&](int tid) { if (tid == 0) { partial[((long long)c.block() * nq + qn) * 2] = sm[0]; partial[((long long)c.block() * nq + qn) * 2 + 1] = sm[1]; } });
+    }
+  }
+};
+struct KMomentsFinal {            // out[2*nq] = ordered sum of the block partials
+  const double* partial; int nblocks_in; int nq; double* out;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int q2 = c.block() * c.nthreads() + tid;
+      if (q2 >= 2 * nq) return;
+      double acc = 0;
+      for (int b = 0; b < nblocks_in; b++) acc += partial[(long long)b * 2 * nq + q2];
+      out[q2] = acc;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Regroup by new shape (cauchy_estimator.hpp:744-779): canonical rank of every slot inside its new
+// shape = [old terms in (old shape, parent) order] ++ [children in (old shape, parent, t) order].
+// Pass 1 counts per chunk, pass 2 scans the chunk counts per (kind, shape) bin, pass 3 scatters.
+// ---------------------------------------------------------------------------------------------
+constexpr int RANK_CHUNK = 256;
+MCE_HD int slot_region(const SlotView& sl, long long slot) {
+  int m = 0;
+  for (int k = 1; k < NSHAPE; k++) if (sl.slot_begin[k] <= slot && slot < sl.slot_begin[k + 1]) m = k;
+  return m;
+}
+struct KRankCount {     // counts[(kind*NSHAPE + shape) * nchunks + chunk]
+  SlotView sl; int nchunks; int* counts;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    int* hist = (int*)c.smem();      // [2*NSHAPE]
+    c.par([&](int tid) { for (int i = tid; i < 2 * NSHAPE; i += c.nthreads()) hist[i] = 0; });
+    c.par([&](int tid) {
+      const long long slot = (long long)c.block() * RANK_CHUNK + tid;
+      if (tid >= RANK_CHUNK || slot >= sl.n_slots) return;
+      const SlotMeta& me = sl.meta[slot];
+      if (me.newm) c.atomic_add(&hist[(me.flags & 1) * NSHAPE + me.newm], 1);
+    });
+    c.par([&](int tid) { for (int i = tid; i < 2 * NSHAPE; i += c.nthreads()) counts[(long long)i * nchunks + c.block()] = hist[i]; });
+  }
+};
+struct KRankScan {      // exclusive scan over chunks for every bin; one block per bin, serial (nchunks is small)
+  int nchunks; int* counts; int* totals;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      if (tid != 0) return;
+      int* cc = counts + (long long)c.block() * nchunks;
+      int acc = 0;
+      for (int i = 0; i < nchunks; i++) { int v = cc[i]; cc[i] = acc; acc += v; }
+      totals[c.block()] = acc;
+    });
+  }
+};
+struct KRegroup {       // one block per chunk; thread 0 assigns ranks in slot order, then all threads copy payloads
+  StepParams sp; SlotView sl; TermView tv; int nchunks; const int* counts; long long* slot_of_term;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    int* dst = (int*)c.smem();       // [RANK_CHUNK] destination rank (-1 = unused slot)
+    c.par([&](int tid) {
+      if (tid != 0) return;
+      int run[2 * NSHAPE];
+      for (int i = 0; i < 2 * NSHAPE; i++) run[i] = counts[(long long)i * nchunks + c.block()];
+      for (int k = 0; k < RANK_CHUNK; k++) {
+        const long long slot = (long long)c.block() * RANK_CHUNK + k;
+        dst[k] = -1;
+        if (slot >= sl.n_slots) continue;
+        const SlotMeta& me = sl.meta[slot];
+        if (!me.newm) continue;
+        const int kind = me.flags & 1;
+        dst[k] = (kind ? tv.n_old[me.newm] : 0) + run[kind * NSHAPE + me.newm]++;
+      }
+    });
+    const int d = sp.d;
+    c.par([&](int tid) {          // a 32-thread team per slot: coalesced row copies, no barriers needed
+      const int team = tid >> 5, lane = tid & 31, nteams = c.nthreads() >> 5;
+      for (int k = team; k < RANK_CHUNK; k += nteams) {
+        const int rank = dst[k];
+        if (rank < 0) continue;
+        const long long slot = (long long)c.block() * RANK_CHUNK + k;
+        const SlotMeta me = sl.meta[slot];
+        const int m = me.newm, ms = slot_region(sl, slot), MT = sl.MT[ms];
+        const long long ls = slot - sl.slot_begin[ms];
+        const double* Ai = sl.A + sl.A_off[ms] + ls * (long long)MT * d; const double* pi = sl.p + sl.pq_off[ms] + ls * MT; const double* qi = sl.q + sl.pq_off[ms] + ls * MT;
+        double* Ao = term_A(tv, m, rank, d); double* po = term_p(tv, m, rank); double* qo = term_q(tv, m, rank); double* bo = term_b(tv, m, rank, d);
+        for (int i = lane; i < m * d; i += 32) Ao[i] = Ai[i];
+        for (int i = lane; i < m; i += 32) { po[i] = pi[i]; qo[i] = qi[i]; }
+        for (int i = lane; i < d; i += 32) bo[i] = sl.b[slot * d + i];
+        const long long gt = tv.t_begin[m] + rank;
+        if (lane < MAXM) tv.cmap[gt * MAXM + lane] = sl.cmap[slot * MAXM + lane];
+        if (lane == 0) { tv.meta[gt] = me; slot_of_term[gt] = slot; }
+      }
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K10: b <- b - delta over all parents (finalize_extended_moments est:1365-1383, shift_cf_by_bias est:1312).
+// ---------------------------------------------------------------------------------------------
+struct KShiftB {
+  GenView gen; int d; double delta[MAXD]; double sign;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int r = c.block() * c.nthreads() + tid;
+      if (r >= gen.n_alive) return;
+      double* b = gen_b(gen, gen.alive[r], d);
+      if (sign < 0) for (int j = 0; j < d; j++) b[j] -= delta[j];
+      else for (int j = 0; j < d; j++) b[j] += delta[j];
+    });
+  }
+};
+// deterministic_time_prop, est:1331-1355: A <- A T^T, b <- T b (+ B u) without adding process noise.
+struct KDetTimeProp {
+  GenView gen; int d; double T[MAXD * MAXD]; double bu[MAXD]; int has_bu;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int r = c.block() * c.nthreads() + tid;
+      if (r >= gen.n_alive) return;
+      const int gid = gen.alive[r], m = gen_m(gen, gid);
+      double* A = gen_A(gen, gid, m, d); double* b = gen_b(gen, gid, d);
+      double work[MAXD];
+      for (int i = 0; i < m; i++) {
+        for (int k = 0; k < d; k++) work[k] = A[i * d + k];
+        for (int j = 0; j < d; j++) { double sum = 0.0; for (int k = 0; k < d; k++) sum += work[k] * T[k + j * d]; A[i * d + j] = sum; }
+      }
+      for (int k = 0; k < d; k++) work[k] = b[k];
+      for (int i = 0; i < d; i++) { double sum = 0.0; for (int j = 0; j < d; j++) sum += T[i * d + j] * work[j]; b[i] = sum; }
+      if (has_bu) for (int i = 0; i < d; i++) b[i] += 1.0 * bu[i];
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// First step (cauchy_estimator.hpp:1179-1208): d+1 terms from (A0, p0, b0), closed-form tables
+// (make_gtable_first, flattening.hpp:14-67).  One block; thread s handles slot s (0 = old term).
+// out_mom: [2*(1+d+d*d)] raw sums (fz, mean, cov) in term order.
+// ---------------------------------------------------------------------------------------------
+struct KFirstStep {
+  StepParams sp; const double *A0, *p0, *b0; GenView out; double* out_mom; int* out_count;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int d = sp.d, nq = 1 + d + d * d;
+    double* sm_g = (double*)c.smem();                  // [(d+1)][2 + 2d] g and y per slot
+    int* sm_valid = (int*)(sm_g + (d + 1) * (2 + 2 * d)); // [d+1] term index or -1
+    double* sm_scale = (double*)(sm_valid + ((d + 2) & ~1));
+    c.par([&](int tid) {
+      if (tid > d) return;
+      const int s = tid, m = d, t = (s == 0) ? m : s - 1;
+      double mu[(MAXD + 1) * MAXD], rho[MAXD + 1]; unsigned F_int = 0;
+      for (int l = 0; l < m; l++) {
+        double* mu_l = mu + l * d;
+        for (int i = 0; i < d; i++) mu_l[i] = A0[l * d + i];
+        const double H_mu = dot_lr(sp.H, mu_l, d), a = fabs(H_mu);
+        if (a < MU_EPS) rho[l] = p0[l];
+        else { const double sc = 1.0 / H_mu; for (int i = 0; i < d; i++) mu_l[i] *= sc; rho[l] = p0[l] * a; F_int |= (1u << l); }
+      }
+      rho[m] = sp.gamma; for (int i = 0; i < d; i++) mu[m * d + i] = 0; F_int |= (1u << m);
+      sm_valid[s] = ((F_int >> t) & 1u) ? 1 : -1;
+      double* gy = sm_g + s * (2 + 2 * d);
+      for (int i = 0; i < 2 + 2 * d; i++) gy[i] = 0;
+      if (!((F_int >> t) & 1u)) return;
+      const double zeta = sp.msmt - dot_lr(sp.H, b0, d);
+      double cA[MAXD * MAXD], cp[MAXD], cb[MAXD];
+      const double* mu_t = mu + t * d;
+      for (int i = 0; i < d; i++) cb[i] = b0[i] + zeta * mu_t[i];
+      unsigned hofs = 0; int l = 0;
+      for (int _l = 0; _l < m + 1; _l++) {
+        if (_l == t) continue;
+        cp[l] = rho[_l];
+        if ((F_int >> _l) & 1u) for (int i = 0; i < d; i++) cA[l * d + i] = mu[_l * d + i] - mu_t[i];
+        else { for (int i = 0; i < d; i++) cA[l * d + i] = mu[_l * d + i]; hofs |= (1u << l); }
+        l++;
+      }
+      cplx g = eval_g_yei(cA, cp, cb, m, d, hofs, zeta, rho[t], sp.root_point, true, 0, 0, 0, nullptr, nullptr, 0, gy + 2);
+      gy[0] = g.re; gy[1] = g.im;
+      // term index: old term first, then the integrable children in t order (est:1182)
+      int idx = 0;
+      if (s > 0) { idx = 1; for (int tt = 0; tt < t; tt++) idx += (F_int >> tt) & 1u; }
+      sm_valid[s] = idx;
+      double* Ao = gen_A(out, idx, d, d); double* po = gen_p(out, idx, d); double* bo = gen_b(out, idx, d);
+      for (int i = 0; i < m * d; i++) Ao[i] = cA[i];
+      for (int i = 0; i < m; i++) po[i] = cp[i];
+      for (int i = 0; i < d; i++) bo[i] = cb[i];
+      // c, d and Horthog are needed by the table pass; stash them behind y in shared memory is not enough (y is d complex),
+      // so recompute-free: store in the G slot 0 of the table (overwritten below after being read back).
+      cplx* Gt = gen_G(out, idx, d);
+      Gt[0] = make_cplx(zeta, rho[t]);
+      unsigned* Kt = gen_keys(out, idx, d);
+      Kt[0] = hofs;
+    });
+    c.par([&](int tid) {          // compute_moments(true), est:524-579: serial sums in term order
+      if (tid != 0) return;
+      cplx acc[1 + MAXD + MAXD * MAXD];
+      for (int i = 0; i < nq; i++) acc[i] = make_cplx(0, 0);
+      int nt = 0;
+      for (int idx = 0; idx <= d; idx++)
+        for (int s = 0; s <= d; s++) {
+          if (sm_valid[s] != idx) continue;
+          nt++;
+          const double* gy = sm_g + s * (2 + 2 * d);
+          const cplx g = make_cplx(gy[0], gy[1]);
+          acc[0] = cadd(acc[0], g);
+          for (int j = 0; j < d; j++) {
+            const cplx yj = make_cplx(gy[2 + 2 * j], gy[3 + 2 * j]);
+            acc[1 + j] = cadd(acc[1 + j], cmul(g, yj));
+            for (int k = 0; k < d; k++) acc[1 + d + j * d + k] = csub(acc[1 + d + j * d + k], cmul(cmul(g, yj), make_cplx(gy[2 + 2 * k], gy[3 + 2 * k])));
+          }
+        }
+      for (int i = 0; i < nq; i++) { out_mom[2 * i] = acc[i].re; out_mom[2 * i + 1] = acc[i].im; }
+      *out_count = nt;
+      sm_scale[0] = (1.0 / (2.0 * M_PI)) / acc[0].re;       // G_SCALE_FACTOR, est:567
+    });
+    c.par([&](int tid) {          // make_gtable_first, flattening.hpp:14-67 (one thread per term)
+      if (tid > d || sm_valid[tid] < 0) return;
+      const int idx = sm_valid[tid], m = d, cells = 1 << (d - 1);
+      cplx* Gt = gen_G(out, idx, d); unsigned* Kt = gen_keys(out, idx, d);
+      const double c_val = Gt[0].re, d_val = Gt[0].im; const unsigned hofs = Kt[0];
+      const double* p = gen_p(out, idx, d);
+      for (int j = 0; j < cells; j++) {
+        double ygi = 0;
+        for (int k = 0; k < m; k++) if (!((hofs >> k) & 1u)) ygi += p[k] * ((((j >> k) & 1) == 0) ? 1.0 : -1.0);
+        cplx v = csub(cdiv(make_cplx(1, 0), make_cplx(ygi + d_val, c_val)), cdiv(make_cplx(1, 0), make_cplx(ygi - d_val, c_val)));
+        Gt[j] = cscale(v, sm_scale[0]); Kt[j] = (unsigned)j;
+      }
+      out.cells[idx] = cells; out.g_m[idx] = (unsigned char)d; out.alive[idx] = idx;
+    });
+  }
+};
+
+}  // namespace mce
+#endif

@@ -1,0 +1,178 @@
+"""Host-side mirror of the reference's `struct CauchyEstimator` (include/cauchy_estimator.hpp:47-1432) over the
+C ABI of libmce_b200.so.  Same member names, argument meaning and error behaviour as the reference, so code written
+against the reference (src/*.cpp, scripts/swig/cauchy/cauchy_estimator.py:515 PyCauchyEstimator) ports line by line.
+All term-list work happens on the GPU; this file only marshals arguments."""
+import ctypes as ct
+
+import numpy as np
+
+from . import _capi
+
+# numeric_moment_errors bits, cauchy_constants.hpp:104-116
+ERROR_FZ_NEGATIVE = 9
+ERROR_FZ_UNSTABLE = 8
+ERROR_MEAN_AT_CURRENT_STEP_DNE = 7
+ERROR_COVARIANCE_AT_CURRENT_STEP_DNE = 3
+
+
+def _dp(a):
+    return a.ctypes.data_as(ct.POINTER(ct.c_double)) if a is not None else None
+
+
+def _f64(x, n=None):
+    if x is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    if n is not None and a.size != n:
+        raise ValueError("expected %d values, got %d" % (n, a.size))
+    return a
+
+
+class CauchyEstimator:
+    """CauchyEstimator(A0, p0, b0, steps, d, cmcc, pncc, p, print_basic_info) -- est:87.
+
+    root_point / b_pert are the vectors the reference draws with libc rand() in its constructor (est:125-128,
+    cell_enumeration.hpp:467-470); pass recorded values to reproduce a reference run, or leave None to draw them
+    from `seed` with the same distributions (1 + U(0,1], 2U - 1)."""
+
+    def __init__(self, A0, p0, b0, steps, d, cmcc, pncc, p, print_basic_info=False, root_point=None, b_pert=None,
+                 tr_search_idxs_ordering=None, device=-1, seed=0, fast_moments=False):
+        self._lib = _capi.load()
+        self.d, self.cmcc, self.pncc, self.p = int(d), int(cmcc), int(pncc), int(p)
+        self.num_estimation_steps = self.p * int(steps)
+        max_shape = (int(steps) - 1) * self.pncc + self.d if self.d > 1 else self.d + self.pncc
+        rng = np.random.RandomState(seed)
+        if root_point is None:
+            root_point = 1.0 + (rng.randint(0, 2**31 - 1, self.d) + 1.0) / 2.0**31
+        if b_pert is None:
+            b_pert = 2.0 * (rng.randint(0, 2**31 - 1, max_shape) + 1.0) / 2.0**31 - 1.0
+        self.root_point = _f64(root_point, self.d)
+        bp = np.zeros(max(max_shape, 1) + _capi.MAXM)
+        bp[: len(b_pert)] = np.asarray(b_pert, np.float64)[: len(bp)]
+        self.b_pert = bp
+        o = _capi.MceOptions()
+        self._lib.mce_default_options(ct.byref(o))
+        o.device = int(device)
+        o.print_basic_info = int(bool(print_basic_info))
+        o.fast_moments = int(bool(fast_moments))
+        if tr_search_idxs_ordering is not None:
+            for i, v in enumerate(list(tr_search_idxs_ordering)[:12]):
+                o.tr_search_order[i] = int(v)
+        self._A0, self._p0, self._b0 = _f64(A0, self.d * self.d), _f64(p0, self.d), _f64(b0, self.d)
+        self._h = self._lib.mce_create(self.d, self.cmcc, self.pncc, self.p, int(steps), _dp(self._A0), _dp(self._p0), _dp(self._b0),
+                                       _dp(self.root_point), _dp(self.b_pert), ct.byref(o))
+        if not self._h:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+        self.shape_range = self._lib.mce_shape_range(self._h)
+        self.print_basic_info = bool(print_basic_info)
+        self.win_num = 0
+        self._refresh()
+
+    # ---- public fields of the reference struct ----
+    def _refresh(self):
+        m = _capi.MceMoments()
+        self._lib.mce_get_moments(self._h, ct.byref(m))
+        d = self.d
+        self.fz = complex(m.fz[0], m.fz[1])
+        self.fz_after_mu = complex(m.fz_after_mu[0], m.fz_after_mu[1])
+        self.conditional_mean = np.array(m.mean[: 2 * d]).view(np.complex128).copy()
+        self.conditional_variance = np.array(m.cov[: 2 * d * d]).view(np.complex128).reshape(d, d).copy()
+        self.G_SCALE_FACTOR = m.g_scale_factor
+        self.numeric_moment_errors = m.numeric_moment_errors
+        self.Nt = m.Nt
+        self.Nt_after_muc = m.Nt_after_muc
+        self._master_step = m.master_step
+        self.skip_post_mu = bool(m.skip_post_mu)
+
+    @property
+    def master_step(self):
+        return self._master_step
+
+    @master_step.setter
+    def master_step(self, v):          # callers write this field (cauchy_windows.hpp:538,659; pycauchy.hpp:776)
+        self._lib.mce_set_master_step(self._h, int(v))
+        self._master_step = int(v)
+
+    @property
+    def terms_per_shape(self):
+        c = (ct.c_int * self.shape_range)()
+        self._lib.mce_get_terms_per_shape(self._h, c, 0)
+        return np.array(c[:], np.int32)
+
+    def set_win_num(self, win_num):
+        self.win_num = int(win_num)
+
+    def set_function_pointers(self):   # est:192: storage mode is fixed (BINSEARCH + HALF storage) in this build
+        pass
+
+    # ---- the hot path ----
+    def step(self, msmt, Phi, Gamma, beta, H, gamma, B=None, u=None):
+        """int step(msmt, Phi, Gamma, beta, H, gamma, B, u) -- est:1211. Returns numeric_moment_errors."""
+        d = self.d
+        Phi_, Gam_, beta_, H_ = _f64(Phi), _f64(Gamma), _f64(beta), _f64(H, d)
+        B_, u_ = _f64(B), _f64(u)
+        rc = self._lib.mce_step(self._h, float(msmt), _dp(Phi_), _dp(Gam_), _dp(beta_), _dp(H_), float(gamma), _dp(B_), _dp(u_))
+        if rc < 0:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+        self._refresh()
+        return rc
+
+    def finalize_extended_moments(self, x_bar):
+        """est:1358-1394: b <- b - Re(mean) on every term; mean += x_bar; x_bar <- Re(mean) (in place)."""
+        delta = np.ascontiguousarray(self.conditional_mean.real)
+        self._lib.mce_shift_b(self._h, _dp(delta), -1.0)
+        self.conditional_mean = self.conditional_mean + np.asarray(x_bar, np.float64)
+        x_bar[:] = self.conditional_mean.real
+        return x_bar
+
+    def shift_cf_by_bias(self, bias):
+        self._lib.mce_shift_b(self._h, _dp(_f64(bias, self.d)), 1.0)
+
+    def deterministic_time_prop(self, Phi, B=None, u=None):
+        rc = self._lib.mce_deterministic_time_prop(self._h, _dp(_f64(Phi, self.d * self.d)), _dp(_f64(B)), _dp(_f64(u)))
+        if rc < 0:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+
+    def reset(self):
+        self._lib.mce_reset(self._h)
+        self._refresh()
+
+    def reinitialize_start_statistics(self, A0, p0, b0):
+        self._A0, self._p0, self._b0 = _f64(A0, self.d * self.d), _f64(p0, self.d), _f64(b0, self.d)
+        self._lib.mce_reinitialize_start_statistics(self._h, _dp(self._A0), _dp(self._p0), _dp(self._b0))
+
+    def step_stats(self):
+        s = _capi.MceStepStats()
+        self._lib.mce_get_step_stats(self._h, ct.byref(s))
+        return {n: getattr(s, n) for n, _ in s._fields_}
+
+    def export_shape(self, m):
+        """Host copy of the terms with m hyperplanes: A [n, m*d], p [n, m], b [n, d], cells [n], keys, G (concatenated)."""
+        d = self.d
+        n, tot = ct.c_int(0), ct.c_longlong(0)
+        self._lib.mce_export_shape(self._h, m, ct.byref(n), ct.byref(tot), None, None, None, None, None, None)
+        n, tot = n.value, tot.value
+        A, p, b = np.zeros((n, m * d)), np.zeros((n, m)), np.zeros((n, d))
+        cells, keys, G = np.zeros(n, np.int32), np.zeros(tot, np.uint32), np.zeros(tot, np.complex128)
+        if n:
+            n2, t2 = ct.c_int(0), ct.c_longlong(0)
+            self._lib.mce_export_shape(self._h, m, ct.byref(n2), ct.byref(t2), _dp(A), _dp(p), _dp(b),
+                                       cells.ctypes.data_as(ct.POINTER(ct.c_int)), keys.ctypes.data_as(ct.POINTER(ct.c_uint32)),
+                                       G.view(np.float64).ctypes.data_as(ct.POINTER(ct.c_double)))
+        return dict(A=A, p=p, b=b, cells=cells, keys=keys, G=G)
+
+    def print_conditional_mean_variance(self):   # est:513-522
+        print("fz: %.16f + %.16fj" % (self.fz.real, self.fz.imag))
+        print("Conditional Mean:\n", self.conditional_mean)
+        print("Conditional Variance:\n", self.conditional_variance)
+
+    def shutdown(self):
+        if getattr(self, "_h", None):
+            self._lib.mce_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.shutdown()
+        except Exception:
+            pass

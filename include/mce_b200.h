@@ -1,0 +1,115 @@
+/* mce_b200.h -- C ABI of libmce_b200.so, the B200-native replacement for the per-step term propagation of the
+ * Multivariate Cauchy Estimator in natsnyder1/CauchyFriendly.
+ *
+ * Every entry point replaces one member of the reference's `struct CauchyEstimator`
+ * (/root/reference/include/cauchy_estimator.hpp, cited per function below); include/cauchy_estimator.hpp in
+ * this repository wraps them back into that struct so the reference's callers (cauchy_windows.hpp, pycauchy.hpp,
+ * src/ *.cpp, the MATLAB mex shims) compile unchanged.  Conventions are the reference's: caller-owned row-major
+ * `double*` inputs that are consumed during the call (Gamma is d x pncc row-major; H is one 1 x d row per call;
+ * B and u may be NULL), complex outputs as interleaved (re, im) doubles, errors as the reference's
+ * numeric_moment_errors bit field (cauchy_constants.hpp:104-116).  No torch / CUDA types cross this boundary.
+ *
+ * All functions return 0 (or a non-negative value) on success and a negative code on failure;
+ * mce_last_error() returns a static message for the calling thread's last failure.  There is no CPU fallback:
+ * mce_create() fails with MCE_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef MCE_B200_H_
+#define MCE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mce_handle mce_handle;
+
+enum {
+  MCE_OK = 0,
+  MCE_ERR_NO_DEVICE = -1,
+  MCE_ERR_BAD_ARG = -2,
+  MCE_ERR_CUDA = -3,
+  MCE_ERR_STATE = -4,     /* e.g. stepping past num_estimation_steps (the reference exit(1)s, est:1220-1225) */
+  MCE_ERR_CAPACITY = -5
+};
+
+typedef struct mce_options {
+  int device;                 /* CUDA device ordinal; -1 = current device                                    */
+  int tr_search_order[12];    /* TR_SEARCH_IDXS_ORDERING (cauchy_constants.hpp:66); {0,1,2,...} by default   */
+  int print_basic_info;       /* reference quirk A.9(iii): when set, moments are re-evaluated after FTR      */
+  int fast_moments;           /* 0 (default): mean/covariance summed in the reference's serial order (bit-identical to
+                                 NUM_CPUS=1); 1: two-level tree reduction (deterministic, differs in the last bits)      */
+  int reserved[7];
+} mce_options;
+
+/* Fills `o` with the defaults (device -1, identity search order). */
+void mce_default_options(mce_options* o);
+
+/* CauchyEstimator::CauchyEstimator(A0,p0,b0,steps,d,cmcc,pncc,p,print) -- est:87-185.
+ * root_point[d] and b_pert[max_shape] are the two vectors the reference draws with libc rand() in its constructor
+ * (est:125-128, cell_enumeration.hpp:467-470); the host shim keeps drawing them so both implementations see the
+ * same values.  max_shape = (steps-1)*pncc + d  (est:97). */
+mce_handle* mce_create(int d, int cmcc, int pncc, int p, int steps, const double* A0, const double* p0, const double* b0,
+                       const double* root_point, const double* b_pert, const mce_options* opts);
+void mce_destroy(mce_handle* h);                                                   /* ~CauchyEstimator, est:1396 */
+
+/* int CauchyEstimator::step(msmt,Phi,Gamma,beta,H,gamma,B,u) -- est:1211-1245. Returns numeric_moment_errors (>= 0). */
+int mce_step(mce_handle* h, double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H,
+             double gamma, const double* B, const double* u);
+
+/* Public fields read by the callers after step(): fz, conditional_mean, conditional_variance (est:67-69),
+ * G_SCALE_FACTOR, Nt, master_step, numeric_moment_errors, terms_per_shape, shape_range. */
+typedef struct mce_moments {
+  double fz[2];               /* the public `fz` field: 1+0i after a non-final step unless print_basic_info (est:1172-1176) */
+  double fz_after_mu[2];      /* normalisation factor right after the measurement update (what est:795 prints)              */
+  double mean[2 * 16];
+  double cov[2 * 16 * 16];
+  double g_scale_factor;
+  int numeric_moment_errors;
+  int Nt;                     /* terms after the step (after FTR, or after MU on the window's last step)      */
+  int Nt_after_muc;           /* "Total Terms after MUC" (est:791)                                            */
+  int master_step;
+  int skip_post_mu;
+} mce_moments;
+int mce_get_moments(mce_handle* h, mce_moments* out);
+int mce_shape_range(mce_handle* h);
+int mce_get_terms_per_shape(mce_handle* h, int* counts /*[shape_range]*/, int after_muc);
+
+void mce_set_master_step(mce_handle* h, int master_step);   /* callers write this field: cauchy_windows.hpp:538,659 */
+int mce_reset(mce_handle* h);                                                       /* reset(), est:1247-1300 */
+int mce_reinitialize_start_statistics(mce_handle* h, const double* A0, const double* p0, const double* b0); /* est:1302 */
+/* b <- b + sign*delta on every term: finalize_extended_moments (sign=-1, delta=Re mean; est:1358-1394) and
+ * shift_cf_by_bias (sign=+1; est:1312-1328). A no-op after the window's last step, like the reference. */
+int mce_shift_b(mce_handle* h, const double* delta, double sign);
+int mce_deterministic_time_prop(mce_handle* h, const double* Phi, const double* B, const double* u); /* est:1331-1355 */
+
+/* Host mirror of the term list for the reference's side consumers (cpdf_ndim.hpp:680-692 reads A, p, b, m, the
+ * parent table and enc_B of every term) and for the parity tests.  Call with NULL arrays to get the sizes. */
+int mce_export_shape(mce_handle* h, int m, int* n_terms, long long* n_cells_total, double* A /*[n][m*d]*/, double* p /*[n][m]*/,
+                     double* b /*[n][d]*/, int* cells /*[n]*/, uint32_t* keys /*[sum cells]*/, double* G /*[sum cells][2]*/);
+
+/* Statistics of the last step: device milliseconds per phase and algorithmic byte counts (bench.py roofline). */
+typedef struct mce_step_stats {
+  double ms_total, ms_tp, ms_mu, ms_moments, ms_regroup, ms_ftr, ms_gtable, ms_compact;
+  long long parents, slots, terms_after_muc, groups, survivors;
+  long long bytes_gtable_algorithmic;   /* SURVEY.md 8(d) formula with the actual per-term cell counts */
+  long long bytes_step_algorithmic;
+  long long kernel_launches;
+  int ftr_rounds_max;
+  int diag_unmodelled_alias, diag_hash_overflow;
+} mce_step_stats;
+int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
+
+/* Test hook: keep a host copy of the post-MUC term list and FTR flag arrays of the last step. */
+int mce_debug_capture(mce_handle* h, int enable);
+int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,
+                        int* meta /*[n][8]*/, uint8_t* cmap /*[n][32]*/, int8_t* csmap /*[n][32]*/, int* F /*[n]*/);
+
+const char* mce_last_error(void);
+const char* mce_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCE_B200_H_ */

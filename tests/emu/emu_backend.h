@@ -1,0 +1,65 @@
+// emu_backend.h -- TEST INFRASTRUCTURE ONLY. A sequential stand-in for the CUDA backend that lets the
+// kernel bodies of cauchyfriendly_b200/csrc/mce_kern_*.h be unit-tested on machines without a GPU:
+// every `ctx.par(f)` runs f(0..nthreads-1) in a loop, blocks run one after another.  It is compiled into
+// tests/emu/_build/libmce_emu.so by tests/emu/build.sh and loaded only by `-m "not gpu"` tests; the product
+// library libmce_b200.so contains the CUDA backend alone and fails to create a handle without a GPU.
+#ifndef MCE_EMU_BACKEND_H_
+#define MCE_EMU_BACKEND_H_
+
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <algorithm>
+#include <numeric>
+#include <string>
+#include <vector>
+
+namespace mce {
+
+struct EmuCtx {
+  int block_, nblocks_, nthreads_;
+  unsigned char* smem_;
+  int block() const { return block_; }
+  int nblocks() const { return nblocks_; }
+  int nthreads() const { return nthreads_; }
+  unsigned char* smem() const { return smem_; }
+  template <class F> void par(F&& f) { for (int t = 0; t < nthreads_; t++) f(t); }
+  template <class T> T uniform(const T& v) { return v; }
+  int atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
+  unsigned atomic_xor(unsigned* p, unsigned v) { unsigned o = *p; *p ^= v; return o; }
+  unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
+  unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
+  int load_relaxed(const int* p) { return *p; }
+};
+
+struct EmuBackend {
+  long long launch_count = 0;
+  static bool available(int, std::string*) { return true; }
+  bool init(int, std::string*) { return true; }
+  void shutdown() {}
+  void* alloc(size_t n) { void* p = malloc(n ? n : 1); memset(p, 0xCD, n); return p; }   // poison: catches reads of unwritten memory
+  void free(void* p) { ::free(p); }
+  void h2d(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+  void d2h(void* d, const void* s, size_t n) { memcpy(d, s, n); }
+  void memset(void* p, int v, size_t n) { ::memset(p, v, n); }
+  double tic() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+  double toc(double t0) { return tic() - t0; }
+  template <class K> void launch(const K& k, int nblocks, int nthreads, size_t smem) {
+    launch_count++;
+    std::vector<unsigned char> sm(smem + 64, 0xCD);
+    for (int b = 0; b < nblocks; b++) {
+      EmuCtx c{b, nblocks, nthreads, sm.data()};
+      k.run(c);
+    }
+  }
+  void sort_pairs(const unsigned long long* kin, unsigned long long* kout, const int* vin, int* vout, int n) {
+    std::vector<int> idx(n); std::iota(idx.begin(), idx.end(), 0);
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return kin[a] < kin[b]; });
+    for (int i = 0; i < n; i++) { kout[i] = kin[idx[i]]; vout[i] = vin[idx[i]]; }
+  }
+  void exclusive_scan(const int* in, int* out, int n) { int acc = 0; for (int i = 0; i < n; i++) { int v = in[i]; out[i] = acc; acc += v; } }
+};
+
+}  // namespace mce
+#endif

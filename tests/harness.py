@@ -1,0 +1,194 @@
+"""Test harness: drives a C-ABI library (include/mce_b200.h) through a scenario and returns the same named
+arrays that oracle/ref_run.cpp and oracle/mce_oracle_run.c dump, so results can be diffed with compare.py.
+
+`load_product()` loads cauchyfriendly_b200/libmce_b200.so (CUDA, the product); `load_emu()` loads the
+sequential emulation of the kernel bodies (tests/emu, CPU-only logic tests)."""
+import ctypes as ct
+import os
+import subprocess
+
+import numpy as np
+
+from mceio import SHIFT_EXPLICIT, SHIFT_OWN_MEAN, key_digest, read_dump
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAXM = 32
+
+
+import sys
+sys.path.insert(0, ROOT)
+from cauchyfriendly_b200._capi import MceMoments, MceOptions, MceStepStats, bind  # noqa: E402
+
+
+def _dp(a):
+    return a.ctypes.data_as(ct.POINTER(ct.c_double)) if a is not None else None
+
+
+def load_emu(rebuild=False):
+    so = os.path.join(ROOT, "tests", "emu", "_build", "libmce_emu.so")
+    if rebuild or not os.path.exists(so):
+        subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")])
+    return bind(ct.CDLL(so))
+
+
+def load_product():
+    from cauchyfriendly_b200 import _capi
+    return _capi.load()
+
+
+class Session:
+    def __init__(self, lib, sc, print_basic_info=False):
+        self.lib, self.sc = lib, sc
+        o = MceOptions()
+        lib.mce_default_options(ct.byref(o))
+        for i in range(12):
+            o.tr_search_order[i] = sc.tr_order[i]
+        o.print_basic_info = int(print_basic_info)
+        self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
+        self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
+        if not self.h:
+            raise RuntimeError(lib.mce_last_error().decode())
+        self.shape_range = lib.mce_shape_range(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.mce_destroy(self.h)
+            self.h = None
+
+    def step(self, r):
+        Phi = np.ascontiguousarray(r.Phi, np.float64)
+        Gam = np.ascontiguousarray(r.Gamma, np.float64)
+        beta = np.ascontiguousarray(r.beta, np.float64)
+        H = np.ascontiguousarray(r.H, np.float64)
+        B = np.ascontiguousarray(r.B, np.float64) if r.B is not None else None
+        u = np.ascontiguousarray(r.u, np.float64) if r.u is not None else None
+        rc = self.lib.mce_step(self.h, r.msmt, _dp(Phi), _dp(Gam), _dp(beta), _dp(H), r.gamma, _dp(B), _dp(u))
+        if rc < 0:
+            raise RuntimeError("mce_step failed (%d): %s" % (rc, self.lib.mce_last_error().decode()))
+        return rc
+
+    def moments(self):
+        m = MceMoments()
+        self.lib.mce_get_moments(self.h, ct.byref(m))
+        return m
+
+    def stats(self):
+        s = MceStepStats()
+        self.lib.mce_get_step_stats(self.h, ct.byref(s))
+        return s
+
+    def counts(self, after_muc):
+        c = (ct.c_int * self.shape_range)()
+        self.lib.mce_get_terms_per_shape(self.h, c, int(after_muc))
+        return np.array(c[:], np.int32)
+
+    def shift_b(self, delta, sign=-1.0):
+        dl = np.ascontiguousarray(delta, np.float64)
+        self.lib.mce_shift_b(self.h, _dp(dl), sign)
+
+    def export_shape(self, m):
+        d = self.sc.d
+        n, tot = ct.c_int(0), ct.c_longlong(0)
+        self.lib.mce_export_shape(self.h, m, ct.byref(n), ct.byref(tot), None, None, None, None, None, None)
+        n, tot = n.value, tot.value
+        A, p, b = np.zeros((n, m * d)), np.zeros((n, m)), np.zeros((n, d))
+        cells, keys, G = np.zeros(n, np.int32), np.zeros(tot, np.uint32), np.zeros(tot, np.complex128)
+        if n:
+            n2, t2 = ct.c_int(0), ct.c_longlong(0)
+            self.lib.mce_export_shape(self.h, m, ct.byref(n2), ct.byref(t2), _dp(A), _dp(p), _dp(b), cells.ctypes.data_as(ct.POINTER(ct.c_int)),
+                                      keys.ctypes.data_as(ct.POINTER(ct.c_uint32)), G.view(np.float64).ctypes.data_as(ct.POINTER(ct.c_double)))
+        return dict(A=A, p=p, b=b, cells=cells, keys=keys, G=G)
+
+    def debug_muc_shape(self, m):
+        d = self.sc.d
+        n = ct.c_int(0)
+        self.lib.mce_debug_muc_shape(self.h, m, ct.byref(n), None, None, None, None, None, None, None, None, None)
+        n = n.value
+        if n == 0:
+            return None
+        A, p, q, b, cd = np.zeros((n, m * d)), np.zeros((n, m)), np.zeros((n, m)), np.zeros((n, d)), np.zeros((n, 2))
+        meta, cmap, F = np.zeros((n, 8), np.int32), np.zeros((n, MAXM), np.uint8), np.zeros(n, np.int32)
+        csmap = np.zeros((n, MAXM), np.int8)
+        self.lib.mce_debug_muc_shape(self.h, m, ct.byref(n := ct.c_int(0)), _dp(A), _dp(p), _dp(q), _dp(b), _dp(cd),
+                                     meta.ctypes.data_as(ct.POINTER(ct.c_int)), cmap.ctypes.data_as(ct.POINTER(ct.c_uint8)), csmap.ctypes.data_as(ct.POINTER(ct.c_int8)),
+                                     F.ctypes.data_as(ct.POINTER(ct.c_int)))
+        return dict(A=A, p=p, q=q, b=b, cd=cd, meta=meta, cmap=cmap, csmap=csmap, F=F)
+
+
+def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None):
+    """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
+    s = Session(lib, sc)
+    out = {}
+    d = sc.d
+    MS = s.shape_range - 1
+    try:
+        if capture:
+            lib.mce_debug_capture(s.h, 1)
+        nrec = len(sc.rec) if max_steps is None else min(max_steps, len(sc.rec))
+        for k in range(nrec):
+            r = sc.rec[k]
+            sp = "s%d" % (k + 1)
+            first = k == 0
+            with_tp = (k % sc.p) == 0 and not first
+            err = s.step(r)
+            mo = s.moments()
+            st = s.stats()
+            out[sp + "/info"] = np.array([int(with_tp), mo.skip_post_mu, mo.Nt_after_muc, mo.Nt, err, int(first)], np.int32)
+            out[sp + "/muc/counts"] = s.counts(True)
+            mom = np.zeros(1 + d + d * d, np.complex128)
+            mom[0] = complex(mo.fz[0], mo.fz[1]) if first else complex(mo.fz_after_mu[0], mo.fz_after_mu[1])  # ref_run can only see fz = 1 after step 1
+            mom[1 : 1 + d] = np.array(mo.mean[: 2 * d]).view(np.complex128)
+            mom[1 + d :] = np.array(mo.cov[: 2 * d * d]).view(np.complex128)
+            out[sp + "/moments"] = mom
+            out[sp + "/gscale"] = np.array([mo.g_scale_factor])
+            out[sp + "/stats"] = np.array([st.ms_total, st.ms_tp, st.ms_mu, st.ms_moments, st.ms_regroup, st.ms_ftr, st.ms_gtable, st.ms_compact,
+                                           st.ftr_rounds_max, st.diag_unmodelled_alias, st.diag_hash_overflow, st.kernel_launches])
+            full = (k + 1) <= full_upto
+            if not mo.skip_post_mu:
+                cnt = s.counts(False)
+                out[sp + "/ftr/counts"] = cnt
+                for m in range(1, s.shape_range):
+                    if cnt[m] <= 0:
+                        continue
+                    e = s.export_shape(m)
+                    pre = "%s/ftr/m%d" % (sp, m)
+                    out[pre + "/digest"] = key_digest(e["cells"], e["keys"])
+                    out[pre + "/fdigest"] = np.array([np.abs(e["G"]).sum(), e["p"].sum(), np.abs(e["b"]).sum()])
+                    if full:
+                        for nm in ("A", "p", "b", "cells", "keys", "G"):
+                            out[pre + "/" + nm] = e[nm]
+                        out[pre + "/encB"] = e["keys"].astype(np.int32)
+                if full and capture and not first:
+                    mc = s.counts(True)
+                    for m in range(1, s.shape_range):
+                        if mc[m] <= 0:
+                            continue
+                        c = s.debug_muc_shape(m)
+                        if c is None:
+                            continue
+                        pre = "%s/muc/m%d" % (sp, m)
+                        for nm in ("A", "p", "q", "b", "cd", "meta", "F"):
+                            out[pre + "/" + nm] = c[nm]
+                        cm = np.full((c["cmap"].shape[0], MS), 255, np.uint8)
+                        cm[:, : min(MS, MAXM)] = c["cmap"][:, :MS]
+                        out[pre + "/cmap"] = cm
+                        out[pre + "/csmap"] = np.ascontiguousarray(c["csmap"][:, :MS])
+            if on_step:
+                on_step(k + 1, s, out)
+            if r.shift_kind == SHIFT_EXPLICIT and shift_mode == "recorded":
+                s.shift_b(r.delta, -1.0)
+            elif r.shift_kind in (SHIFT_OWN_MEAN, SHIFT_EXPLICIT):
+                s.shift_b(np.array(mo.mean[: 2 * d])[0::2], -1.0)
+    finally:
+        s.close()
+    return out
+
+
+def oracle_dump(scenario_path, out_path, full_upto=0, max_steps=None, use_ref=False):
+    """Runs the C oracle (or the compiled reference) on a scenario file and reads its dump."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_run_cpu1") if use_ref else os.path.join(ROOT, "oracle", "_build", "mce_oracle_run")
+    cmd = [exe, scenario_path, out_path, "--full-upto", str(full_upto)]
+    if max_steps is not None:
+        cmd += ["--max-steps", str(max_steps)]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
+    return read_dump(out_path)

@@ -1,0 +1,34 @@
+"""CPU-only logic test of the kernel bodies: the sequential emulation backend (tests/emu, test infrastructure) runs
+the same mce_kern_*.h code the GPU runs and must reproduce the reference's golden dumps bit for bit.  This does not
+replace the `-m gpu` parity tests; it catches logic regressions on machines without a GPU."""
+import os
+
+import pytest
+
+from compare import compare_dumps
+from harness import ROOT, load_emu, run_scenario
+from mceio import read_dump, read_scenario
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CASES = {"lti3": (8, 5), "lti2": (10, 6), "lti4": (6, 4), "lti3_3msmts": (12, 7), "lti4_2pnoise": (5, 3), "lti4_2msmts": (9, 5),
+         "syn2": (12, 3), "syn3": (8, 3), "syn5": (5, 3), "syn7": (4, 2), "syn8": (4, 2), "leo7": (6, 3)}
+
+
+def _upto(d, k):
+    return {n: v for n, v in d.items() if n == "header" or int(n.split("/")[0][1:]) <= k}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return load_emu(rebuild=True)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_emulated_kernels_match_golden(emu, name):
+    steps, full = CASES[name]
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
+    got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True)
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
+    assert not probs, "\n".join(probs[:20])

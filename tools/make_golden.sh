@@ -1,0 +1,20 @@
+#!/bin/sh
+# Regenerates the golden dumps under tests/golden/ by running the UNMODIFIED reference (oracle/_ref/ref_run_cpu1,
+# built from /root/reference by `make -C oracle ref`) on every committed scenario.  Full term/table dumps are kept
+# for the first few steps only (small files); later steps carry per-shape counts, key digests and moments.
+set -e
+cd "$(dirname "$0")/.."
+python tools/gen_scenarios.py tests/golden
+[ -f tests/golden/leo7.mces ] || oracle/_ref/ref_gen_leo7 tests/golden/leo7.mces 4
+R=oracle/_ref/ref_run_cpu1
+$R tests/golden/lti3.mces         tests/golden/lti3.ref.mced         --full-upto 5
+$R tests/golden/lti2.mces         tests/golden/lti2.ref.mced         --full-upto 6
+$R tests/golden/lti4.mces         tests/golden/lti4.ref.mced         --full-upto 4
+$R tests/golden/lti3_3msmts.mces  tests/golden/lti3_3msmts.ref.mced  --full-upto 7
+$R tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.ref.mced --full-upto 3
+$R tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.ref.mced  --full-upto 5
+for n in 2 3 4 5 6 7 8; do $R tests/golden/syn$n.mces tests/golden/syn$n.ref.mced --full-upto 3; done
+$R tests/golden/leo7.mces         tests/golden/leo7.ref.mced         --full-upto 3
+# the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
+oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
+ls -la tests/golden
