@@ -1,0 +1,265 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 MCE term-propagation path.
+
+Metric (BASELINE.json): child terms/s (and ms per MCE step) on the 7-state LEO GPS sliding-window estimator
+(configs[3]: d=7, 3 GPS measurements per time step, 4 time steps = 12 measurement updates, replayed open-loop
+from tests/golden/leo7.mces, which records the reference example src/leo_satellite_7state_gps.cpp).
+
+One bench *step* = one full pass of that 12-MU window through CauchyEstimator::step() on a fresh estimator
+(mce_reset between passes): 2.0 M child terms are generated and globally de-duplicated per pass.
+  value  : child terms / s, device time (CUDA events on the engine's stream, summed over the 12 step() calls)
+  e2e    : same metric, wall clock around the reference-facing C-ABI calls with HOST buffers (every step() call
+           uploads Phi/Gamma/H/... and downloads the moment sums; nothing is cached between passes)
+  N > 1  : one independent window per GPU (the reference's SlidingWindowManager runs one estimator process per
+           window, cauchy_windows.hpp:353-376), aggregate child terms/s, max-over-ranks time.  scaling = "weak".
+--impl reference times the reference's own CPU implementation (oracle/_ref/ref_run_cpu8, the unmodified
+reference compiled with its default NUM_CPUS = 8) on a bounded prefix of the same window.
+"""
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+SCEN = os.path.join(ROOT, "tests", "golden", "leo7.mces")
+WORKLOAD = "leo7_gps_d7_p3_window4 (12 MUs, tests/golden/leo7.mces)"
+METRIC = "child_terms_per_sec"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                              timeout=5).decode().strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if "Active" in v and "Not" not in v:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def _parse_ref_lines(text):
+    rows = []
+    for m in re.finditer(r"step (\d+): after MUC (\d+), after FTR (\d+), ([0-9.]+) ms", text):
+        rows.append((int(m.group(1)), int(m.group(2)), int(m.group(3)), float(m.group(4))))
+    return rows
+
+
+def _child_terms(rows):
+    """child terms of MU k = terms after MUC - terms that entered the step (previous after-FTR count)."""
+    tot, prev = 0, 1
+    for _, muc, ftr, _ in rows:
+        tot += muc - prev
+        prev = ftr
+    return tot
+
+
+def run_reference_sample(n_mu):
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_run_cpu8")
+    kind = "reference"
+    if not os.path.exists(exe):
+        exe = os.path.join(ROOT, "oracle", "_build", "mce_oracle_run")
+        kind = "port"
+        if not os.path.exists(exe):
+            subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    t0 = time.time()
+    out = subprocess.check_output([exe, SCEN, "--time-only", "--max-steps", str(n_mu)], stderr=subprocess.DEVNULL).decode()
+    wall = time.time() - t0
+    rows = _parse_ref_lines(out)
+    step_ms = sum(r[3] for r in rows)
+    return kind, rows, step_ms, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    # size the sample so that (steps + warmup) passes end within a few minutes: MU k costs about 2.2x MU k-1
+    budget_s = 150.0 / max(1, args.steps + args.warmup)
+    kind, rows, ms, _ = run_reference_sample(8)
+    n_mu = 8
+    est = ms / 1e3
+    while n_mu < 11 and est * 3.2 <= budget_s:      # predicted cumulative cost of one more MU
+        est *= 3.2
+        n_mu += 1
+    for _ in range(args.warmup):
+        run_reference_sample(n_mu)
+    tot_ms, tot_child = 0.0, 0
+    for _ in range(args.steps):
+        kind, rows, ms, _ = run_reference_sample(n_mu)
+        tot_ms += ms
+        tot_child += _child_terms(rows)
+    value = tot_child / (tot_ms / 1e3)
+    cores = 8 if kind == "reference" else 1
+    sample = "MUs 1..%d of the 12-MU window per step (%d child terms), %s" % (
+        n_mu, tot_child // max(1, args.steps), "unmodified reference, NUM_CPUS=8 pthreads" if kind == "reference" else "plain-C oracle port, 1 thread")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "child terms/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_mus": n_mu},
+            "cpu_baseline": {"value": value, "unit": "child terms/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "child terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    from harness import Session, load_product
+    from mceio import SHIFT_EXPLICIT, read_scenario
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = load_product()
+    sc = read_scenario(SCEN)
+    s = Session(lib, sc, device=local_rank)
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def one_pass(collect):
+        ev_ms, wall0, rows, gt_ms, gt_bytes, gt_launch, h2d, d2h, launches, phases = 0.0, time.perf_counter(), [], 0.0, 0, 0, 0, 0, 0, None
+        prev = 1
+        child = 0
+        heaviest = (0.0, 0)
+        for k, r in enumerate(sc.rec):
+            s.step(r)
+            st = s.stats()
+            ev_ms += st.ev_step_ms
+            child += st.terms_after_muc - prev
+            prev = st.survivors if k + 1 < len(sc.rec) else st.terms_after_muc
+            gt_ms += st.ev_gtable_ms
+            gt_bytes += st.bytes_gtable_algorithmic
+            gt_launch += st.gtable_launches
+            launches += st.kernel_launches
+            d = sc.d
+            h2d += 8 * (2 + d * d + d * sc.pncc + sc.pncc + d)      # msmt, gamma, Phi, Gamma, beta, H
+            d2h += 16 * (1 + d + d * d) + 8 * 66                   # moment sums + per-shape counters
+            if st.ev_step_ms > heaviest[0]:
+                heaviest = (st.ev_step_ms, k + 1, st.terms_after_muc, st.survivors)
+            if r.shift_kind == SHIFT_EXPLICIT:
+                s.shift_b(r.delta, -1.0)
+        mo = s.moments()
+        wall = time.perf_counter() - wall0
+        lib.mce_reset(s.h)
+        return dict(ev_ms=ev_ms, wall_s=wall, child=child, gt_ms=gt_ms, gt_bytes=gt_bytes, gt_launch=gt_launch, h2d=h2d, d2h=d2h,
+                    launches=launches, heaviest=heaviest, Nt=mo.Nt)
+
+    for _ in range(max(3, args.warmup)):
+        one_pass(False)
+        l2_flush.fill_(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t_region0 = time.perf_counter()
+    acc = []
+    for _ in range(args.steps):
+        l2_flush.fill_(1)                      # L2 flush between timed iterations
+        torch.cuda.synchronize()
+        acc.append(one_pass(True))
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    region_s = time.perf_counter() - t_region0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    ev_s = sum(a["ev_ms"] for a in acc) / 1e3
+    wall_s = sum(a["wall_s"] for a in acc)
+    child = sum(a["child"] for a in acc)
+    if dist:
+        t = torch.tensor([ev_s, wall_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ev_s, wall_s = float(t[0]), float(t[1])
+        c = torch.tensor([child], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        child = int(c[0])
+    if rank == 0:
+        peaks, which = _peaks()
+        a0 = acc[-1]
+        gt_ms_per_launch = sum(a["gt_ms"] for a in acc) / max(1, sum(a["gt_launch"] for a in acc))
+        gt_bytes_per_launch = sum(a["gt_bytes"] for a in acc) / max(1, sum(a["gt_launch"] for a in acc))
+        achieved = gt_bytes_per_launch / (gt_ms_per_launch * 1e-3) / 1e9 if gt_ms_per_launch > 0 else 0.0
+        traffic = None
+        tf = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tf):
+            try:
+                traffic = json.load(open(tf)).get("gtable_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {"metric": METRIC, "value": child / ev_s, "unit": "child terms/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "child_terms_per_step": child // (args.steps * world), "mus_per_step": len(sc.rec),
+                           "ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
+                           "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
+                           "parallelism": "window-per-gpu x%d" % world, "l2": "flushed between timed iterations (256 MiB fill)",
+                           "moments": "reference serial order (bit-exact)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
+                "e2e": {"value": child / wall_s, "unit": "child terms/s", "h2d_bytes_per_step": a0["h2d"], "d2h_bytes_per_step": a0["d2h"]},
+                "gpu_launches": int(sum(a["launches"] for a in acc)),
+                "clocks": sampler.summary(),
+                "roofline": {"bound": "hbm", "kernel": "KGTable (child B-table + G-table build per reduction group)", "achieved": achieved,
+                             "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                             "traffic": traffic, "bytes_per_launch_algorithmic": gt_bytes_per_launch, "ms_per_launch": gt_ms_per_launch},
+                "timed_region_wall_s": region_s}
+        # CPU baseline: the reference itself on this box's host cores, bounded sample (MUs 1..9 of the same window)
+        if world == 1 and not args.no_cpu_baseline:
+            kind, rows, ms, _ = run_reference_sample(9)
+            cb = _child_terms(rows) / (ms / 1e3)
+            line["cpu_baseline"] = {"value": cb, "unit": "child terms/s", "cores": 8 if kind == "reference" else 1, "kind": kind,
+                                    "sample": "MUs 1..9 of the 12-MU window (%d child terms, %.1f s of step() time), %s" % (
+                                        _child_terms(rows), ms / 1e3, "unmodified reference NUM_CPUS=8" if kind == "reference" else "plain-C oracle, 1 thread")}
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        gpu_arm(a)

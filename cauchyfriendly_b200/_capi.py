@@ -22,7 +22,9 @@ class MceStepStats(ct.Structure):
     _fields_ = [(n, ct.c_double) for n in ("ms_total", "ms_tp", "ms_mu", "ms_moments", "ms_regroup", "ms_ftr", "ms_gtable", "ms_compact")] + \
                [(n, ct.c_longlong) for n in ("parents", "slots", "terms_after_muc", "groups", "survivors", "bytes_gtable_algorithmic",
                                              "bytes_step_algorithmic", "kernel_launches")] + \
-               [(n, ct.c_int) for n in ("ftr_rounds_max", "diag_unmodelled_alias", "diag_hash_overflow")]
+               [("ftr_rounds_max", ct.c_int), ("diag_unmodelled_alias", ct.c_int), ("diag_hash_overflow", ct.c_int),
+                ("ev_step_ms", ct.c_double), ("ev_gtable_ms", ct.c_double), ("gtable_launches", ct.c_longlong),
+                ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong)]
 
 
 # every symbol include/mce_b200.h declares

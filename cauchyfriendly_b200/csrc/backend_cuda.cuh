@@ -56,6 +56,7 @@ struct CudaBackend {
   void shutdown() {
     if (cub_tmp) cudaFree(cub_tmp);
     cub_tmp = nullptr; cub_tmp_bytes = 0;
+    for (int i = 0; i < 8; i++) if (evs[i]) { cudaEventDestroy(evs[i]); evs[i] = nullptr; }
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -80,6 +81,18 @@ struct CudaBackend {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
   }
   double toc(double t0) { return tic() - t0; }
+  // device-side timing with CUDA events on the launching stream (no host synchronisation until ev_elapsed)
+  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void ev_record(int i) {
+    if (!evs[i]) MCE_CUDA_CHECK(cudaEventCreate(&evs[i]));
+    MCE_CUDA_CHECK(cudaEventRecord(evs[i], stream));
+  }
+  double ev_elapsed(int i0, int i1) {
+    float ms = 0;
+    MCE_CUDA_CHECK(cudaEventSynchronize(evs[i1]));
+    MCE_CUDA_CHECK(cudaEventElapsedTime(&ms, evs[i0], evs[i1]));
+    return ms;
+  }
 
   template <class K>
   void launch(const K& k, int nblocks, int nthreads, size_t smem) {

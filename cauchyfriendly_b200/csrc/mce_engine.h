@@ -29,6 +29,8 @@ struct StepStats {
   long long parents = 0, slots = 0, terms_after_muc = 0, groups = 0, survivors = 0;
   long long bytes_gtable = 0, bytes_step = 0, launches = 0;
   int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
+  double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0;   // CUDA-event durations on the stream
+  long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0;
 };
 
 template <class BE>
@@ -100,6 +102,7 @@ class Engine {
   struct GenStore {
     GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G;
     std::vector<int> alive_per_shape;   // survivors per shape
+    long long sum_cells = 0;            // total table cells of the survivors
   } gen[2];
   int cur = 0;
   DevBuf<BE> wsA, wsp, wsb, wsm, wsSgn, wsXor, wsTpB, wsTpBc;
@@ -257,8 +260,11 @@ class Engine {
     skip_post_mu = (master_step == num_estimation_steps - 1);                               // SKIP_LAST_STEP, est:1229
     stats = StepStats();
     double t0 = be.tic();
+    be.ev_record(0);
     int rc = (master_step == 0) ? step_first(msmt, H, gamma) : step_general(msmt, Phi, Gamma, beta, H, gamma, B, u);
     if (rc < 0) return rc;
+    be.ev_record(1);
+    stats.ev_step_ms = be.ev_elapsed(0, 1);
     stats.ms_total = be.toc(t0);
     stats.launches = be.launch_count; be.launch_count = 0;
     master_step++;
@@ -285,7 +291,7 @@ class Engine {
     finalize_moments(raw.data(), false);        // compute_moments(true): no numerical check on the first step (quirk A.9 iv)
     ng.v.n_alive = nt;
     std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0); ng.alive_per_shape[d] = nt;
-    Nt = nt; Nt_muc = nt;
+    Nt = nt; Nt_muc = nt; ng.sum_cells = (long long)nt << (d - 1);
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = nt; muc_per_shape = terms_per_shape;
     if (!print_basic_info) fz = make_cplx(1, 0);       // est:1198-1204
     last_mean = mean; last_var = var; last_fz = fz;
@@ -364,11 +370,11 @@ class Engine {
     if (fast_moments) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
-      be.launch(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 32, 0);     // d = 0: only fz, in serial order
+      be.launch(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
       be.launch(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
       be.launch(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
     } else {
-      be.launch(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, 1, ((2 * nq + 31) / 32) * 32, 0);
+      be.launch(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
 
     // ---- canonical ranks of the new terms inside their new shapes ----
@@ -480,6 +486,7 @@ class Engine {
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
     const size_t gsm = KGTable::smem_bytes(HC2);
     long long total_groups = 0;
+    be.ev_record(2);
     for (int phase = 0; phase < 2; phase++)
       for (int m = 1; m < NSHAPE; m++) {
         if (n_groups[m] == 0) continue;
@@ -490,7 +497,10 @@ class Engine {
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
         KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
         be.launch(k, g1 - g0, nth, gsm);
+        stats.gtable_launches++;
       }
+    be.ev_record(3);
+    stats.ev_gtable_ms = be.ev_elapsed(2, 3);
     stats.groups = total_groups;
     stats.ms_gtable = be.toc(tph); tph = be.tic();
 
@@ -516,6 +526,7 @@ class Engine {
     ng.v.n_alive = n_surv;
     int hd[16]; be.d2h(hd, diag, sizeof(int) * 4);
     stats.diag_alias = hd[0]; stats.diag_hash = hd[1];
+    stats.cells_parents = pg.sum_cells; ng.sum_cells = (long long)(unsigned)hd[2] | ((long long)hd[3] << 32); stats.cells_survivors = ng.sum_cells;
     stats.survivors = n_surv;
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0);
     for (int m = 1; m < shape_range; m++) terms_per_shape[m] = ng.alive_per_shape[m];
@@ -523,18 +534,19 @@ class Engine {
     cur = 1 - cur;
     if (!print_basic_info) fz = make_cplx(1, 0);           // est:1172-1176
     stats.ms_compact = be.toc(tph);
-    // algorithmic bytes: parents (term + G/B tables), post-MUC payload written + read, survivors written
+    // algorithmic bytes with the ACTUAL table sizes: every compulsory input read once, every output
+    // written once, the post-MUC term payload written + read once (FTR is a global barrier). A table cell is
+    // 4 B key + 16 B complex value in this layout (the reference's padded KeyCValue + B entry is 28 B).
     {
-      long long bytes = 0, bg = 0;
+      long long term_in = 0, payload = 0, term_out = 0;
       for (int m = 1; m < NSHAPE; m++) {
-        const long long H = cell_count_central_half(m, d);
-        bytes += (long long)pg.alive_per_shape[m] * (8LL * (m * d + m + d) + 28LL * H);
-        bytes += 2LL * tv.n[m] * (8LL * (m * d + 2 * m + d) + 2 * m);
-        bytes += (long long)ng.alive_per_shape[m] * (28LL * H + 8LL * (m * d + m + d));
-        bg += (long long)pg.alive_per_shape[m] * 28LL * H + (long long)tv.n[m] * (8LL * (m * d + 2 * m + d) + 2 * m) +
-              (long long)ng.alive_per_shape[m] * (28LL * H + 8LL * (m * d + m + d));
+        term_in += (long long)pg.alive_per_shape[m] * 8LL * (m * d + m + d);
+        payload += (long long)tv.n[m] * (8LL * (m * d + 2 * m + d) + 2 * m);
+        term_out += (long long)ng.alive_per_shape[m] * 8LL * (m * d + m + d);
       }
-      stats.bytes_step = bytes; stats.bytes_gtable = bg;
+      const long long tab_in = 20LL * stats.cells_parents, tab_out = 20LL * stats.cells_survivors;
+      stats.bytes_step = term_in + tab_in + 2 * payload + term_out + tab_out;
+      stats.bytes_gtable = tab_in + payload + term_out + tab_out;     // what the group kernel itself must move
     }
     return 0;
   }

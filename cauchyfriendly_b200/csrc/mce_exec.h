@@ -34,6 +34,7 @@ struct DevCtx {
   }
   __device__ __forceinline__ int atomic_add(int* p, int v) { return atomicAdd(p, v); }
   __device__ __forceinline__ unsigned atomic_xor(unsigned* p, unsigned v) { return atomicXor(p, v); }
+  __device__ __forceinline__ unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { return atomicAdd(p, v); }
   __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
   __device__ __forceinline__ unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
   __device__ __forceinline__ int load_relaxed(const int* p) { return *(const volatile int*)p; }

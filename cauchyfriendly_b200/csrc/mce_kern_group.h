@@ -468,7 +468,10 @@ struct KGTable {
       for (int i = tid; i < m * d; i += c.nthreads()) Ao[i] = As[i];
       for (int i = tid; i < m; i += c.nthreads()) po[i] = ps[i];
       for (int i = tid; i < d; i += c.nthreads()) bo[i] = bs[i];
-      if (tid == 0) { alive_flag[gid_out] = 1; next.cells[gid_out] = nB; next.g_m[gid_out] = (unsigned char)m; }
+      if (tid == 0) {
+        alive_flag[gid_out] = 1; next.cells[gid_out] = nB; next.g_m[gid_out] = (unsigned char)m;
+        c.atomic_add_u64((unsigned long long*)(diag + 2), (unsigned long long)nB);   // total cells of the new generation
+      }
     });
   }
 };

@@ -278,34 +278,77 @@ struct KMsmtUpdate {
 // normaliser 1/(2 pi Re fz) scales every new G and hence every term-approximation decision);
 // mean / covariance sums use a fixed-shape two-level reduction (deterministic; parity bar 1e-9).
 // ---------------------------------------------------------------------------------------------
-// Serial-order sums of all 1 + d + d*d complex moment accumulators: real accumulator q2 = 2*q + part is owned
-// by thread q2 and adds its addend for slot 0, 1, 2, ... in slot order, which is the order of the reference's
-// cache_moments loop (parents in shape/index order, each followed by its children).  The addends are computed
-// exactly as est:318-325 does: fz += g; mean_j += g*y_j; cov_jk -= (g*y_j)*y_k.  Unused slots hold g = y = 0
-// and leave every accumulator unchanged, so the sums are bit-identical to the NUM_CPUS = 1 reference.
+// Serial-order sums of all 1 + d + d*d complex moment accumulators.  The addends are computed exactly as
+// est:318-325 does -- fz += g; mean_j += g*y_j; cov_jk -= (g*y_j)*y_k -- and every real accumulator adds them for
+// slot 0, 1, 2, ... in slot order, the order of the reference's cache_moments loop (parents in shape/index order,
+// each followed by its children).  Unused slots hold g = y = 0 and leave the accumulators unchanged, so the sums
+// are bit-identical to the NUM_CPUS = 1 reference.
+// Layout: block b owns MOM_QB complex quantities; warp 0 keeps their 2*MOM_QB running sums (one lane each) and
+// walks the slots serially.  The other warps run a two-stage software pipeline ahead of it: while warp 0 sums
+// tile t they compute the addends of tile t+1 from a shared-memory copy of (g, y) and stage the raw (g, y) of
+// tile t+2 from HBM with coalesced loads.  The serial DADD chain of warp 0 is the critical path.
+constexpr int MOM_QB = 16, MOM_TILE = 256;
 struct KMomentsSerial {
   const cplx* g; const double* y; long long n; int d; double* out /*[2*(1+d+d*d)]*/;
+  static MCE_HD size_t smem_bytes(int d) { return sizeof(double) * (2 * MOM_QB + 2 * MOM_TILE * 2 * MOM_QB + 2 * MOM_TILE * (2 + 2 * d)); }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    c.par([&](int tid) {
-      const int nq = 1 + d + d * d;
-      if (tid >= 2 * nq || c.block() != 0) return;
-      const int q = tid >> 1, part = tid & 1;
-      const int j = q == 0 ? 0 : (q <= d ? q - 1 : (q - 1 - d) / d), k = q <= d ? 0 : (q - 1 - d) % d;
-      double acc = 0;
-      for (long long i = 0; i < n; i++) {
-        const cplx gv = g[i];
-        double v;
-        if (q == 0) v = part ? gv.im : gv.re;
-        else {
-          const double* yy = y + i * 2 * d;
-          cplx w = cmul(gv, make_cplx(yy[2 * j], yy[2 * j + 1]));
-          if (q > d) w = cmul(w, make_cplx(yy[2 * k], yy[2 * k + 1]));
-          v = part ? w.im : w.re;
+    const int nq = 1 + d + d * d, qbase = c.block() * MOM_QB, NA = 2 * MOM_QB, W = 2 + 2 * d;
+    double* accs = (double*)c.smem();
+    double* buf = accs + NA;                          // [2][MOM_TILE][NA]  addends
+    double* raw = buf + 2 * MOM_TILE * NA;            // [2][MOM_TILE][W]   (g.re, g.im, y[0..2d))
+    const long long ntiles = (n + MOM_TILE - 1) / MOM_TILE;
+    auto tile_cnt = [&](long long t) { const long long s0 = t * MOM_TILE; return (int)((n - s0) < MOM_TILE ? (n - s0) : MOM_TILE); };
+    auto stage = [&](long long t, int lane, int nlanes) {            // HBM -> raw[t & 1]
+      const long long s0 = t * MOM_TILE; const int cnt = tile_cnt(t);
+      double* rt = raw + (t & 1) * MOM_TILE * W;
+      const double* gs = (const double*)(g + s0); const double* ys = y + s0 * 2 * d;
+      for (int e = lane; e < cnt * 2; e += nlanes) rt[(e >> 1) * W + (e & 1)] = gs[e];
+      for (int e = lane; e < cnt * 2 * d; e += nlanes) rt[(e / (2 * d)) * W + 2 + (e % (2 * d))] = ys[e];
+    };
+    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t & 1] -> buf[t & 1]
+      const int cnt = tile_cnt(t);
+      const double* rt = raw + (t & 1) * MOM_TILE * W;
+      double* bt = buf + (t & 1) * MOM_TILE * NA;
+      for (int it = lane; it < cnt * MOM_QB; it += nlanes) {
+        const int sidx = it / MOM_QB, ql = it % MOM_QB, q = qbase + ql;
+        cplx w = make_cplx(0, 0);
+        if (q < nq) {
+          const double* row = rt + sidx * W;
+          const cplx gv = make_cplx(row[0], row[1]);
+          if (q == 0) w = gv;
+          else {
+            const int j = q <= d ? q - 1 : (q - 1 - d) / d;
+            w = cmul(gv, make_cplx(row[2 + 2 * j], row[3 + 2 * j]));
+            if (q > d) { const int k = (q - 1 - d) % d; w = cmul(w, make_cplx(row[2 + 2 * k], row[3 + 2 * k])); w.re = -w.re; w.im = -w.im; }
+          }
         }
-        if (q > d) acc -= v; else acc += v;
+        bt[sidx * NA + 2 * ql] = w.re; bt[sidx * NA + 2 * ql + 1] = w.im;
       }
-      out[tid] = acc;
-    });
+    };
+    c.par([&](int tid) { if (tid < NA) accs[tid] = 0; else if (ntiles > 0) stage(0, tid - NA, c.nthreads() - NA); });
+    c.par([&](int tid) { if (tid >= NA) { if (ntiles > 0) produce(0, tid - NA, c.nthreads() - NA); if (ntiles > 1) stage(1, tid - NA, c.nthreads() - NA); } });
+    for (long long t = 0; t < ntiles; t++) {
+      c.par([&](int tid) {
+        if (tid < NA) {
+          const int cnt = tile_cnt(t);
+          const double* bt = buf + (t & 1) * MOM_TILE * NA + tid;
+          double acc = accs[tid];
+          int sidx = 0;
+          for (; sidx + 8 <= cnt; sidx += 8) {
+            const double v0 = bt[(sidx + 0) * NA], v1 = bt[(sidx + 1) * NA], v2 = bt[(sidx + 2) * NA], v3 = bt[(sidx + 3) * NA];
+            const double v4 = bt[(sidx + 4) * NA], v5 = bt[(sidx + 5) * NA], v6 = bt[(sidx + 6) * NA], v7 = bt[(sidx + 7) * NA];
+            acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+          }
+          for (; sidx < cnt; sidx++) acc += bt[sidx * NA];
+          accs[tid] = acc;
+        } else {
+          // order matters for the shared buffers: produce(t+1) reads raw[(t+1)&1], stage(t+2) then overwrites raw[t&1]
+          if (t + 1 < ntiles) produce(t + 1, tid - NA, c.nthreads() - NA);
+          if (t + 2 < ntiles) stage(t + 2, tid - NA, c.nthreads() - NA);
+        }
+      });
+    }
+    c.par([&](int tid) { if (tid < NA && qbase * 2 + tid < 2 * nq) out[qbase * 2 + tid] = accs[tid]; });
   }
 };
 

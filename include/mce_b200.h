@@ -98,6 +98,10 @@ typedef struct mce_step_stats {
   long long kernel_launches;
   int ftr_rounds_max;
   int diag_unmodelled_alias, diag_hash_overflow;
+  double ev_step_ms;                    /* CUDA-event time of the whole step on the engine's stream            */
+  double ev_gtable_ms;                  /* CUDA-event time of the group (B-table + G-table) kernel launches     */
+  long long gtable_launches;
+  long long cells_parents, cells_survivors;   /* actual table cells read / written by the group kernel          */
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 

@@ -28,6 +28,7 @@ struct EmuCtx {
   template <class T> T uniform(const T& v) { return v; }
   int atomic_add(int* p, int v) { int o = *p; *p += v; return o; }
   unsigned atomic_xor(unsigned* p, unsigned v) { unsigned o = *p; *p ^= v; return o; }
+  unsigned long long atomic_add_u64(unsigned long long* p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
   unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
   unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
   int load_relaxed(const int* p) { return *p; }
@@ -45,6 +46,9 @@ struct EmuBackend {
   void memset(void* p, int v, size_t n) { ::memset(p, v, n); }
   double tic() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
   double toc(double t0) { return tic() - t0; }
+  double ev_t[8] = {0};
+  void ev_record(int i) { ev_t[i] = tic(); }
+  double ev_elapsed(int i0, int i1) { return ev_t[i1] - ev_t[i0]; }
   template <class K> void launch(const K& k, int nblocks, int nthreads, size_t smem) {
     launch_count++;
     std::vector<unsigned char> sm(smem + 64, 0xCD);

@@ -37,13 +37,15 @@ def load_product():
 
 
 class Session:
-    def __init__(self, lib, sc, print_basic_info=False):
+    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False):
         self.lib, self.sc = lib, sc
         o = MceOptions()
         lib.mce_default_options(ct.byref(o))
         for i in range(12):
             o.tr_search_order[i] = sc.tr_order[i]
         o.print_basic_info = int(print_basic_info)
+        o.device = int(device)
+        o.fast_moments = int(fast_moments)
         self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
         self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
         if not self.h:
