@@ -13,6 +13,7 @@
 
 #include "mce_kern_ftr.h"
 #include "mce_kern_group.h"
+#include "mce_kern_group2.h"
 #include "mce_kern_prop.h"
 
 namespace mce {
@@ -495,8 +496,14 @@ class Engine {
         total_groups += g1 - g0;
         const int Hm = cell_count_central_half(m, d);
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
-        KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
-        be.launch(k, g1 - g0, nth, gsm);
+        if (max_shape <= 16) {
+          const int NW = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
+          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], Hcap, NW, aflag, diag};
+          be.launch(k, g1 - g0, nth, KGTable2::smem_bytes(Hcap, NW));
+        } else {
+          KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
+          be.launch(k, g1 - g0, nth, gsm);
+        }
         stats.gtable_launches++;
       }
     be.ev_record(3);

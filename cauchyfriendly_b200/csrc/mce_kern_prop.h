@@ -298,12 +298,27 @@ struct KMomentsSerial {
     double* raw = buf + 2 * MOM_TILE * NA;            // [2][MOM_TILE][W]   (g.re, g.im, y[0..2d))
     const long long ntiles = (n + MOM_TILE - 1) / MOM_TILE;
     auto tile_cnt = [&](long long t) { const long long s0 = t * MOM_TILE; return (int)((n - s0) < MOM_TILE ? (n - s0) : MOM_TILE); };
-    auto stage = [&](long long t, int lane, int nlanes) {            // HBM -> raw[t & 1]
+    auto stage = [&](long long t, int lane, int nlanes) {            // HBM -> raw[t & 1]: 16-byte loads, all issued before the first store
       const long long s0 = t * MOM_TILE; const int cnt = tile_cnt(t);
       double* rt = raw + (t & 1) * MOM_TILE * W;
-      const double* gs = (const double*)(g + s0); const double* ys = y + s0 * 2 * d;
-      for (int e = lane; e < cnt * 2; e += nlanes) rt[(e >> 1) * W + (e & 1)] = gs[e];
-      for (int e = lane; e < cnt * 2 * d; e += nlanes) rt[(e / (2 * d)) * W + 2 + (e % (2 * d))] = ys[e];
+      const cplx* gs = g + s0; const cplx* ys = (const cplx*)(y + s0 * 2 * d);   // y rows are d (re, im) pairs; 16-byte aligned
+      const int nvec = cnt * (1 + d);
+      cplx v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { const int e = lane + u * nlanes; if (e < nvec) v[u] = e < cnt ? gs[e] : ys[e - cnt]; }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = lane + u * nlanes;
+        if (e < nvec) {
+          double* dst = e < cnt ? rt + e * W : rt + ((e - cnt) / d) * W + 2 + 2 * ((e - cnt) % d);
+          dst[0] = v[u].re; dst[1] = v[u].im;
+        }
+      }
+      for (int e = lane + 8 * nlanes; e < nvec; e += nlanes) {         // only reached with very few staging threads
+        const cplx w = e < cnt ? gs[e] : ys[e - cnt];
+        double* dst = e < cnt ? rt + e * W : rt + ((e - cnt) / d) * W + 2 + 2 * ((e - cnt) % d);
+        dst[0] = w.re; dst[1] = w.im;
+      }
     };
     auto produce = [&](long long t, int lane, int nlanes) {          // raw[t & 1] -> buf[t & 1]
       const int cnt = tile_cnt(t);
