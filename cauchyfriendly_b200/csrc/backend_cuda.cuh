@@ -22,8 +22,12 @@ namespace mce {
       throw std::runtime_error(std::string(#expr) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
   } while (0)
 
+// Kernels may declare `static constexpr int kMaxThreads, kMinBlocks` to bound their register allocation.
+template <class K, class = void> struct launch_traits { static constexpr int max_threads = 1024, min_blocks = 1; };
+template <class K> struct launch_traits<K, decltype((void)K::kMaxThreads)> { static constexpr int max_threads = K::kMaxThreads, min_blocks = K::kMinBlocks; };
+
 template <class K>
-__global__ void mce_kernel_entry(const __grid_constant__ K k) {
+__global__ void __launch_bounds__(launch_traits<K>::max_threads, launch_traits<K>::min_blocks) mce_kernel_entry(const __grid_constant__ K k) {
   extern __shared__ __align__(16) unsigned char mce_dyn_smem[];
   DevCtx c;
   c.smem_ = mce_dyn_smem;

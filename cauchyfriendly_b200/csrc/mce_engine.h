@@ -294,7 +294,7 @@ class Engine {
     std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0); ng.alive_per_shape[d] = nt;
     Nt = nt; Nt_muc = nt; ng.sum_cells = (long long)nt << (d - 1);
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = nt; muc_per_shape = terms_per_shape;
-    if (!print_basic_info) fz = make_cplx(1, 0);       // est:1198-1204
+    if (print_basic_info) post_ftr_moments(sp); else fz = make_cplx(1, 0);       // est:1198-1204
     last_mean = mean; last_var = var; last_fz = fz;
     stats.parents = 1; stats.slots = d + 1; stats.terms_after_muc = nt; stats.groups = nt; stats.survivors = nt;
     return 0;
@@ -539,7 +539,7 @@ class Engine {
     for (int m = 1; m < shape_range; m++) terms_per_shape[m] = ng.alive_per_shape[m];
     Nt = n_surv;
     cur = 1 - cur;
-    if (!print_basic_info) fz = make_cplx(1, 0);           // est:1172-1176
+    if (print_basic_info) post_ftr_moments(sp); else fz = make_cplx(1, 0);           // est:1166-1176 (quirk A.9 iii)
     stats.ms_compact = be.toc(tph);
     // algorithmic bytes with the ACTUAL table sizes: every compulsory input read once, every output
     // written once, the post-MUC term payload written + read once (FTR is a global barrier). A table cell is
@@ -597,6 +597,23 @@ class Engine {
       }
     }
     cap.push_back(std::move(cs));
+  }
+
+  // compute_moments(false), est:524-602: moments of the surviving terms from their new tables; no numeric check.
+  void post_ftr_moments(const StepParams& sp) {
+    GenStore& g = gen[cur];
+    const int n = g.v.n_alive, nq = 1 + d + d * d;
+    if (n == 0) return;
+    cplx* gg = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(n + 8));
+    double* yy = (double*)sly.ensure(sizeof(double) * (size_t)(n + 1) * 2 * d);
+    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    be.launch(KPostFtrMoments{sp, g.v, gg, yy}, (n + 127) / 128, 128, 0);
+    be.launch(KMomentsSerial{gg, yy, (long long)n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
+    std::vector<double> raw(2 * nq);
+    be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
+    const cplx keep = fz_mu;
+    finalize_moments(raw.data(), false);
+    fz_mu = keep;
   }
 
   // ------------------------------------------------------------------------------------------

@@ -19,23 +19,40 @@ namespace mce {
 #define MCE_POPC(x) __popc(x)
 #define MCE_FFS(x) (__ffs((int)(x)) - 1)
 #define MCE_NOINLINE __noinline__
+#define MCE_NOUNROLL _Pragma("unroll 1")
 #else
+#define MCE_NOUNROLL
 #define MCE_POPC(x) __builtin_popcount(x)
 #define MCE_FFS(x) (__builtin_ffs((int)(x)) - 1)
 #define MCE_NOINLINE
 #endif
 
-struct Group2Sm {
-  int nB, flag, cnt, owner, sigma, pad0;
-  int t_m, t_phc, t_pcells, t_z, t_is_child, t_has_cmap;
-  unsigned t_hflag, t_enc_lhp, t_csneg, t_mask;
-  double t_c, t_d, t_psq;
-  const cplx* t_pG;
-  double q[MAXM];
-  unsigned char cmap[MAXM];
-  unsigned char ksrc[MAXM];     // coaligned child: child row feeding parent position k (255 = none)
-  unsigned kflip;               // bit k: flip the sign at parent position k
+constexpr int G2_CHUNK = 32;      // members staged per chunk
+
+struct Group2Member {              // everything the kernel needs to know about one member, gathered in one parallel phase
+  int ti, parent, gidp, phc, pc, own_cells;
+  unsigned hflag, enc_lhp, csneg, mask, kflip;
+  unsigned char z, is_child, has_cmap, pbc;
+  double c, d, psq;
+  unsigned char ksrc[MAXM];
 };
+
+struct Group2Sm {
+  int cnt, owner, pad0, pad1;
+  unsigned sgbits[MAXM];           // per-row orientation bits of the member being staged (update_btable's sigma)
+  int flag[G2_CHUNK];              // per member: some cell is not negligible
+  double q[MAXM];
+  Group2Member mem[G2_CHUNK];
+};
+
+// x with its sign bit xor-ed by `neg` (0 or 1): -x is exact, so this equals `neg ? -x : x`
+MCE_HD double flip_sign(double x, unsigned neg) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double(__double2hiint(x) ^ (int)(neg << 31), __double2loint(x));
+#else
+  union { double d; unsigned long long u; } v; v.d = x; v.u ^= (unsigned long long)neg << 63; return v.d;
+#endif
+}
 
 // rank of `key` among the set bits of bm (pf = exclusive prefix popcounts per word), or -1 when absent
 MCE_HD int bitmap_rank(const unsigned* bm, const unsigned short* pf, unsigned key) {
@@ -45,6 +62,7 @@ MCE_HD int bitmap_rank(const unsigned* bm, const unsigned short* pf, unsigned ke
 }
 
 struct KGTable2 {
+  static constexpr int kMaxThreads = 128, kMinBlocks = 8;   // 64 registers: 8 CTAs (32 warps) per SM
   StepParams sp; GenView prev; GenView next; ParentWs ws; TermView tv;
   int m, g0;
   const int* order; const int* grp_start;
@@ -55,12 +73,18 @@ struct KGTable2 {
     return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + 1024) * sizeof(unsigned short) + 64;
   }
 
-  // ---- bitmap helpers (block-wide) ----
-  template <class Ctx> MCE_KERNEL_FN void bm_zero(Ctx& c, unsigned* bm, int nw) const {
-    c.par([&](int tid) { for (int i = tid; i < nw; i += c.nthreads()) bm[i] = 0; });
-  }
-  template <class Ctx> MCE_KERNEL_FN void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const {
-    // nw is 2^(bits-5): 1..2048 words. Thread t sums a contiguous chunk, then a serial pass over the chunk sums.
+  // exclusive prefix popcounts of a bitmap; *total (may be null) receives the number of set bits
+  template <class Ctx> MCE_KERNEL_FN MCE_NOINLINE void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const {
+    if (nw <= 64) {               // one phase: word w sums the popcounts below it
+      c.par([&](int tid) {
+        if (tid >= nw) return;
+        int s = 0;
+        for (int i = 0; i < tid; i++) s += MCE_POPC(bm[i]);
+        pf[tid] = (unsigned short)s;
+        if (tid == nw - 1 && total) *total = s + MCE_POPC(bm[tid]);
+      });
+      return;
+    }
     const int nt = c.nthreads(), chunk = (nw + nt - 1) / nt;
     c.par([&](int tid) {
       const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
@@ -73,7 +97,7 @@ struct KGTable2 {
       int acc = 0;
       const int nchunks = (nw + chunk - 1) / chunk;
       for (int k = 0; k < nchunks; k++) { const int v = pf[nw + k]; pf[nw + k] = (unsigned short)acc; acc += v; }
-      *total = acc;
+      if (total) *total = acc;
     });
     c.par([&](int tid) {
       const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
@@ -91,87 +115,92 @@ struct KGTable2 {
     *mask = ws.sgnmask[r] ^ ws.bxor[r];
   }
 
-  // Stage term `ti`: scalars, q, coalignment maps, and the rank structure (bmP, pfP) of its parent's table.
-  template <class Ctx> MCE_KERNEL_FN void stage_term(Ctx& c, Group2Sm* sm, unsigned* bmP, unsigned short* pfP, int ti) const {
+  // One thread per member of the chunk: every dependent global load of the member's description happens here, in parallel.
+  MCE_HD void load_member(Group2Member* e, int ti) const {
     const long long gt = tv.t_begin[m] + ti;
     const SlotMeta me = tv.meta[gt];
-    const int gidp = prev.alive[me.parent], phc = gen_m(prev, gidp), pc = prev.cells[gidp];
-    const int nwP = phc >= 5 ? (1 << (phc - 5)) : 1;
-    const unsigned* pk = gen_keys(prev, gidp, phc);
-    c.par([&](int tid) {
-      if (tid == 0) {
-        sm->t_m = m; sm->t_phc = phc; sm->t_pcells = pc; sm->t_z = me.z; sm->t_is_child = me.flags & 1; sm->t_has_cmap = (me.flags >> 1) & 1;
-        sm->t_hflag = me.hflag; sm->t_enc_lhp = me.enc_lhp; sm->t_csneg = me.csneg; sm->t_c = me.c_val; sm->t_d = me.d_val;
-        sm->t_pG = gen_G(prev, gidp, phc);
-        sm->t_mask = ws.sgnmask[me.parent] ^ ws.bxor[me.parent];
-        const double* p = term_p(tv, m, ti);
-        double s = 0; for (int i = 0; i < m; i++) s += p[i];
-        sm->t_psq = s * s;
-        sm->flag = 0;
-        if ((me.flags & 3) == 3) {         // coaligned new child: parent position k <- child row cmap[l], flipped by cs_map[l]
-          const unsigned char* cm = tv.cmap + gt * MAXM;
-          unsigned flip = 0; int k = 0, l = 0;
-          while (k < phc) {
-            if (k == me.z) { sm->ksrc[k] = 255; k++; if (k == phc) break; }
-            sm->ksrc[k] = cm[l]; if ((me.csneg >> l) & 1u) flip |= (1u << k);
-            k++; l++;
-          }
-          sm->kflip = flip;
-        }
+    const int gidp = prev.alive[me.parent], phc = gen_m(prev, gidp);
+    e->ti = ti; e->parent = me.parent; e->gidp = gidp; e->phc = phc; e->pc = prev.cells[gidp];
+    e->own_cells = sp.with_tp ? ws.tpB_cells[me.parent] : e->pc;
+    e->hflag = me.hflag; e->enc_lhp = me.enc_lhp; e->csneg = me.csneg; e->mask = ws.sgnmask[me.parent];   // bxor is read when needed (it can change)
+    e->z = me.z; e->is_child = me.flags & 1; e->has_cmap = (me.flags >> 1) & 1; e->pbc = me.pbc;
+    e->c = me.c_val; e->d = me.d_val;
+    const double* p = term_p(tv, m, ti);
+    double s = 0; for (int i = 0; i < m; i++) s += p[i];       // sum_vec, flat:106-107
+    e->psq = s * s;
+    e->kflip = 0;
+    if ((me.flags & 3) == 3) {         // coaligned new child: parent position k <- child row cmap[l], flipped by cs_map[l] (flat:194-217)
+      const unsigned char* cm = tv.cmap + gt * MAXM;
+      unsigned flip = 0; int k = 0, l = 0;
+      while (k < phc) {
+        if (k == me.z) { e->ksrc[k] = 255; k++; if (k == phc) break; }
+        e->ksrc[k] = cm[l]; if ((me.csneg >> l) & 1u) flip |= (1u << k);
+        k++; l++;
       }
-      if (tid < m) sm->q[tid] = term_q(tv, m, ti)[tid];
-      for (int i = tid; i < nwP; i += c.nthreads()) bmP[i] = 0;
-    });
-    c.par([&](int tid) { for (int i = tid; i < pc; i += c.nthreads()) { const unsigned k = pk[i]; c.atomic_or(&bmP[k >> 5], 1u << (k & 31)); } });
-    int tot;
-    bm_prefix(c, bmP, pfP, nwP, &tot);
+      e->kflip = flip;
+    }
   }
 
+  // Stage member `e`: q, the rank structure (bmP, pfP) of its parent's table, and -- when `ref` >= 0 -- the per-row
+  // orientation bits between term `ref` and this member (ce:586-599).  `pending` is executed by every thread first.
+  template <class Ctx, class Pending> MCE_KERNEL_FN void stage_member(Ctx& c, Group2Sm* sm, const Group2Member* e, unsigned* bmP, unsigned short* pfP, int ref, Pending pending) const {
+    const int phc = e->phc, pc = e->pc;
+    const int nwP = phc >= 5 ? (1 << (phc - 5)) : 1;
+    const unsigned* pk = gen_keys(prev, e->gidp, phc);
+    c.par([&](int tid) {
+      pending(tid);
+      if (tid < m) {
+        sm->q[tid] = ((e->hflag >> tid) & 1u) ? 0.0 : term_q(tv, m, e->ti)[tid];
+        if (ref >= 0) sm->sgbits[tid] = orient_bit(term_A(tv, m, ref, sp.d), term_A(tv, m, e->ti, sp.d), tid, sp.d);
+      }
+      MCE_NOUNROLL for (int i = tid; i < nwP; i += c.nthreads()) bmP[i] = 0;
+    });
+    c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < pc; i += c.nthreads()) { const unsigned k = pk[i]; c.atomic_or(&bmP[k >> 5], 1u << (k & 31)); } });
+    bm_prefix(c, bmP, pfP, nwP, (int*)nullptr);
+  }
+  MCE_HD unsigned sigma_of(const Group2Sm* sm) const { unsigned s = 0; for (int i = 0; i < m; i++) s |= sm->sgbits[i]; return s; }
+
   // G_p lookup through the rank structure (eval_gs.hpp:94-153 semantics: half storage, conjugate of the opposite cell, 0 when absent)
-  MCE_HD cplx lookup(const Group2Sm* sm, const unsigned* bmP, const unsigned short* pfP, int enc_l) const {
-    const int phc = sm->t_phc, top = 1 << (phc - 1), rev = (1 << phc) - 1;
+  MCE_HD cplx lookup(const Group2Member* e, const cplx* pG, const unsigned* bmP, const unsigned short* pfP, int enc_l) const {
+    const int phc = e->phc, top = 1 << (phc - 1), rev = (1 << phc) - 1;
     const bool cj = (enc_l & top) != 0;
     const int r = bitmap_rank(bmP, pfP, (unsigned)(cj ? (rev ^ enc_l) : enc_l));
     if (r < 0) return make_cplx(0, 0);
-    const cplx v = sm->t_pG[r];
+    const cplx v = pG[r];
     return cj ? cconj(v) : v;
   }
 
-  // G of one cell of the staged term, flattening.hpp:129-247
-  MCE_HDN MCE_NOINLINE cplx eval_cell(Group2Sm* sm, const unsigned* bmP, const unsigned short* pfP, unsigned key) const {
-    const int mm = sm->t_m, phc = sm->t_phc;
+  // G of one cell of the staged member, flattening.hpp:129-247
+  MCE_HDN MCE_NOINLINE cplx eval_cell(Group2Sm* sm, const Group2Member* e, int* flag, const unsigned* bmP, const unsigned short* pfP, unsigned key) const {
+    const int phc = e->phc;
+    // ygi = sum over non-H-orthogonal rows of q_k s_k, in row order (flat:137-154).  sm->q holds +0.0 for the H-orthogonal
+    // rows (adding +0.0 never changes a running sum that started at +0.0), so the loop is branch-free; s_k flips the sign bit.
     double ygi = 0;
-    const unsigned hf = sm->t_hflag;
-    for (int k = 0; k < mm; k++) if (!((hf >> k) & 1u)) ygi += ((key >> k) & 1u) ? -sm->q[k] : sm->q[k];
+    MCE_NOUNROLL for (int k = 0; k < m; k++) ygi += flip_sign(sm->q[k], (key >> k) & 1u);
     int lp, lm;
     const int phc_mask = (1 << phc) - 1;
-    if (!sm->t_is_child) { lp = (int)(key & (unsigned)phc_mask); lm = lp; }
+    if (!e->is_child) { lp = (int)(key & (unsigned)phc_mask); lm = lp; }
     else {
-      const int z = sm->t_z;
-      if (!sm->t_has_cmap) {              // insert a zero bit at position z, truncate to phc bits
+      const int z = e->z;
+      if (!e->has_cmap) {              // insert a zero bit at position z, truncate to phc bits
         const unsigned low = key & ((1u << z) - 1u), high = (z < 31) ? ((key >> z) << (z + 1)) : 0u;
         lp = (int)((z < phc ? (low | high) : key) & (unsigned)phc_mask);
       } else {
         unsigned v = 0;
-        for (int k = 0; k < phc; k++) { const unsigned s = sm->ksrc[k]; if (s != 255u) v |= ((key >> s) & 1u) << k; }
-        lp = (int)((v ^ sm->kflip) & (unsigned)phc_mask);
+        for (int k = 0; k < phc; k++) { const unsigned s = e->ksrc[k]; if (s != 255u) v |= ((key >> s) & 1u) << k; }
+        lp = (int)((v ^ e->kflip) & (unsigned)phc_mask);
         if (z < phc) lp &= ~(1 << z);
       }
       lm = (z < phc) ? (lp | (1 << z)) : lp;
     }
-    const cplx gp = lookup(sm, bmP, pfP, lp ^ (int)sm->t_enc_lhp);
-    const cplx gm = lookup(sm, bmP, pfP, lm ^ (int)sm->t_enc_lhp);
-    cplx g = csub(cdiv(gp, make_cplx(ygi + sm->t_d, sm->t_c)), cdiv(gm, make_cplx(ygi - sm->t_d, sm->t_c)));
+    const cplx* pG = gen_G(prev, e->gidp, phc);
+    const cplx gp = lookup(e, pG, bmP, pfP, lp ^ (int)e->enc_lhp);
+    const cplx gm = lookup(e, pG, bmP, pfP, lm ^ (int)e->enc_lhp);
+    cplx g = csub(cdiv(gp, make_cplx(ygi + e->d, e->c)), cdiv(gm, make_cplx(ygi - e->d, e->c)));
     g = cscale(g, sp.gscale);
-    if (!*(volatile int*)&sm->flag)        // |G| only matters until one cell is found non-negligible (flat:242-247)
-      if ((sm->t_psq * cabs_(g)) > TERM_APPROXIMATION_EPS) sm->flag = 1;
+    if (!*(volatile int*)flag)             // |G| only matters until one cell is found non-negligible (flat:242-247)
+      if ((e->psq * cabs_(g)) > TERM_APPROXIMATION_EPS) *flag = 1;
     return g;
-  }
-
-  template <class Ctx> MCE_KERNEL_FN void orient(Ctx& c, Group2Sm* sm, int ti, int tj) const {
-    const double* Ai = term_A(tv, m, ti, sp.d); const double* Aj = term_A(tv, m, tj, sp.d);
-    c.par([&](int tid) { if (tid == 0) sm->sigma = 0; });
-    c.par([&](int tid) { if (tid < m) { unsigned b = orient_bit(Ai, Aj, tid, sp.d); if (b) c.atomic_or((unsigned*)&sm->sigma, b); } });
   }
 
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
@@ -181,8 +210,8 @@ struct KGTable2 {
     cplx* acc = (cplx*)(base + ((sizeof(Group2Sm) + 15) & ~(size_t)15));
     cplx* Gm = acc + HC;
     unsigned* Bk = (unsigned*)(Gm + HC);
-    unsigned* bmP = Bk + HC;             // parent-table rank structure of the staged term
-    unsigned* bmA = bmP + NW;            // scratch bitmap: parent B_mu / child keys / final keys
+    unsigned* bmP = Bk + HC;             // parent-table rank structure of the staged member
+    unsigned* bmA = bmP + NW;            // scratch bitmap: parent B_mu / TP table / final keys
     unsigned short* pfP = (unsigned short*)(bmA + NW);
     unsigned short* pfA = pfP + NW + 16 + c.nthreads();   // prefix arrays carry chunk totals behind them
     const int gi = g0 + c.block();
@@ -192,33 +221,38 @@ struct KGTable2 {
     const unsigned rev_m = (1u << m) - 1u, top_m = 1u << (m - 1);
     const int nwM = m >= 5 ? (1 << (m - 5)) : 1;
 
+    // ---- chunk 0 of the member descriptions (root included) ----
+    int cbase = 0;
+    auto load_chunk = [&](int tid) {
+      if (tid < G2_CHUNK) { sm->flag[tid] = 0; if (cbase + tid < ncomb) load_member(&sm->mem[tid], members[cbase + tid]); }
+    };
+    c.par([&](int tid) { load_chunk(tid); if (tid == 0) sm->owner = -1; });
+    const Group2Member* eR = &sm->mem[0];
+
     // ---- B-table of the root (K7) ----
-    const int root = members[0];
-    const SlotMeta meR = tv.meta[tv.t_begin[m] + root];
     int nB = 0;
-    if (meR.flags & 1) {
+    if (eR->is_child) {
       if (m <= d) {
         nB = 1 << (m - 1);
-        c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = (unsigned)i; if (tid == 0) sm->owner = -1; });
+        c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = (unsigned)i; });
       } else {
         const unsigned* src; int ncp; unsigned mask;
-        parent_B_src(meR.parent, &src, &ncp, &mask);
-        const int pbc = meR.pbc, z = meR.z;
+        parent_B_src(eR->parent, &src, &ncp, &mask);
+        const int pbc = eR->pbc, z = eR->z;
         const int nwPb = pbc >= 5 ? (1 << (pbc - 5)) : 1;
-        unsigned* bmC = bmP;            // the child-key bitmap borrows bmP (not in use before the first stage_term)
+        unsigned* bmC = bmP;            // the child-key bitmap borrows bmP (not in use before the first stage_member)
         c.par([&](int tid) {
-          for (int i = tid; i < nwPb; i += c.nthreads()) bmA[i] = 0;
-          for (int i = tid; i < nwM; i += c.nthreads()) bmC[i] = 0;
-          if (tid == 0) sm->owner = -1;
+          MCE_NOUNROLL for (int i = tid; i < nwPb; i += c.nthreads()) bmA[i] = 0;
+          MCE_NOUNROLL for (int i = tid; i < nwM; i += c.nthreads()) bmC[i] = 0;
         });
-        c.par([&](int tid) { for (int i = tid; i < ncp; i += c.nthreads()) { const unsigned b = src[i] ^ mask; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
+        c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < ncp; i += c.nthreads()) { const unsigned b = src[i] ^ mask; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
         const unsigned mask_z = 1u << z, hbit = 1u << (pbc - 1), rev_pbc = (pbc >= 32) ? 0xffffffffu : ((1u << pbc) - 1u), mask_low = (1u << z) - 1u;
         const bool coal = m < pbc;
-        const unsigned char* cm = tv.cmap + (tv.t_begin[m] + root) * MAXM;
+        const unsigned char* cm = tv.cmap + (tv.t_begin[m] + eR->ti) * MAXM;
         c.par([&](int tid) {            // pairs (b, b ^ 2^z) both present -> two child sign vectors (ce:261-320), coalesced on the fly (ce:323-366)
           unsigned sel[MAXM]; int nsel = 0;
           if (coal) { unsigned seen = 0; for (int j = 0; j < pbc; j++) { const unsigned ci = cm[j]; if (!((seen >> ci) & 1u)) { seen |= (1u << ci); sel[nsel++] = 1u << j; } } }
-          for (int i = tid; i < ncp; i += c.nthreads()) {
+          MCE_NOUNROLL for (int i = tid; i < ncp; i += c.nthreads()) {
             const unsigned b = src[i] ^ mask;
             unsigned bq = b ^ mask_z;
             if (bq & hbit) bq ^= rev_pbc;
@@ -236,81 +270,90 @@ struct KGTable2 {
           }
         });
         bm_prefix(c, bmC, pfP, nwM, &sm->cnt);
-        nB = c.uniform(sm->cnt);
         c.par([&](int tid) {            // enumerate the set bits: keys in ascending order
-          for (int w = tid; w < nwM; w += c.nthreads()) {
+          MCE_NOUNROLL for (int w = tid; w < nwM; w += c.nthreads()) {
             unsigned bits = bmC[w]; int o = pfP[w];
             while (bits) { const int b = MCE_FFS(bits); bits &= bits - 1u; Bk[o++] = (unsigned)(w * 32 + b); }
           }
         });
+        nB = sm->cnt;                    // written two barriers ago; not modified again
       }
     } else {
       const unsigned* src; unsigned mask;
-      parent_B_src(meR.parent, &src, &nB, &mask);
-      c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = meR.parent; });
+      parent_B_src(eR->parent, &src, &nB, &mask);
+      c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = eR->parent; });
     }
 
     // ---- root table, with re-election when the candidate is negligible (flat:399-489) ----
-    int k = 0, cur = root, accepted = 0;
+    auto nothing = [](int) {};
+    int k = 0, accepted = 0, lfr = -1;
+    const Group2Member* e = eR;
     for (;;) {
-      stage_term(c, sm, bmP, pfP, cur);
-      c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) acc[i] = eval_cell(sm, bmP, pfP, Bk[i]); });
-      if (c.uniform(sm->flag)) { accepted = 1; break; }
-      const int lfr = cur;
-      if (++k >= ncomb) break;
-      cur = members[k];
-      const SlotMeta meK = tv.meta[tv.t_begin[m] + cur];
-      if (meK.flags & 1) {
-        orient(c, sm, lfr, cur);
-        unsigned sigma = (unsigned)c.uniform(sm->sigma);
-        if (sigma & top_m) sigma ^= rev_m;
-        if (sigma)
-          c.par([&](int tid) {
-            for (int i = tid; i < nB; i += c.nthreads()) Bk[i] ^= sigma;
-            if (tid == 0 && sm->owner >= 0) c.atomic_xor(ws.bxor + sm->owner, sigma);
-          });
-      } else {
+      // candidate k (chunk-local index kk)
+      if (k - cbase >= G2_CHUNK) { c.par(nothing); cbase = k; c.par([&](int tid) { load_chunk(tid); }); }   // the empty phase keeps slow readers of the old chunk ahead of its reload
+      const int kk = k - cbase;
+      e = &sm->mem[kk];
+      if (k > 0 && !e->is_child) {       // old term: its own table becomes the group's table (flat:443-473)
         const unsigned* src; unsigned mask;
-        parent_B_src(meK.parent, &src, &nB, &mask);
-        c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = meK.parent; });
+        parent_B_src(e->parent, &src, &nB, &mask);
+        c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = e->parent; });
       }
+      stage_member(c, sm, e, bmP, pfP, (k > 0 && e->is_child) ? lfr : -1, nothing);
+      unsigned sigma = 0;
+      if (k > 0 && e->is_child) {        // new child: re-orient the group's table in place (flat:433-441)
+        sigma = sigma_of(sm);
+        if (sigma & top_m) sigma ^= rev_m;
+      }
+      c.par([&](int tid) {
+        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm, e, &sm->flag[kk], bmP, pfP, key); }
+        if (sigma && tid == 0 && sm->owner >= 0) c.atomic_xor(ws.bxor + sm->owner, sigma);   // the table is a parent's B memory, shared with its children
+      });
+      if (sm->flag[kk]) { accepted = 1; break; }
+      lfr = e->ti;
+      if (++k >= ncomb) break;
     }
     if (!accepted) {
       c.par([&](int tid) { if (tid == 0) { alive_flag[gid_out] = 0; next.cells[gid_out] = 0; next.g_m[gid_out] = (unsigned char)m; } });
       return;
     }
-    const int rsel = cur;
+    const int rsel = e->ti;
 
-    // ---- remaining members (flat:491-550) ----
+    // ---- remaining members (flat:491-550): G table of the member, added cell by cell to the root's ----
+    int pend = 0; bool pend_cj = false;          // deferred "acc += Gm" of the previous member (runs inside the next phase)
+    auto do_pending = [&](int tid) {
+      if (!pend) return;
+      MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) acc[i] = cadd(acc[i], pend_cj ? cconj(Gm[i]) : Gm[i]);
+    };
     for (++k; k < ncomb; ++k) {
-      const int t = members[k];
-      const SlotMeta meT = tv.meta[tv.t_begin[m] + t];
-      int own_cells = nB;
-      if (!(meT.flags & 1)) own_cells = sp.with_tp ? ws.tpB_cells[meT.parent] : prev.cells[prev.alive[meT.parent]];
-      orient(c, sm, rsel, t);
-      const unsigned sigma_raw = (unsigned)c.uniform(sm->sigma);
+      if (k - cbase >= G2_CHUNK) { c.par([&](int tid) { do_pending(tid); }); pend = 0; cbase = k; c.par([&](int tid) { load_chunk(tid); }); }
+      const int kk = k - cbase;
+      const Group2Member* et = &sm->mem[kk];
+      stage_member(c, sm, et, bmP, pfP, rsel, do_pending);
+      pend = 0;
+      const unsigned sigma_raw = sigma_of(sm);
       const bool cj = (sigma_raw & top_m) != 0;
-      stage_term(c, sm, bmP, pfP, t);
-      if ((meT.flags & 1) || own_cells != nB) {
+      if (et->is_child || et->own_cells != nB) {
+        // table = root's table re-oriented (update_btable, ce:584-625): cell i of the member is cell i of the root
         const unsigned sigma_n = cj ? (sigma_raw ^ rev_m) : sigma_raw;
-        if (!(meT.flags & 1)) c.par([&](int tid) { if (tid == 0) c.atomic_add(diag, 1); });
-        c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) Gm[i] = eval_cell(sm, bmP, pfP, Bk[i] ^ sigma_n); });
-        if (c.uniform(sm->flag))
-          c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) acc[i] = cadd(acc[i], cj ? cconj(Gm[i]) : Gm[i]); });
+        c.par([&](int tid) {
+          MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, Bk[i] ^ sigma_n);
+          if (!et->is_child && tid == 0) c.atomic_add(diag, 1);     // flat:516-539 also rewrites the parent's B memory: not modelled
+        });
+        if (sm->flag[kk]) { pend = 1; pend_cj = cj; }
       } else {
-        // old term with its own table: cell i of its B_mu is position i of its (sorted) previous table; add by key (flat:291-314)
+        // old term with its own table: cell i of its B_mu is position i of its (sorted) source table; add by key (flat:291-314)
         const unsigned* src; int nT; unsigned mask;
-        parent_B_src(meT.parent, &src, &nT, &mask);
+        parent_B_src(et->parent, &src, &nT, &mask);
         if (sp.with_tp) {               // on TP steps B_mu comes from the DCE-TP table, not from the G-table keys: rank over tpB
-          c.par([&](int tid) { for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
-          c.par([&](int tid) { for (int i = tid; i < nT; i += c.nthreads()) { const unsigned b = src[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
-          int tot; bm_prefix(c, bmA, pfA, nwM, &tot);
+          c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
+          c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) { const unsigned b = src[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
+          bm_prefix(c, bmA, pfA, nwM, (int*)nullptr);
         }
         const unsigned* bmT = sp.with_tp ? bmA : bmP; const unsigned short* pfT = sp.with_tp ? pfA : pfP;
-        c.par([&](int tid) { for (int i = tid; i < nT; i += c.nthreads()) Gm[i] = eval_cell(sm, bmP, pfP, src[i] ^ mask); });
-        if (c.uniform(sm->flag))
+        c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, src[i] ^ mask); });
+        if (sm->flag[kk])
           c.par([&](int tid) {
-            for (int i = tid; i < nB; i += c.nthreads()) {
+            MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) {
               unsigned kq = Bk[i] ^ sigma_raw; bool cjj = false;
               if (kq & top_m) { cjj = true; kq ^= rev_m; }
               const int jj = bitmap_rank(bmT, pfT, kq ^ mask);      // position of the member's cell with key kq
@@ -321,17 +364,17 @@ struct KGTable2 {
     }
 
     // ---- write the surviving term; rank of a key in the bitmap of the final keys = its sorted position (flat:251-252) ----
-    c.par([&](int tid) { for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
-    c.par([&](int tid) { for (int i = tid; i < nB; i += c.nthreads()) { const unsigned b = Bk[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
-    int tot; bm_prefix(c, bmA, pfA, nwM, &tot);
+    c.par([&](int tid) { do_pending(tid); MCE_NOUNROLL for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
+    c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned b = Bk[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
+    bm_prefix(c, bmA, pfA, nwM, (int*)nullptr);
     unsigned* ko = gen_keys(next, gid_out, m); cplx* Go = gen_G(next, gid_out, m);
     const double* As = term_A(tv, m, rsel, d); const double* ps = term_p(tv, m, rsel); const double* bs = term_b(tv, m, rsel, d);
     double* Ao = gen_A(next, gid_out, m, d); double* po = gen_p(next, gid_out, m); double* bo = gen_b(next, gid_out, d);
     c.par([&](int tid) {
-      for (int i = tid; i < nB; i += c.nthreads()) { const unsigned b = Bk[i]; const int pos = bitmap_rank(bmA, pfA, b); ko[pos] = b; Go[pos] = acc[i]; }
+      MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned b = Bk[i]; const int pos = bitmap_rank(bmA, pfA, b); ko[pos] = b; Go[pos] = acc[i]; }
       for (int i = tid; i < m * d; i += c.nthreads()) Ao[i] = As[i];
-      for (int i = tid; i < m; i += c.nthreads()) po[i] = ps[i];
-      for (int i = tid; i < d; i += c.nthreads()) bo[i] = bs[i];
+      MCE_NOUNROLL for (int i = tid; i < m; i += c.nthreads()) po[i] = ps[i];
+      MCE_NOUNROLL for (int i = tid; i < d; i += c.nthreads()) bo[i] = bs[i];
       if (tid == 0) {
         alive_flag[gid_out] = 1; next.cells[gid_out] = nB; next.g_m[gid_out] = (unsigned char)m;
         c.atomic_add_u64((unsigned long long*)(diag + 2), (unsigned long long)nB);

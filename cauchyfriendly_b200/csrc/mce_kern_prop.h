@@ -287,7 +287,7 @@ struct KMsmtUpdate {
 // walks the slots serially.  The other warps run a two-stage software pipeline ahead of it: while warp 0 sums
 // tile t they compute the addends of tile t+1 from a shared-memory copy of (g, y) and stage the raw (g, y) of
 // tile t+2 from HBM with coalesced loads.  The serial DADD chain of warp 0 is the critical path.
-constexpr int MOM_QB = 16, MOM_TILE = 256;
+constexpr int MOM_QB = 2, MOM_TILE = 256;
 struct KMomentsSerial {
   const cplx* g; const double* y; long long n; int d; double* out /*[2*(1+d+d*d)]*/;
   static MCE_HD size_t smem_bytes(int d) { return sizeof(double) * (2 * MOM_QB + 2 * MOM_TILE * 2 * MOM_QB + 2 * MOM_TILE * (2 + 2 * d)); }
@@ -320,28 +320,42 @@ struct KMomentsSerial {
         dst[0] = w.re; dst[1] = w.im;
       }
     };
-    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t & 1] -> buf[t & 1]
+    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t & 1] -> buf[t & 1]; a lane keeps one quantity
       const int cnt = tile_cnt(t);
       const double* rt = raw + (t & 1) * MOM_TILE * W;
       double* bt = buf + (t & 1) * MOM_TILE * NA;
-      for (int it = lane; it < cnt * MOM_QB; it += nlanes) {
-        const int sidx = it / MOM_QB, ql = it % MOM_QB, q = qbase + ql;
+      const int ql = lane % MOM_QB, q = qbase + ql, step = nlanes / MOM_QB;
+      if (lane >= step * MOM_QB) return;
+      const int j = q == 0 ? 0 : (q <= d ? q - 1 : (q - 1 - d) / d), k = q <= d ? 0 : (q - 1 - d) % d;
+      for (int sidx = lane / MOM_QB; sidx < cnt; sidx += step) {
         cplx w = make_cplx(0, 0);
         if (q < nq) {
           const double* row = rt + sidx * W;
           const cplx gv = make_cplx(row[0], row[1]);
           if (q == 0) w = gv;
           else {
-            const int j = q <= d ? q - 1 : (q - 1 - d) / d;
             w = cmul(gv, make_cplx(row[2 + 2 * j], row[3 + 2 * j]));
-            if (q > d) { const int k = (q - 1 - d) % d; w = cmul(w, make_cplx(row[2 + 2 * k], row[3 + 2 * k])); w.re = -w.re; w.im = -w.im; }
+            if (q > d) { w = cmul(w, make_cplx(row[2 + 2 * k], row[3 + 2 * k])); w.re = -w.re; w.im = -w.im; }
           }
         }
         bt[sidx * NA + 2 * ql] = w.re; bt[sidx * NA + 2 * ql + 1] = w.im;
       }
     };
-    c.par([&](int tid) { if (tid < NA) accs[tid] = 0; else if (ntiles > 0) stage(0, tid - NA, c.nthreads() - NA); });
-    c.par([&](int tid) { if (tid >= NA) { if (ntiles > 0) produce(0, tid - NA, c.nthreads() - NA); if (ntiles > 1) stage(1, tid - NA, c.nthreads() - NA); } });
+    // Roles: lanes 0..NA-1 of warp 0 own the running sums.  Warps 1.. stage; of those, only the warps that do not share
+    // warp 0's scheduler partition (warp id % 4 != 0) compute addends, so their fp64 work never queues in front of the
+    // dependent DADD chain that is this kernel's critical path.
+    const int nstage = c.nthreads() - 32;
+    auto prod_lane = [&](int tid, int* lane, int* nlanes) {       // producer index among warps with id % 4 != 0, or -1
+      const int w = tid >> 5;
+      *nlanes = ((c.nthreads() >> 5) - ((c.nthreads() >> 5) + 3) / 4) * 32;
+      *lane = (w & 3) ? ((w - 1 - (w >> 2)) * 32 + (tid & 31)) : -1;
+    };
+    c.par([&](int tid) { if (tid < NA) accs[tid] = 0; if (tid >= 32 && ntiles > 0) stage(0, tid - 32, nstage); });
+    c.par([&](int tid) {
+      int pl, pn; prod_lane(tid, &pl, &pn);
+      if (pl >= 0 && ntiles > 0) produce(0, pl, pn);
+      if (tid >= 32 && ntiles > 1) stage(1, tid - 32, nstage);
+    });
     for (long long t = 0; t < ntiles; t++) {
       c.par([&](int tid) {
         if (tid < NA) {
@@ -356,11 +370,11 @@ struct KMomentsSerial {
           }
           for (; sidx < cnt; sidx++) acc += bt[sidx * NA];
           accs[tid] = acc;
-        } else {
-          // order matters for the shared buffers: produce(t+1) reads raw[(t+1)&1], stage(t+2) then overwrites raw[t&1]
-          if (t + 1 < ntiles) produce(t + 1, tid - NA, c.nthreads() - NA);
-          if (t + 2 < ntiles) stage(t + 2, tid - NA, c.nthreads() - NA);
         }
+        // order matters for the shared buffers: produce(t+1) reads raw[(t+1)&1], stage(t+2) then overwrites raw[t&1]
+        int pl, pn; prod_lane(tid, &pl, &pn);
+        if (pl >= 0 && t + 1 < ntiles) produce(t + 1, pl, pn);
+        if (tid >= 32 && t + 2 < ntiles) stage(t + 2, tid - 32, nstage);
       });
     }
     c.par([&](int tid) { if (tid < NA && qbase * 2 + tid < 2 * nq) out[qbase * 2 + tid] = accs[tid]; });
@@ -485,6 +499,34 @@ struct KRegroup {       // one block per chunk; thread 0 assigns ranks in slot o
         if (lane < MAXM) tv.cmap[gt * MAXM + lane] = sl.cmap[slot * MAXM + lane];
         if (lane == 0) { tv.meta[gt] = me; slot_of_term[gt] = slot; }
       }
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K11: moment contributions of the surviving terms from their NEW tables (eval_g_yei_after_ftr, cauchy_term.hpp:403-433),
+// used by compute_moments(false) when print_basic_info is set (cauchy_estimator.hpp:1166-1171, quirk A.9 iii).
+// ---------------------------------------------------------------------------------------------
+struct KPostFtrMoments {
+  StepParams sp; GenView gen; cplx* g; double* y;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int r = c.block() * c.nthreads() + tid;
+      if (r >= gen.n_alive) return;
+      const int d = sp.d, gid = gen.alive[r], m = gen_m(gen, gid);
+      const double* A = gen_A(gen, gid, m, d); const double* p = gen_p(gen, gid, m); const double* b = gen_b(gen, gid, d);
+      double tmp[MAXD];
+      for (int j = 0; j < d; j++) tmp[j] = 0;
+      int enc_sv = 0;
+      for (int l = 0; l < m; l++) {
+        const double s = dot_lr(A + l * d, sp.root_point, d) > 0 ? 1.0 : -1.0;
+        const double sc = p[l] * s;
+        for (int j = 0; j < d; j++) tmp[j] += sc * A[l * d + j];
+        if (s < 0) enc_sv |= 1 << l;
+      }
+      g[r] = g_lookup(enc_sv, m, gen_keys(gen, gid, m), gen_G(gen, gid, m), gen.cells[gid]);
+      double* yo = y + (long long)r * 2 * d;
+      for (int j = 0; j < d; j++) { yo[2 * j] = -tmp[j]; yo[2 * j + 1] = b[j]; }
     });
   }
 };

@@ -91,7 +91,7 @@ struct CauchyEstimator
         fz = MAKE_CMPLX(0, 0);
         mce_options opts; mce_default_options(&opts);
         for(int i = 0; i < 12; i++) opts.tr_search_order[i] = TR_SEARCH_IDXS_ORDERING[i];
-        opts.print_basic_info = 0;   // quirk A.9(iii) (post-FTR moment recomputation) is not reproduced; prints are host-side below
+        opts.print_basic_info = _print_basic_info ? 1 : 0;   // quirk A.9(iii): with prints on, moments are recomputed after FTR
         handle = mce_create(d, cmcc, pncc, p, _steps, A0_init, p0_init, b0_init, root_point, b_pert, &opts);
         free(b_pert);
         if(handle == NULL)
@@ -205,10 +205,13 @@ struct CauchyEstimator
             sync_host_mirror();
         if(print_basic_info)
         {
-            printf("Step %d/%d:\n", master_step+1, num_estimation_steps);
-            printf(skip_post_mu ? "Total Terms after MU: %d\n" : "Total Terms after MUC: %d\n", last_Nt_after_muc);
+            if(master_step > 0)     // step_first prints only the moments (est:1184 -> compute_moments(true))
+            {
+                printf("Step %d/%d:\n", master_step+1, num_estimation_steps);
+                printf(skip_post_mu ? "Total Terms after MU: %d\n" : "Total Terms after MUC: %d\n", last_Nt_after_muc);
+            }
             print_conditional_mean_variance();
-            if(!skip_post_mu)
+            if(!skip_post_mu && master_step > 0)
             {
                 printf("Total Terms after FTR: %d\n", Nt);
                 for(int i = 0; i < shape_range; i++)

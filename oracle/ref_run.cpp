@@ -30,6 +30,7 @@ struct Opts {
   int max_steps = 1 << 30;
   int quiet = 1;
   int time_only = 0;      // no dumps at all, just per-step wall time
+  int print_info = 0;     // construct the estimator with print_basic_info = true (quirk A.9 iii: moments recomputed after FTR)
 };
 
 static void put_i32(FILE* f, const std::string& name, const std::vector<int>& v) {
@@ -141,6 +142,7 @@ int main(int argc, char** argv) {
     else if (a == "--max-steps") o.max_steps = atoi(argv[++i]);
     else if (a == "--verbose") o.quiet = 0;
     else if (a == "--time-only") o.time_only = 1;
+    else if (a == "--print-basic-info") o.print_info = 1;
     else if (!o.scenario) o.scenario = argv[i];
     else o.out = argv[i];
   }
@@ -153,7 +155,7 @@ int main(int argc, char** argv) {
   const int d = sc.d;
   set_tr_search_idxs_ordering(sc.tr_order, d < 12 ? d : 12);
 
-  CauchyEstimator est(sc.A0, sc.p0, sc.b0, sc.steps, d, sc.cmcc, sc.pncc, sc.p, false);
+  CauchyEstimator est(sc.A0, sc.p0, sc.b0, sc.steps, d, sc.cmcc, sc.pncc, sc.p, o.print_info != 0);
   // Replace the rand()-drawn vectors by the recorded ones so every implementation sees the same values.
   for (int i = 0; i < d; i++) est.root_point[i] = sc.root_point[i];
   const int MS = est.shape_range - 1;

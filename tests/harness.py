@@ -117,9 +117,9 @@ class Session:
         return dict(A=A, p=p, q=q, b=b, cd=cd, meta=meta, cmap=cmap, csmap=csmap, F=F)
 
 
-def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None):
+def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc)
+    s = Session(lib, sc, print_basic_info=print_basic_info)
     out = {}
     d = sc.d
     MS = s.shape_range - 1
@@ -186,11 +186,13 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
     return out
 
 
-def oracle_dump(scenario_path, out_path, full_upto=0, max_steps=None, use_ref=False):
+def oracle_dump(scenario_path, out_path, full_upto=0, max_steps=None, use_ref=False, print_basic_info=False):
     """Runs the C oracle (or the compiled reference) on a scenario file and reads its dump."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_run_cpu1") if use_ref else os.path.join(ROOT, "oracle", "_build", "mce_oracle_run")
     cmd = [exe, scenario_path, out_path, "--full-upto", str(full_upto)]
     if max_steps is not None:
         cmd += ["--max-steps", str(max_steps)]
+    if print_basic_info:
+        cmd += ["--print-basic-info"]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
     return read_dump(out_path)

@@ -1,0 +1,58 @@
+"""Drop-in check: the reference's OWN example programs (src/cauchy_estimator.cpp, src/leo_satellite_7state_gps.cpp),
+compiled unchanged against include/cauchy_estimator.hpp + libmce_b200.so (tools/build_dropin.sh), print the same term
+counts and moments as the same programs built from the unmodified reference (oracle/_ref/ex_*_cpu1)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from harness import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _parse(text):
+    """[(terms after MUC/MU, fz string, mean row string)] for every 'after MU' moment block."""
+    out = []
+    blocks = re.split(r"Moment Information \(after MU\)", text)
+    counts = re.findall(r"Total Terms after MUC?: (\d+)", text)
+    for b in blocks[1:]:
+        fz = re.search(r"fz: (\S+) \+ (\S+)j", b)
+        mean = re.search(r"Conditional Mean:\s*\n([^\n]*)\n", b)
+        out.append((fz.group(1), fz.group(2), mean.group(1).strip() if mean else ""))
+    return counts, out
+
+
+def _run(exe, cwd):
+    return subprocess.run([exe], cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500).stdout.decode(errors="replace")
+
+
+def _golden(name):
+    counts, moments = [], []
+    for line in open(os.path.join(ROOT, "tests", "golden", name + ".txt")):
+        if line.startswith("counts "):
+            counts = line.split()[1:]
+        elif line.startswith("moment "):
+            a, b, c = line[len("moment "):].rstrip("\n").split(" | ")
+            moments.append((a, b, c))
+    return counts, moments
+
+
+@pytest.mark.parametrize("ref_name,our_name", [("ex_cauchy_estimator_cpu1", "cauchy_estimator"), ("ex_leo7_cpu1", "leo_satellite_7state_gps")])
+def test_reference_example_runs_on_the_gpu_path(ref_name, our_name, tmp_path):
+    """The golden text files hold the parsed output of the unmodified reference example (NUM_CPUS=1 build), generated in
+    the build container (the 7-state example needs ~4 CPU-minutes there); our binary is the same example source compiled
+    against the drop-in header.  Both examples print with print_basic_info = true, i.e. they also exercise quirk A.9(iii)."""
+    our_exe = os.path.join(ROOT, "build", "dropin", our_name)
+    if not os.path.exists(our_exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    work = tmp_path / "bin"
+    work.mkdir()
+    (tmp_path / "log" / "leo7" / "dense" / "w5").mkdir(parents=True)
+    ours = _run(our_exe, str(work))
+    c_ref, m_ref = _golden(ref_name)
+    c_our, m_our = _parse(ours)
+    assert len(m_ref) >= 10
+    assert c_our == c_ref, "term counts differ:\n%s\n%s\n%s" % (c_ref, c_our, ours[-1500:])
+    assert m_our == m_ref
