@@ -13,7 +13,7 @@ class MceOptions(ct.Structure):
 
 
 class MceMoments(ct.Structure):
-    _fields_ = [("fz", ct.c_double * 2), ("fz_after_mu", ct.c_double * 2), ("mean", ct.c_double * 32), ("cov", ct.c_double * 512),
+    _fields_ = [("fz", ct.c_double * 2), ("fz_after_mu", ct.c_double * 2), ("mean", ct.c_double * 32), ("cov", ct.c_double * 512), ("mean_after_mu", ct.c_double * 32), ("cov_after_mu", ct.c_double * 512),
                 ("g_scale_factor", ct.c_double), ("numeric_moment_errors", ct.c_int), ("Nt", ct.c_int), ("Nt_after_muc", ct.c_int),
                 ("master_step", ct.c_int), ("skip_post_mu", ct.c_int)]
 

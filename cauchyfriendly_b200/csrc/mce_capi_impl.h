@@ -64,6 +64,8 @@ int mce_get_moments(mce_handle* h, mce_moments* out) {
   out->fz[0] = e->fz.re; out->fz[1] = e->fz.im; out->fz_after_mu[0] = e->fz_mu.re; out->fz_after_mu[1] = e->fz_mu.im;
   for (int i = 0; i < e->d; i++) { out->mean[2 * i] = e->mean[i].re; out->mean[2 * i + 1] = e->mean[i].im; }
   for (int i = 0; i < e->d * e->d; i++) { out->cov[2 * i] = e->var[i].re; out->cov[2 * i + 1] = e->var[i].im; }
+  for (int i = 0; i < e->d; i++) { out->mean_after_mu[2 * i] = e->mean_mu[i].re; out->mean_after_mu[2 * i + 1] = e->mean_mu[i].im; }
+  for (int i = 0; i < e->d * e->d; i++) { out->cov_after_mu[2 * i] = e->var_mu[i].re; out->cov_after_mu[2 * i + 1] = e->var_mu[i].im; }
   out->g_scale_factor = e->G_SCALE_FACTOR; out->numeric_moment_errors = e->numeric_moment_errors;
   out->Nt = e->Nt; out->Nt_after_muc = e->Nt_muc; out->master_step = e->master_step; out->skip_post_mu = e->skip_post_mu;
   return 0;

@@ -92,7 +92,7 @@ class Engine {
   int tr_order[12];
   std::vector<double> A0, p0, b0, root_point, b_pert;
   double G_SCALE_FACTOR = 0;
-  cplx fz, last_fz, fz_mu; std::vector<cplx> mean, var, last_mean, last_var;
+  cplx fz, last_fz, fz_mu; std::vector<cplx> mean, var, last_mean, last_var, mean_mu, var_mu;   // *_mu: as of the end of the measurement update
   std::vector<int> terms_per_shape, muc_per_shape;
   StepStats stats;
   std::string error;
@@ -128,7 +128,7 @@ class Engine {
     root_point.assign(root_point_, root_point_ + d);
     b_pert.assign(MAXM, 0.0);
     for (int i = 0; i < max_shape && i < MAXM; i++) b_pert[i] = b_pert_[i];
-    mean.assign(d, make_cplx(0, 0)); var.assign(d * d, make_cplx(0, 0)); last_mean = mean; last_var = var;
+    mean.assign(d, make_cplx(0, 0)); var.assign(d * d, make_cplx(0, 0)); last_mean = mean; last_var = var; mean_mu = mean; var_mu = var;
     fz = last_fz = make_cplx(0, 0);
     terms_per_shape.assign(shape_range, 0); muc_per_shape.assign(shape_range, 0);
     terms_per_shape[d] = 1;
@@ -216,7 +216,7 @@ class Engine {
     const cplx Ifz = make_cplx(0, fz.re);
     for (int i = 0; i < d; i++) mean[i] = cdiv(mean[i], Ifz);
     for (int i = 0; i < d; i++) for (int j = 0; j < d; j++) var[i * d + j] = csub(cdiv(var[i * d + j], fz), cmul(mean[i], mean[j]));
-    fz_mu = fz;
+    fz_mu = fz; mean_mu = mean; var_mu = var;
     if (!check) return;
     const bool first_msmt = (master_step % p) == 0, not_last = (master_step % p) != (p - 1), last = (master_step % p) == (p - 1);
     if (first_msmt) {
@@ -250,7 +250,7 @@ class Engine {
     if (mean_okay) last_mean = mean; else mean = last_mean;
     if (cov_okay) last_var = var; else var = last_var;
     if (!mean_okay && !cov_okay) fz = last_fz; else last_fz = fz;
-    fz_mu = fz;
+    fz_mu = fz; mean_mu = mean; var_mu = var;
   }
 
   // ------------------------------------------------------------------------------------------
@@ -611,9 +611,9 @@ class Engine {
     be.launch(KMomentsSerial{gg, yy, (long long)n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     std::vector<double> raw(2 * nq);
     be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
-    const cplx keep = fz_mu;
+    const cplx keep = fz_mu; const std::vector<cplx> km = mean_mu, kv = var_mu;
     finalize_moments(raw.data(), false);
-    fz_mu = keep;
+    fz_mu = keep; mean_mu = km; var_mu = kv;
   }
 
   // ------------------------------------------------------------------------------------------

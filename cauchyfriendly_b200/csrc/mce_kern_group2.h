@@ -198,8 +198,13 @@ struct KGTable2 {
     const cplx gm = lookup(e, pG, bmP, pfP, lm ^ (int)e->enc_lhp);
     cplx g = csub(cdiv(gp, make_cplx(ygi + e->d, e->c)), cdiv(gm, make_cplx(ygi - e->d, e->c)));
     g = cscale(g, sp.gscale);
-    if (!*(volatile int*)flag)             // |G| only matters until one cell is found non-negligible (flat:242-247)
-      if ((e->psq * cabs_(g)) > TERM_APPROXIMATION_EPS) *flag = 1;
+    if (!*(volatile int*)flag) {           // |G| only matters until one cell is found non-negligible (flat:242-247)
+      // max(|re|,|im|) <= |G| <= |re|+|im| and rounding is monotone, so the two cheap bounds decide almost every cell
+      // exactly as `psq * cabs(G) > eps` would; hypot runs only in between.
+      const double ar = fabs(g.re), ai = fabs(g.im), mx = ar > ai ? ar : ai;
+      if ((e->psq * mx) > TERM_APPROXIMATION_EPS) *flag = 1;
+      else if ((e->psq * (ar + ai)) > TERM_APPROXIMATION_EPS) { if ((e->psq * cabs_(g)) > TERM_APPROXIMATION_EPS) *flag = 1; }
+    }
     return g;
   }
 

@@ -363,9 +363,14 @@ struct KMomentsSerial {
           const double* bt = buf + (t & 1) * MOM_TILE * NA + tid;
           double acc = accs[tid];
           int sidx = 0;
-          for (; sidx + 8 <= cnt; sidx += 8) {
-            const double v0 = bt[(sidx + 0) * NA], v1 = bt[(sidx + 1) * NA], v2 = bt[(sidx + 2) * NA], v3 = bt[(sidx + 3) * NA];
-            const double v4 = bt[(sidx + 4) * NA], v5 = bt[(sidx + 5) * NA], v6 = bt[(sidx + 6) * NA], v7 = bt[(sidx + 7) * NA];
+          if (cnt >= 8) {      // register double-buffering: the next 8 addends are in flight while the current 8 are added
+            double v0 = bt[0 * NA], v1 = bt[1 * NA], v2 = bt[2 * NA], v3 = bt[3 * NA], v4 = bt[4 * NA], v5 = bt[5 * NA], v6 = bt[6 * NA], v7 = bt[7 * NA];
+            for (sidx = 8; sidx + 8 <= cnt; sidx += 8) {
+              const double w0 = bt[(sidx + 0) * NA], w1 = bt[(sidx + 1) * NA], w2 = bt[(sidx + 2) * NA], w3 = bt[(sidx + 3) * NA];
+              const double w4 = bt[(sidx + 4) * NA], w5 = bt[(sidx + 5) * NA], w6 = bt[(sidx + 6) * NA], w7 = bt[(sidx + 7) * NA];
+              acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
+              v0 = w0; v1 = w1; v2 = w2; v3 = w3; v4 = w4; v5 = w5; v6 = w6; v7 = w7;
+            }
             acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
           }
           for (; sidx < cnt; sidx++) acc += bt[sidx * NA];

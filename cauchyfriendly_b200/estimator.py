@@ -36,8 +36,8 @@ class CauchyEstimator:
     from `seed` with the same distributions (1 + U(0,1], 2U - 1)."""
 
     def __init__(self, A0, p0, b0, steps, d, cmcc, pncc, p, print_basic_info=False, root_point=None, b_pert=None,
-                 tr_search_idxs_ordering=None, device=-1, seed=0, fast_moments=False):
-        self._lib = _capi.load()
+                 tr_search_idxs_ordering=None, device=-1, seed=0, fast_moments=False, _lib=None):
+        self._lib = _lib if _lib is not None else _capi.load()   # _lib: test hook (tests/emu), never set by product code
         self.d, self.cmcc, self.pncc, self.p = int(d), int(cmcc), int(pncc), int(p)
         self.num_estimation_steps = self.p * int(steps)
         max_shape = (int(steps) - 1) * self.pncc + self.d if self.d > 1 else self.d + self.pncc

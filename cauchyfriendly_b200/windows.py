@@ -1,0 +1,181 @@
+"""Sliding-window bank over B200 estimators -- host-side mirror of the reference's PySlidingWindowManager
+(scripts/swig/cauchy/cauchy_estimator.py:1092-1333) and of SlidingWindowManager::step (include/cauchy_windows.hpp:1025-1165)
+for LTI / LTV systems.
+
+W estimators ("windows") run staggered: at steady state window w has folded in 1..W time steps; the fullest window without
+covariance error flags provides the estimate, and the window that just emptied is re-seeded from that estimate with
+Speyer's initialisation (cauchy_util.hpp:23-112) and the last measurement.
+
+Multi-GPU: windows are independent estimators, so they are sharded over ranks (window w lives on rank w % world_size, one
+process per GPU, torch.distributed).  The only exchange per step is an all-gather of each window's (count, error code, fz,
+mean, covariance) -- 3 + n + n*n doubles per window -- after which every rank runs the same selection logic; there is no
+data-path collective.  This is the reference's own unit of distribution (one forked process per window,
+cauchy_windows.hpp:353-376)."""
+import numpy as np
+
+from .estimator import CauchyEstimator
+
+COV_UNSTABLE_FINAL = 1 << 1   # ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT (cauchy_constants.hpp:114)
+COV_DNE = 1 << 3              # ERROR_COVARIANCE_AT_CURRENT_STEP_DNE
+
+
+def speyers_window_init(x1_hat, Var, H, gamma, z1):
+    """Speyer's window initialisation, cauchy_util.hpp:23-112 (window_var_boost = NULL): returns A0 (n x n), p0, b0 of a
+    one-term characteristic function whose first measurement update reproduces (x1_hat, Var)."""
+    x1_hat = np.asarray(x1_hat, np.float64)
+    Var = np.array(Var, np.float64)
+    H = np.asarray(H, np.float64).reshape(-1)
+    n = x1_hat.size
+    w = np.linalg.eigvalsh(Var)
+    if np.any(w < -1e-5):                       # COV_EIGENVALUE_TOLERANCE: make the covariance more positive definite
+        Var = Var + np.eye(n) * (-1e-5 - w.min())
+    resid = z1 - H @ x1_hat
+    scale = gamma * gamma + resid * resid
+    M = Var + (Var @ np.outer(H, H) @ Var) / scale
+    eigs, vecs = np.linalg.eigh(M)
+    A0 = vecs.T.copy()                          # rows are the eigenvectors
+    b0 = x1_hat - (Var @ H) * (resid / scale)
+    HA = A0 @ H
+    scale3 = (scale + H @ Var @ H) / gamma
+    p0 = eigs / scale3 * HA / np.sign(HA)
+    return A0, p0, b0
+
+
+class SlidingWindowBank:
+    """LTI/LTV sliding-window Cauchy estimator (W windows of depth W).
+
+    step(msmts, controls) mirrors PySlidingWindowManager.step and returns (xhat, Phat, wavg_xhat, wavg_Phat)."""
+
+    def __init__(self, num_windows, A0, p0, b0, Phi, B, Gamma, beta, H, gamma, *, estimator_cls=CauchyEstimator, est_kwargs=None,
+                 dist=None, seed=0, debug_print=False):
+        self.W = int(num_windows)
+        self.n = int(np.asarray(p0).size)
+        self.Phi = np.asarray(Phi, np.float64).reshape(self.n, self.n)
+        self.Gamma = np.asarray(Gamma, np.float64).reshape(self.n, -1)
+        self.pncc = self.Gamma.shape[1]
+        self.beta = np.asarray(beta, np.float64).reshape(self.pncc)
+        self.H = np.asarray(H, np.float64).reshape(-1, self.n)
+        self.p = self.H.shape[0]
+        self.gamma = np.asarray(gamma, np.float64).reshape(self.p)
+        self.B = None if B is None else np.asarray(B, np.float64).reshape(self.n, -1)
+        self.cmcc = 0 if self.B is None else self.B.shape[1]
+        self.dist = dist
+        self.rank = dist.get_rank() if dist is not None else 0
+        self.world = dist.get_world_size() if dist is not None else 1
+        self.debug_print = debug_print
+        kw = dict(est_kwargs or {})
+        # every window is created with the same (seeded) root point / perturbation, on the rank that owns it
+        self.ests = {}
+        for w in range(self.W):
+            if w % self.world == self.rank:
+                self.ests[w] = estimator_cls(A0, p0, b0, self.W, self.n, self.cmcc, self.pncc, self.p, seed=seed, **kw)
+                self.ests[w].set_win_num(w + 1)
+        self.win_counts = np.zeros(self.W, np.int64)
+        self.step_idx = 0
+        self.moment_info = {"x": [], "P": [], "fz": [], "win_idx": [], "err_code": []}
+        self.avg_moment_info = {"x": [], "P": [], "win_idx": [], "err_code": []}
+        n = self.n
+        self._stats = np.zeros((self.W, 3 + n + n * n))      # per window: count, err, fz, mean[n], cov[n*n] (last measurement)
+        self._last_msmts = None
+
+    # ---- one estimator, one time step: p measurement updates (PyCauchyEstimator._call_step, cauchy_estimator.py:612-656) ----
+    def _step_window(self, w, msmts, controls, first_msmt=0):
+        est = self.ests[w]
+        u = None if controls is None or self.cmcc == 0 else np.asarray(controls, np.float64)
+        for i in range(first_msmt, self.p):
+            est.step(msmts[i], self.Phi, self.Gamma, self.beta, self.H[i], self.gamma[i], self.B, u)
+        n = self.n
+        row = self._stats[w]
+        row[1] = est.numeric_moment_errors
+        row[2] = est.fz_after_mu.real if est.fz_after_mu.real != 0 else est.fz.real
+        row[3:3 + n] = est.conditional_mean.real
+        row[3 + n:] = est.conditional_variance.real.ravel()
+
+    def _exchange(self):
+        """All ranks end up with every window's statistics (the only communication of a step)."""
+        if self.dist is None or self.world == 1:
+            return
+        import torch
+        mine = torch.from_numpy(self._stats.copy())
+        owner = torch.tensor([w % self.world for w in range(self.W)])
+        mine[owner != self.rank] = 0
+        backend = self.dist.get_backend()
+        if backend == "nccl":
+            mine = mine.cuda()
+        self.dist.all_reduce(mine)              # rows are disjoint across ranks: a sum is a gather
+        self._stats[:] = mine.cpu().numpy()
+
+    def _best_window(self):
+        okays = np.zeros(self.W, bool)
+        idxs = []
+        for i in range(self.W):
+            if self.win_counts[i] > 0:
+                err = int(self._stats[i, 1])
+                if not ((err & COV_UNSTABLE_FINAL) or (err & COV_DNE)):
+                    idxs.append((i, self.win_counts[i]))
+                    okays[i] = True
+        if self.step_idx == 0:
+            best, okays[0] = 0, True
+        else:
+            if not idxs:
+                raise RuntimeError("No window is available without an error code!")
+            best = sorted(idxs, key=lambda x: x[1], reverse=True)[0][0]
+        return best, okays
+
+    def _mean_cov(self, w):
+        n = self.n
+        return self._stats[w, 3:3 + n].copy(), self._stats[w, 3 + n:].reshape(n, n).copy()
+
+    def step(self, msmts, controls=None):
+        msmts = np.asarray(msmts, np.float64).reshape(self.p)
+        min_idx = max_idx = None
+        if self.step_idx == 0:
+            if 0 in self.ests:
+                self._step_window(0, msmts, controls)
+            self.win_counts[0] += 1
+        else:
+            max_idx = int(np.argmax(self.win_counts))
+            min_idx = int(np.argmin(self.win_counts))
+            for w in range(self.W):
+                if self.win_counts[w] > 0:
+                    if w in self.ests:
+                        self._step_window(w, msmts, controls)
+                    self.win_counts[w] += 1
+        self._stats[:, 0] = self.win_counts
+        self._exchange()
+        best, okays = self._best_window()
+        xhat, Phat = self._mean_cov(best)
+        self.moment_info["x"].append(xhat); self.moment_info["P"].append(Phat)
+        self.moment_info["fz"].append(self._stats[best, 2]); self.moment_info["win_idx"].append(best)
+        self.moment_info["err_code"].append(int(self._stats[best, 1]))
+        # weighted average over the usable windows (cauchy_estimator.py:1218-1259)
+        wsum, xavg, Pavg, err_or = 0.0, np.zeros(self.n), np.zeros((self.n, self.n)), 0
+        for w in range(self.W):
+            if self.win_counts[w] > 0 and okays[w]:
+                f = self.win_counts[w] / self.W
+                x, P = self._mean_cov(w)
+                wsum += f; xavg += x * f; Pavg += P * f; err_or |= int(self._stats[w, 1])
+        xavg /= wsum; Pavg /= wsum
+        self.avg_moment_info["x"].append(xavg); self.avg_moment_info["P"].append(Pavg)
+        self.avg_moment_info["win_idx"].append(-1); self.avg_moment_info["err_code"].append(err_or)
+        # re-seed the empty window about the best window's estimate and the last measurement (reset_about_estimator, :888-923)
+        if self.step_idx > 0:
+            if min_idx in self.ests:
+                A0, p0, b0 = speyers_window_init(xhat, Phat, self.H[self.p - 1], self.gamma[self.p - 1], msmts[self.p - 1])
+                est = self.ests[min_idx]
+                est.reset()
+                est.reinitialize_start_statistics(A0, p0, b0)
+                self._step_window(min_idx, msmts, None, first_msmt=self.p - 1)
+                est.master_step = self.p
+            self.win_counts[min_idx] += 1
+            if self.win_counts[max_idx] == self.W:
+                if max_idx in self.ests:
+                    self.ests[max_idx].reset()
+                self.win_counts[max_idx] = 0
+        self.step_idx += 1
+        return xhat, Phat, xavg, Pavg
+
+    def shutdown(self):
+        for e in self.ests.values():
+            e.shutdown()
+        self.ests = {}

@@ -163,9 +163,13 @@ struct CauchyEstimator
         Nt = m.Nt; skip_post_mu = m.skip_post_mu;
         mce_get_terms_per_shape(handle, terms_per_shape, 0);
         last_fz_after_mu = MAKE_CMPLX(m.fz_after_mu[0], m.fz_after_mu[1]);
+        for(int i = 0; i < d; i++) mean_after_mu[i] = MAKE_CMPLX(m.mean_after_mu[2*i], m.mean_after_mu[2*i+1]);
+        for(int i = 0; i < d*d; i++) var_after_mu[i] = MAKE_CMPLX(m.cov_after_mu[2*i], m.cov_after_mu[2*i+1]);
         last_Nt_after_muc = m.Nt_after_muc;
     }
     C_COMPLEX_TYPE last_fz_after_mu;
+    C_COMPLEX_TYPE mean_after_mu[32];
+    C_COMPLEX_TYPE var_after_mu[32*32];
     int last_Nt_after_muc;
 
     void print_conditional_mean_variance()      // est:513-522
@@ -173,6 +177,16 @@ struct CauchyEstimator
         const int precision = 16;
         printf("Moment Information (after MU) at step %d, MU %d/%d\n", (master_step+1) / p, (master_step % p)+1, p);
         printf("fz: %.*lf + %.*lfj\n", precision, creal(last_fz_after_mu), precision, cimag(last_fz_after_mu));
+        printf("Conditional Mean:\n");
+        print_cmat(mean_after_mu, 1, d, precision);
+        printf("Conditional Variance:\n");
+        print_cmat(var_after_mu, d, d, precision);
+    }
+    void print_moments_after_ftr()              // est:591-600
+    {
+        const int precision = 16;
+        printf("Moment Information (after FTR) at step %d, MU %d/%d\n", (master_step+1) / p, (master_step % p)+1, p);
+        printf("fz: %.*lf + %.*lfj\n", precision, creal(fz), precision, cimag(fz));
         printf("Conditional Mean:\n");
         print_cmat(conditional_mean, 1, d, precision);
         printf("Conditional Variance:\n");
@@ -211,6 +225,8 @@ struct CauchyEstimator
                 printf(skip_post_mu ? "Total Terms after MU: %d\n" : "Total Terms after MUC: %d\n", last_Nt_after_muc);
             }
             print_conditional_mean_variance();
+            if(!skip_post_mu)
+                print_moments_after_ftr();
             if(!skip_post_mu && master_step > 0)
             {
                 printf("Total Terms after FTR: %d\n", Nt);

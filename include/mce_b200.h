@@ -65,6 +65,8 @@ typedef struct mce_moments {
   double fz_after_mu[2];      /* normalisation factor right after the measurement update (what est:795 prints)              */
   double mean[2 * 16];
   double cov[2 * 16 * 16];
+  double mean_after_mu[2 * 16];       /* moments as checked right after the measurement update; they differ from mean/cov  */
+  double cov_after_mu[2 * 16 * 16];   /* only with print_basic_info (quirk A.9 iii: recomputed from the tables after FTR)   */
   double g_scale_factor;
   int numeric_moment_errors;
   int Nt;                     /* terms after the step (after FTR, or after MU on the window's last step)      */

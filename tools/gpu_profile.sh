@@ -2,11 +2,13 @@
 # Timings, bench line, ncu launch list and one full ncu capture of the dominant kernel. Output -> gpurun_out/
 mkdir -p gpurun_out
 R=${1:-r01}
+echo "=== full gpu test-suite"
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -12
 echo "=== timings"
 timeout 600 python tools/time_scenario.py leo7 2 2>&1 | tail -34
 timeout 300 python tools/time_scenario.py lti3 2 2>&1 | tail -15
 echo "=== bench"
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err; tail -2 gpurun_out/bench_$R.err; cat gpurun_out/bench_$R.json
+timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err; tail -2 gpurun_out/bench_$R.err; cat gpurun_out/bench_$R.json
 echo "=== bench reference arm"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 0 > gpurun_out/bench_ref_$R.json 2>/dev/null; cat gpurun_out/bench_ref_$R.json
 echo "=== ncu launch list (one cold pass of leo7)"
