@@ -332,7 +332,12 @@ class Engine {
         const int cgen = cell_count_general(max_mtp, d);
         const int acc_cap = next_pow2(cgen + 1), vis_cap = next_pow2(DCE_STORAGE_MULT * cgen);
         const int nth = 128;
-        be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag}, n_alive, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
+        if (max_shape <= 16) {
+          const int NWt = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
+          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag}, n_alive, nth, KTpDce2::smem_bytes(NWt, nth));
+        } else {
+          be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag}, n_alive, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
+        }
       }
     }
     stats.ms_tp = be.toc(tph); tph = be.tic();
@@ -430,7 +435,7 @@ class Engine {
     int* i1 = (int*)scratchI1.ensure(sizeof(int) * (size_t)(max_n + 4));
     int* i2 = (int*)scratchI2.ensure(sizeof(int) * (size_t)(max_n + 4));
     int* i3 = (int*)scratchI3.ensure(sizeof(int) * (size_t)(max_n + 4));
-    int* unk = (int*)unkBuf.ensure(64);
+    int* unk = (int*)unkBuf.ensure(sizeof(int) * (NSHAPE + 8));
     std::vector<int> n_groups(NSHAPE, 0), n_phase1(NSHAPE, 0), gstart_off(NSHAPE, 0);
     int goff = 0;
     if (capture) cap.clear();
@@ -447,7 +452,7 @@ class Engine {
       int rounds = 0;
       for (;;) {
         be.memset(unk, 0, sizeof(int));
-        be.launch(KFtrRound{tv, sp, m, k1, i1, wide, F, unk}, nb, 128, 0);
+        be.launch(KFtrRoundTiled{tv, sp, m, k1, i1, wide, F, unk}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
         int nu = 0; be.d2h(&nu, unk, sizeof(int));
         rounds++;
         if (nu == 0) break;
@@ -458,24 +463,14 @@ class Engine {
       be.sort_pairs(k0, k1, i0, order, n);
       be.launch(KGroupHeads{n, F, order, i2}, nb, 128, 0);
       be.exclusive_scan(i2, i3, n);
-      int last_rank = 0, last_head = 0;
-      be.d2h(&last_rank, i3 + (n - 1), sizeof(int)); be.d2h(&last_head, i2 + (n - 1), sizeof(int));
-      const int ng_m = last_rank + last_head;
+      be.memset(unk, 0, 2 * sizeof(int));
+      be.launch(KCountRoots{n, tv.n_old[m], F, unk}, nb, 128, 2 * sizeof(int));
+      int cr[2] = {0, 0};
+      be.d2h(cr, unk, 2 * sizeof(int));
+      const int ng_m = cr[0];
       n_groups[m] = ng_m;
+      n_phase1[m] = cr[1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
       be.launch(KGroupFill{n, i2, i3, gstart, ng_m}, nb, 128, 0);
-      // groups whose root is an old term come first (roots ascend): their count = rank of the first head at order position >= ... root >= n_old
-      // roots are sorted ascending, so count roots < n_old: F[j]==j for j < n_old  <=> heads among the first positions; use the scan of heads over F order
-      {
-        // number of roots with index < n_old = number of j < n_old with F[j] == j; computed from a scan over term order
-        be.launch(KRootFlags{tv.n_old[m], F, i2}, (tv.n_old[m] + 127) / 128 + 1, 128, 0);
-        int np1 = 0;
-        if (tv.n_old[m] > 0) {
-          be.exclusive_scan(i2, i3, tv.n_old[m]);
-          int a = 0, b2 = 0; be.d2h(&a, i3 + (tv.n_old[m] - 1), sizeof(int)); be.d2h(&b2, i2 + (tv.n_old[m] - 1), sizeof(int));
-          np1 = a + b2;
-        }
-        n_phase1[m] = np1;
-      }
       goff += ng_m + 1;
       if (capture) capture_shape(tv, m, F, ws, with_tp);
     }
@@ -522,11 +517,9 @@ class Engine {
       be.exclusive_scan(fi, fr, ngr);
       be.launch(KAliveCompact{ngr, aflag, fr, ng.v.alive}, (ngr + 127) / 128, 128, 0);
       std::vector<int> bounds(NSHAPE + 1, 0);
-      for (int m = 1; m <= NSHAPE; m++) {
-        const int g = ng.v.gid_begin[m];
-        if (g >= ngr) { int a = 0, b2 = 0; be.d2h(&a, fr + (ngr - 1), sizeof(int)); be.d2h(&b2, fi + (ngr - 1), sizeof(int)); bounds[m] = a + b2; }
-        else be.d2h(&bounds[m], fr + g, sizeof(int));
-      }
+      int* dbounds = (int*)unkBuf.ensure(sizeof(int) * (NSHAPE + 8));
+      be.launch(KShapeBounds{ng.v, ngr, fi, fr, dbounds}, 1, 64, 0);
+      be.d2h(bounds.data(), dbounds, sizeof(int) * (NSHAPE + 1));
       for (int m = 1; m < NSHAPE; m++) ng.alive_per_shape[m] = bounds[m + 1] - bounds[m];
       n_surv = bounds[NSHAPE];
     }

@@ -114,6 +114,99 @@ struct KFtrRound {
   }
 };
 
+// Tiled variant of KFtrRound: a block owns FTR_TB consecutive positions of the sorted primary axis.  The union of their
+// epsilon-windows is staged chunk by chunk into shared memory (index, decision state, b, p and the first m scalars of A of
+// every candidate), so each candidate is fetched from HBM once per block instead of once per (term, candidate) pair.
+constexpr int FTR_TB = 128, FTR_C = 128;
+struct KFtrRoundTiled {
+  TermView tv; StepParams sp; int m; const unsigned long long* skeys; const int* sidx; const unsigned char* wide; int* F; int* n_unknown;
+  static MCE_HD size_t smem_bytes(int m, int d) {
+    return (size_t)(FTR_TB + FTR_C) * (sizeof(double) * (d + 2 * m) + sizeof(unsigned long long) + 2 * sizeof(int) + 4) + 64;
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int n = tv.n[m], d = sp.d, ax0 = sp.tr_order[0], W = d + 2 * m;
+    const int p0 = c.block() * FTR_TB;
+    unsigned char* base = c.smem();
+    double* tdat = (double*)base;                              // [FTR_TB][W]  own terms: b, p, A[0..m)
+    double* cdat = tdat + FTR_TB * W;                          // [FTR_C][W]   candidates
+    unsigned long long* ckey = (unsigned long long*)(cdat + FTR_C * W);
+    int* cidx = (int*)(ckey + FTR_C);
+    int* cF = cidx + FTR_C;
+    int* tmin = cF + FTR_C;                                    // [FTR_TB][2] running (min_root, min_unknown)
+    int* ctl = tmin + 2 * FTR_TB;                              // [0] any undecided term in the tile, [1] lo_pos, [2] hi_pos
+    unsigned char* cw = (unsigned char*)(ctl + 4);             // [FTR_C] wide flags
+    const int ntile = (n - p0) < FTR_TB ? (n - p0) : FTR_TB;
+    c.par([&](int tid) { if (tid == 0) ctl[0] = 0; });
+    c.par([&](int tid) {
+      for (int t = tid; t < ntile; t += c.nthreads()) {
+        const int j = sidx[p0 + t];
+        if (c.load_relaxed(F + j) == -1) ctl[0] = 1;
+        tmin[2 * t] = 0x7fffffff; tmin[2 * t + 1] = 0x7fffffff;
+        double* row = tdat + t * W;
+        const double* bj = term_b(tv, m, j, d); const double* pj = term_p(tv, m, j); const double* Aj = term_A(tv, m, j, d);
+        for (int k = 0; k < d; k++) row[k] = bj[k];
+        for (int k = 0; k < m; k++) { row[d + k] = pj[k]; row[d + m + k] = Aj[k]; }
+      }
+      if (tid == 0) {            // union of the tile's windows on the sorted axis (conservative slack; the exact interval test is in ftr_match)
+        const double vlo = term_b(tv, m, sidx[p0], d)[ax0], vhi = term_b(tv, m, sidx[p0 + ntile - 1], d)[ax0];
+        const unsigned long long klo = f64_sort_key(vlo - (4.0 * REDUCTION_EPS + 8.0 * fabs(vlo) * 2.3e-16));
+        const unsigned long long khi = f64_sort_key(vhi + (4.0 * REDUCTION_EPS + 8.0 * fabs(vhi) * 2.3e-16));
+        int lo = 0, hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (skeys[mid] < klo) lo = mid + 1; else hi = mid; }
+        ctl[1] = lo;
+        lo = 0; hi = n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (skeys[mid] <= khi) lo = mid + 1; else hi = mid; }
+        ctl[2] = lo;
+      }
+    });
+    if (!ctl[0]) return;         // every term of the tile is decided (ctl[0] is not written again)
+    const int lo_pos = ctl[1], hi_pos = ctl[2];
+    for (int cs = lo_pos; cs < hi_pos; cs += FTR_C) {
+      const int cn = (hi_pos - cs) < FTR_C ? (hi_pos - cs) : FTR_C;
+      c.par([&](int tid) {        // stage a chunk of candidates
+        for (int q = tid; q < cn; q += c.nthreads()) {
+          const int i = sidx[cs + q];
+          cidx[q] = i; ckey[q] = skeys[cs + q]; cF[q] = c.load_relaxed(F + i); cw[q] = wide[i];
+          double* row = cdat + q * W;
+          const double* bi = term_b(tv, m, i, d); const double* pi = term_p(tv, m, i); const double* Ai = term_A(tv, m, i, d);
+          for (int k = 0; k < d; k++) row[k] = bi[k];
+          for (int k = 0; k < m; k++) { row[d + k] = pi[k]; row[d + m + k] = Ai[k]; }
+        }
+      });
+      c.par([&](int tid) {        // every undecided term of the tile against the chunk
+        for (int t = tid; t < ntile; t += c.nthreads()) {
+          const int j = sidx[p0 + t];
+          if (c.load_relaxed(F + j) != -1) continue;
+          const double* rj = tdat + t * W;
+          const double slack = 4.0 * REDUCTION_EPS + 8.0 * fabs(rj[ax0]) * 2.3e-16;
+          const unsigned long long klo = f64_sort_key(rj[ax0] - slack), khi = f64_sort_key(rj[ax0] + slack);
+          int min_root = tmin[2 * t], min_unknown = tmin[2 * t + 1];
+          for (int q = 0; q < cn; q++) {
+            const int i = cidx[q];
+            if (!(i < j && i < min_root) || ckey[q] < klo || ckey[q] > khi || !cw[q]) continue;
+            const int Fi = cF[q];
+            if (Fi != i && Fi != -1) continue;
+            const double* ri = cdat + q * W;
+            if (!ftr_match(ri, rj, ri + d, rj + d, ri + d + m, rj + d + m, m, d, sp.tr_order)) continue;
+            if (Fi == i) { if (i < min_root) min_root = i; }
+            else if (i < min_unknown) min_unknown = i;
+          }
+          tmin[2 * t] = min_root; tmin[2 * t + 1] = min_unknown;
+        }
+      });
+    }
+    c.par([&](int tid) {
+      for (int t = tid; t < ntile; t += c.nthreads()) {
+        const int j = sidx[p0 + t];
+        if (c.load_relaxed(F + j) != -1) continue;
+        const int min_root = tmin[2 * t], min_unknown = tmin[2 * t + 1];
+        if (min_unknown < min_root) { c.atomic_add(n_unknown, 1); continue; }   // an undecided lower term could still claim j
+        F[j] = (min_root != 0x7fffffff) ? min_root : j;
+      }
+    });
+  }
+};
+
 // After sorting term indices by (F, index): group heads and sizes. order[] holds term indices sorted by root.
 struct KGroupHeads {
   int n; const int* F; const int* order; int* is_head;
@@ -133,6 +226,28 @@ struct KGroupFill {     // head_rank = exclusive scan of is_head; grp_start[rank
       if (k >= n) return;
       if (is_head[k]) grp_start[head_rank[k]] = k;
       if (k == 0) grp_start[n_groups] = n;
+    });
+  }
+};
+struct KCountRoots {    // out[0] = number of roots, out[1] = number of roots that are old terms (index < n_old)
+  int n, n_old; const int* F; int* out;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    int* sm = (int*)c.smem();
+    c.par([&](int tid) { if (tid < 2) sm[tid] = 0; });
+    c.par([&](int tid) {
+      const int j = c.block() * c.nthreads() + tid;
+      if (j < n && F[j] == j) { c.atomic_add(&sm[0], 1); if (j < n_old) c.atomic_add(&sm[1], 1); }
+    });
+    c.par([&](int tid) { if (tid < 2 && sm[tid]) c.atomic_add(out + tid, sm[tid]); });
+  }
+};
+struct KShapeBounds {   // bounds[m] = number of surviving groups with gid < gid_begin[m] (rank = exclusive scan of the alive flags)
+  GenView gen; int ngr; const int* flags; const int* rank; int* bounds;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      if (tid > NSHAPE) return;
+      const int g = gen.gid_begin[tid];
+      bounds[tid] = g >= ngr ? rank[ngr - 1] + flags[ngr - 1] : rank[g];
     });
   }
 };

@@ -27,6 +27,133 @@ namespace mce {
 #define MCE_NOINLINE
 #endif
 
+// ---------------------------------------------------------------------------------------------
+// K2 for max_shape <= 16: DCE-TP with bitmaps.  The visited set F[2^m] of cell_enumeration.hpp:735 is a 2^m-bit
+// bitmap (atomicOr tells the first visitor), "restriction is a parent cell" (ce:790-798) is a bit test in the
+// parent's key bitmap, "the opposite was accepted too" (ce:816-852) a bit test in the accepted bitmap, and the
+// surviving half is enumerated in ascending key order from that bitmap -- no hash table, no sort.
+// ---------------------------------------------------------------------------------------------
+struct KTpDce2 {
+  static constexpr int kMaxThreads = 128, kMinBlocks = 6;
+  StepParams sp; GenView gen; ParentWs ws; int NW /* 2^max_shape / 32 */; int* diag;
+  static MCE_HD size_t smem_bytes(int NW, int nthreads) {
+    return sizeof(double) * MAXM * MAXD + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int r = c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
+    const unsigned* pkeys = gen_keys(gen, gid, phc);
+    unsigned* out = ws.tpB + (long long)r * ws.tpB_stride;
+    if (m == phc) {                       // Gamma fully coaligned: B is unchanged (est:680-685)
+      c.par([&](int tid) { for (int i = tid; i < pcells; i += c.nthreads()) out[i] = pkeys[i]; if (tid == 0) ws.tpB_cells[r] = pcells; });
+      return;
+    }
+    if (m < d) {                          // ce:681-687: trivial keys, the cell count keeps its previous value
+      c.par([&](int tid) { for (int i = tid; i < pcells; i += c.nthreads()) out[i] = (unsigned)i; if (tid == 0) ws.tpB_cells[r] = pcells; });
+      return;
+    }
+    if (m == d) {                         // ce:454-459: no combinations exist for m <= d -> empty table (serial-path behaviour)
+      c.par([&](int tid) { if (tid == 0) ws.tpB_cells[r] = 0; });
+      return;
+    }
+    double* sA = (double*)c.smem();
+    unsigned* bmVis = (unsigned*)(sA + MAXM * MAXD);      // visited sign vectors (m bits)
+    unsigned* bmAcc = bmVis + NW;                        // accepted sign vectors
+    unsigned* bmPar = bmAcc + NW;                        // parent keys (phc bits)
+    unsigned* niv = bmPar + NW;
+    unsigned* cmask = niv + c.nthreads();
+    int* cnt = (int*)(cmask + c.nthreads());
+    unsigned short* pf = (unsigned short*)(cnt + 8);
+    const int nwM = m >= 5 ? (1 << (m - 5)) : 1, nwP = phc >= 5 ? (1 << (phc - 5)) : 1;
+    const double* Ag = ws.A + (long long)r * sp.max_shape * d;
+    c.par([&](int tid) {
+      for (int i = tid; i < m * d; i += c.nthreads()) sA[i] = Ag[i];
+      for (int i = tid; i < nwM; i += c.nthreads()) { bmVis[i] = 0; bmAcc[i] = 0; }
+      for (int i = tid; i < nwP; i += c.nthreads()) bmPar[i] = 0;
+    });
+    c.par([&](int tid) { for (int i = tid; i < pcells; i += c.nthreads()) { const unsigned k = pkeys[i]; c.atomic_or(&bmPar[k >> 5], 1u << (k & 31)); } });
+    const long long ncombo = (long long)binom_u64(m, d);
+    const int two_to_d = 1 << d;
+    const unsigned phc_mask = (1u << phc) - 1u, top_phc = 1u << (phc - 1);
+    for (long long base = 0; base < ncombo; base += c.nthreads()) {
+      c.par([&](int tid) {                 // vertex of d hyperplanes with the perturbed offsets (ce:741-776)
+        cmask[tid] = 0;
+        const long long ci = base + tid;
+        if (ci >= ncombo) return;
+        int combo[MAXD]; double Ac[MAXD * MAXD], bc[MAXD], vertex[MAXD];
+        unrank_combo(ci, m, d, combo);
+        unsigned cm = 0;
+        for (int j = 0; j < d; j++) {
+          for (int l = 0; l < d; l++) Ac[j * d + l] = sA[combo[j] * d + l];
+          bc[j] = sp.b_pert[combo[j]]; cm |= (1u << combo[j]);
+        }
+        if (!solve_vertex(Ac, bc, vertex, d)) return;
+        unsigned sgn = 0;
+        for (int ac = 0; ac < m; ac++) {
+          if ((cm >> ac) & 1u) continue;
+          if ((dot_lr(sA + ac * d, vertex, d) - sp.b_pert[ac]) < 0) sgn |= (1u << ac);
+        }
+        niv[tid] = sgn; cmask[tid] = cm;
+      });
+      c.par([&](int tid) {                 // encircle every vertex: 2^d sign patterns on the combo rows (ce:778-812)
+        const long long items = (long long)c.nthreads() * two_to_d;
+        MCE_NOUNROLL for (long long it = tid; it < items; it += c.nthreads()) {
+          const int slot = (int)(it / two_to_d), pat = (int)(it % two_to_d);
+          const unsigned cm = cmask[slot];
+          if (!cm) continue;
+          unsigned sv = niv[slot], rest = cm; int bit = 0;
+          while (rest) { const int row = MCE_FFS(rest); rest &= rest - 1u; if ((pat >> bit) & 1) sv |= (1u << row); bit++; }
+          const unsigned vbit = 1u << (sv & 31);
+          if (bmVis[sv >> 5] & vbit) continue;                       // cheap pre-test
+          if (c.atomic_or(&bmVis[sv >> 5], vbit) & vbit) continue;   // somebody else was first
+          unsigned psv = sv & phc_mask;
+          if (psv & top_phc) psv ^= phc_mask;
+          if (!((bmPar[psv >> 5] >> (psv & 31)) & 1u)) continue;     // Check 1: restriction must be a parent cell
+          c.atomic_or(&bmAcc[sv >> 5], vbit);
+        }
+      });
+    }
+    // Check 2 (ce:816-852): keep cells whose opposite was accepted too, store the half with bit m-1 clear.
+    const unsigned rev_m = (1u << m) - 1u;
+    const int nwH = m >= 6 ? (1 << (m - 6)) : 1;                     // words holding keys with bit m-1 clear
+    c.par([&](int tid) {
+      for (int w = tid; w < nwH; w += c.nthreads()) {
+        unsigned bits = bmAcc[w], keep = 0;
+        if (m < 6) bits &= (1u << (1 << (m - 1))) - 1u;              // tiny arrangements: lower half of the single word
+        while (bits) {
+          const int b = MCE_FFS(bits); bits &= bits - 1u;
+          const unsigned key = (unsigned)(w * 32 + b), opp = key ^ rev_m;
+          if ((bmAcc[opp >> 5] >> (opp & 31)) & 1u) keep |= 1u << b;
+        }
+        bmVis[w] = keep;                                             // bmVis is free now: reuse it for the surviving half
+      }
+    });
+    // prefix popcounts + ordered enumeration
+    if (nwH <= 64) {
+      c.par([&](int tid) {
+        if (tid >= nwH) return;
+        int sacc = 0;
+        for (int i = 0; i < tid; i++) sacc += MCE_POPC(bmVis[i]);
+        pf[tid] = (unsigned short)sacc;
+        if (tid == nwH - 1) cnt[0] = sacc + MCE_POPC(bmVis[tid]);
+      });
+    } else {
+      c.par([&](int tid) {
+        if (tid != 0) return;
+        int sacc = 0;
+        for (int i = 0; i < nwH; i++) { pf[i] = (unsigned short)sacc; sacc += MCE_POPC(bmVis[i]); }
+        cnt[0] = sacc;
+      });
+    }
+    c.par([&](int tid) {
+      for (int w = tid; w < nwH; w += c.nthreads()) {
+        unsigned bits = bmVis[w]; int o = pf[w];
+        while (bits) { const int b = MCE_FFS(bits); bits &= bits - 1u; out[o++] = (unsigned)(w * 32 + b); }
+      }
+      if (tid == 0) ws.tpB_cells[r] = cnt[0];
+    });
+  }
+};
+
 constexpr int G2_CHUNK = 32;      // members staged per chunk
 
 struct Group2Member {              // everything the kernel needs to know about one member, gathered in one parallel phase

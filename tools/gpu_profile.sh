@@ -20,6 +20,9 @@ c=[int(m.group(1)) for m in re.finditer(r"cumulative (\d+)", open("gpurun_out/pr
 print(c[10]-1)
 PY
 )
+echo "=== DRAM traffic of every KGTable launch"
+timeout 900 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:KGTable --csv --log-file gpurun_out/gtable_traffic_$R.csv python tools/profile_pass.py leo7 > /dev/null 2>&1
+python tools/traffic_json.py gpurun_out/gtable_traffic_$R.csv > gpurun_out/traffic_$R.json; cat gpurun_out/traffic_$R.json
 echo "=== ncu full capture of the last KGTable launch of MU 11 (skip $SKIP)"
 timeout 1200 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:KGTable -s $SKIP -c 1 -o gpurun_out/prof_gtable_$R -f python tools/profile_pass.py leo7 11 > gpurun_out/ncu_full_$R.log 2>&1
 tail -3 gpurun_out/ncu_full_$R.log
