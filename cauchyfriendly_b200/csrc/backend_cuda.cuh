@@ -36,6 +36,8 @@ __global__ void __launch_bounds__(launch_traits<K>::max_threads, launch_traits<K
 
 struct CudaBackend {
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;       // second stream: the serial moment sums overlap regroup + FTR
+  cudaEvent_t side_ev = nullptr;
   int device = 0;
   long long launch_count = 0;
   void* cub_tmp = nullptr;
@@ -54,6 +56,8 @@ struct CudaBackend {
       if (dev >= 0) MCE_CUDA_CHECK(cudaSetDevice(dev));
       MCE_CUDA_CHECK(cudaGetDevice(&device));
       MCE_CUDA_CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      MCE_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+      MCE_CUDA_CHECK(cudaEventCreateWithFlags(&side_ev, cudaEventDisableTiming));
     } catch (const std::exception& ex) { *why = ex.what(); return false; }
     return true;
   }
@@ -61,6 +65,9 @@ struct CudaBackend {
     if (cub_tmp) cudaFree(cub_tmp);
     cub_tmp = nullptr; cub_tmp_bytes = 0;
     for (int i = 0; i < 8; i++) if (evs[i]) { cudaEventDestroy(evs[i]); evs[i] = nullptr; }
+    if (side_ev) cudaEventDestroy(side_ev);
+    if (side) cudaStreamDestroy(side);
+    side = nullptr; side_ev = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -73,6 +80,7 @@ struct CudaBackend {
   }
   void free(void* p) {
     cudaStreamSynchronize(stream);
+    if (side) cudaStreamSynchronize(side);
     cudaFree(p);
   }
   void h2d(void* d, const void* s, size_t n) { MCE_CUDA_CHECK(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream)); MCE_CUDA_CHECK(cudaStreamSynchronize(stream)); }
@@ -99,14 +107,19 @@ struct CudaBackend {
   }
 
   template <class K>
-  void launch(const K& k, int nblocks, int nthreads, size_t smem) {
+  void launch_on(cudaStream_t st, const K& k, int nblocks, int nthreads, size_t smem) {
     if (nblocks <= 0) return;
     static_assert(sizeof(K) <= 32000, "kernel functor exceeds the 32 KB parameter space (CUDA >= 12.1, sm_70+)");
     if (smem > 48 * 1024) MCE_CUDA_CHECK(cudaFuncSetAttribute(mce_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    mce_kernel_entry<K><<<nblocks, nthreads, smem, stream>>>(k);
+    mce_kernel_entry<K><<<nblocks, nthreads, smem, st>>>(k);
     MCE_CUDA_CHECK(cudaGetLastError());
     launch_count++;
   }
+  template <class K> void launch(const K& k, int nblocks, int nthreads, size_t smem) { launch_on(stream, k, nblocks, nthreads, smem); }
+  // side stream: starts after everything queued on the main stream so far; side_join() blocks the host until it is idle
+  void side_begin() { MCE_CUDA_CHECK(cudaEventRecord(side_ev, stream)); MCE_CUDA_CHECK(cudaStreamWaitEvent(side, side_ev, 0)); }
+  template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch_on(side, k, nblocks, nthreads, smem); }
+  void side_join() { MCE_CUDA_CHECK(cudaStreamSynchronize(side)); }
   void ensure_tmp(size_t bytes) {
     if (bytes > cub_tmp_bytes) {
       if (cub_tmp) { cudaStreamSynchronize(stream); cudaFree(cub_tmp); }

@@ -372,16 +372,25 @@ class Engine {
     stats.ms_mu = be.toc(tph); tph = be.tic();
 
     // ---- moments (K3 tail): serial-order fz, two-level mean/covariance sums ----
+    // The sums run on the side stream: nothing before the G-table build needs them, so they overlap regroup + FTR.
     double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    be.side_begin();
     if (fast_moments) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
-      be.launch(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
-      be.launch(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
-      be.launch(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
+      be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
+      be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
+      be.launch_side(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
     } else {
-      be.launch(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
+      be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
+    auto finish_moments = [&]() {
+      std::vector<double> raw(2 * nq);
+      be.side_join();
+      be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
+      finalize_moments(raw.data(), true);
+      sp.gscale = G_SCALE_FACTOR;
+    };
 
     // ---- canonical ranks of the new terms inside their new shapes ----
     const int nchunks = (int)((nslots + RANK_CHUNK - 1) / RANK_CHUNK);
@@ -389,11 +398,8 @@ class Engine {
     int* totals = (int*)rankTotals.ensure(sizeof(int) * 2 * NSHAPE + 64);
     be.launch(KRankCount{sl, nchunks, counts}, nchunks, RANK_CHUNK, sizeof(int) * 2 * NSHAPE);
     be.launch(KRankScan{nchunks, counts, totals}, 2 * NSHAPE, 32, 0);
-    std::vector<double> raw(2 * nq); std::vector<int> tot(2 * NSHAPE);
-    be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
+    std::vector<int> tot(2 * NSHAPE);
     be.d2h(tot.data(), totals, sizeof(int) * 2 * NSHAPE);
-    finalize_moments(raw.data(), true);
-    sp.gscale = G_SCALE_FACTOR;
     stats.ms_moments = be.toc(tph); tph = be.tic();
 
     TermView tv; memset(&tv, 0, sizeof(tv));
@@ -408,6 +414,7 @@ class Engine {
     tv.t_begin[NSHAPE] = nterms;
     Nt_muc = (int)nterms; stats.terms_after_muc = nterms;
     if (skip_post_mu) {          // est:732-733, 806-828: only the counts change on the window's last step
+      finish_moments();
       terms_per_shape = muc_per_shape; Nt = (int)nterms; finished = true;
       return 0;
     }
@@ -448,11 +455,17 @@ class Engine {
       const int nb = (n + 127) / 128;
       be.launch(KFtrKeys{tv, m, d, tr_order[0], k0, i0, F}, nb, 128, 0);
       be.sort_pairs(k0, k1, i0, i1, n);                     // k1 = sorted keys, i1 = term index at each sorted position
-      be.launch(KFtrWide{tv, m, d, tr_order[0], k1, wide}, nb, 128, 0);
+      be.memset(unk + 2, 0, 2 * sizeof(int));
+      be.launch(KFtrWide{tv, m, d, tr_order[0], k1, wide, (unsigned long long*)(unk + 2)}, nb, 128, 0);
+      unsigned long long dens = 0; be.d2h(&dens, unk + 2, sizeof(dens));
+      // mean epsilon-window population on the sorted axis decides the round kernel: dense clusters (many candidates per
+      // term) amortise the shared-memory staging of the tiled kernel, sparse data is faster with direct scans
+      const bool tiled = (double)dens * 16.0 / (double)n > 24.0;
       int rounds = 0;
       for (;;) {
         be.memset(unk, 0, sizeof(int));
-        be.launch(KFtrRoundTiled{tv, sp, m, k1, i1, wide, F, unk}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
+        if (tiled) be.launch(KFtrRoundTiled{tv, sp, m, k1, i1, wide, F, unk}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
+        else be.launch(KFtrRound{tv, sp, m, k1, i1, wide, F, unk}, nb, 128, 0);
         int nu = 0; be.d2h(&nu, unk, sizeof(int));
         rounds++;
         if (nu == 0) break;
@@ -477,6 +490,8 @@ class Engine {
     stats.ms_ftr = be.toc(tph); tph = be.tic();
 
     // ---- K7/K8: child B-tables and G-tables, one CTA per reduction group ----
+    finish_moments();            // G_SCALE_FACTOR = 1 / (2 pi Re fz) scales every new G (flat:227)
+    stats.ms_moments += be.toc(tph); tph = be.tic();
     fill_gen_layout(ng, n_groups);
     unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);

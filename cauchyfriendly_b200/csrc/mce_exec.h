@@ -38,6 +38,12 @@ struct DevCtx {
   __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
   __device__ __forceinline__ unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
   __device__ __forceinline__ int load_relaxed(const int* p) { return *(const volatile int*)p; }
+  // 16-byte asynchronous global -> shared copy (LDGSTS); the data is visible after cp_async_wait() + a barrier
+  __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
+  }
+  __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory"); }
 };
 #endif
 

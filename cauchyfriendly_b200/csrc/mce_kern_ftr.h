@@ -56,7 +56,7 @@ struct KFtrKeys {
 
 // wide[i]: the root's own axis-0 window holds at least two points (the `(gti - lti) > 2` gate, tr:121)
 struct KFtrWide {
-  TermView tv; int m, d, axis0; const unsigned long long* skeys; unsigned char* wide;
+  TermView tv; int m, d, axis0; const unsigned long long* skeys; unsigned char* wide; unsigned long long* density /* sum of window sizes */;
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
       const int i = c.block() * c.nthreads() + tid;
@@ -72,6 +72,7 @@ struct KFtrWide {
       while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= khi) lo = mid + 1; else hi = mid; }
       const int gti = lo;
       wide[i] = (gti - lti) > 2;
+      if ((i & 15) == 0) c.atomic_add_u64(density, (unsigned long long)(gti - lti - 1));   // 1/16 sample of the window sizes
     });
   }
 };

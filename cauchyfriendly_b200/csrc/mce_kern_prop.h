@@ -283,46 +283,34 @@ struct KMsmtUpdate {
 // slot 0, 1, 2, ... in slot order, the order of the reference's cache_moments loop (parents in shape/index order,
 // each followed by its children).  Unused slots hold g = y = 0 and leave the accumulators unchanged, so the sums
 // are bit-identical to the NUM_CPUS = 1 reference.
-// Layout: block b owns MOM_QB complex quantities; warp 0 keeps their 2*MOM_QB running sums (one lane each) and
-// walks the slots serially.  The other warps run a two-stage software pipeline ahead of it: while warp 0 sums
-// tile t they compute the addends of tile t+1 from a shared-memory copy of (g, y) and stage the raw (g, y) of
-// tile t+2 from HBM with coalesced loads.  The serial DADD chain of warp 0 is the critical path.
-constexpr int MOM_QB = 2, MOM_TILE = 256;
+// Layout: block b owns MOM_QB complex quantities; lanes 0..2*MOM_QB-1 of warp 0 keep their running sums and walk the
+// slots serially: that dependent DADD chain (8 cycles per slot on B200) is the critical path.  The other warps run a
+// software pipeline ahead of it: cp.async stages the raw (g, y) of tile t+3 while the addends of tile t+1 are computed
+// from shared memory; only warps that do not share warp 0's scheduler partition (warp id % 4 != 0) do fp64 work.
+constexpr int MOM_QB = 2, MOM_TILE = 256, MOM_RAW = 3;
 struct KMomentsSerial {
   const cplx* g; const double* y; long long n; int d; double* out /*[2*(1+d+d*d)]*/;
-  static MCE_HD size_t smem_bytes(int d) { return sizeof(double) * (2 * MOM_QB + 2 * MOM_TILE * 2 * MOM_QB + 2 * MOM_TILE * (2 + 2 * d)); }
+  static MCE_HD size_t smem_bytes(int d) { return sizeof(double) * (2 * MOM_QB + 2 * MOM_TILE * 2 * MOM_QB + MOM_RAW * MOM_TILE * (2 + 2 * d)) + 64; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     const int nq = 1 + d + d * d, qbase = c.block() * MOM_QB, NA = 2 * MOM_QB, W = 2 + 2 * d;
-    double* accs = (double*)c.smem();
-    double* buf = accs + NA;                          // [2][MOM_TILE][NA]  addends
-    double* raw = buf + 2 * MOM_TILE * NA;            // [2][MOM_TILE][W]   (g.re, g.im, y[0..2d))
+    double* raw = (double*)c.smem();                  // [MOM_RAW][MOM_TILE][W]   (g.re, g.im, y[0..2d)); 16-byte aligned rows
+    double* buf = raw + MOM_RAW * MOM_TILE * W;       // [2][MOM_TILE][NA]  addends
+    double* accs = buf + 2 * MOM_TILE * NA;
     const long long ntiles = (n + MOM_TILE - 1) / MOM_TILE;
     auto tile_cnt = [&](long long t) { const long long s0 = t * MOM_TILE; return (int)((n - s0) < MOM_TILE ? (n - s0) : MOM_TILE); };
-    auto stage = [&](long long t, int lane, int nlanes) {            // HBM -> raw[t & 1]: 16-byte loads, all issued before the first store
+    auto stage = [&](long long t, int lane, int nlanes) {            // HBM -> raw[t % MOM_RAW], asynchronously, 16 bytes per copy
       const long long s0 = t * MOM_TILE; const int cnt = tile_cnt(t);
-      double* rt = raw + (t & 1) * MOM_TILE * W;
-      const cplx* gs = g + s0; const cplx* ys = (const cplx*)(y + s0 * 2 * d);   // y rows are d (re, im) pairs; 16-byte aligned
+      double* rt = raw + (t % MOM_RAW) * MOM_TILE * W;
+      const cplx* gs = g + s0; const cplx* ys = (const cplx*)(y + s0 * 2 * d);   // y rows are d (re, im) pairs
       const int nvec = cnt * (1 + d);
-      cplx v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) { const int e = lane + u * nlanes; if (e < nvec) v[u] = e < cnt ? gs[e] : ys[e - cnt]; }
-#pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const int e = lane + u * nlanes;
-        if (e < nvec) {
-          double* dst = e < cnt ? rt + e * W : rt + ((e - cnt) / d) * W + 2 + 2 * ((e - cnt) % d);
-          dst[0] = v[u].re; dst[1] = v[u].im;
-        }
-      }
-      for (int e = lane + 8 * nlanes; e < nvec; e += nlanes) {         // only reached with very few staging threads
-        const cplx w = e < cnt ? gs[e] : ys[e - cnt];
-        double* dst = e < cnt ? rt + e * W : rt + ((e - cnt) / d) * W + 2 + 2 * ((e - cnt) % d);
-        dst[0] = w.re; dst[1] = w.im;
+      for (int e = lane; e < nvec; e += nlanes) {
+        if (e < cnt) c.cp_async16(rt + e * W, gs + e);
+        else { const int r = (e - cnt) / d, k = (e - cnt) % d; c.cp_async16(rt + r * W + 2 + 2 * k, ys + (e - cnt)); }
       }
     };
-    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t & 1] -> buf[t & 1]; a lane keeps one quantity
+    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t % MOM_RAW] -> buf[t & 1]; a lane keeps one quantity
       const int cnt = tile_cnt(t);
-      const double* rt = raw + (t & 1) * MOM_TILE * W;
+      const double* rt = raw + (t % MOM_RAW) * MOM_TILE * W;
       double* bt = buf + (t & 1) * MOM_TILE * NA;
       const int ql = lane % MOM_QB, q = qbase + ql, step = nlanes / MOM_QB;
       if (lane >= step * MOM_QB) return;
@@ -341,20 +329,21 @@ struct KMomentsSerial {
         bt[sidx * NA + 2 * ql] = w.re; bt[sidx * NA + 2 * ql + 1] = w.im;
       }
     };
-    // Roles: lanes 0..NA-1 of warp 0 own the running sums.  Warps 1.. stage; of those, only the warps that do not share
-    // warp 0's scheduler partition (warp id % 4 != 0) compute addends, so their fp64 work never queues in front of the
-    // dependent DADD chain that is this kernel's critical path.
     const int nstage = c.nthreads() - 32;
     auto prod_lane = [&](int tid, int* lane, int* nlanes) {       // producer index among warps with id % 4 != 0, or -1
       const int w = tid >> 5;
       *nlanes = ((c.nthreads() >> 5) - ((c.nthreads() >> 5) + 3) / 4) * 32;
       *lane = (w & 3) ? ((w - 1 - (w >> 2)) * 32 + (tid & 31)) : -1;
     };
-    c.par([&](int tid) { if (tid < NA) accs[tid] = 0; if (tid >= 32 && ntiles > 0) stage(0, tid - 32, nstage); });
+    // prologue: tiles 0 and 1 staged and landed, tile 2 in flight, addends of tile 0 ready
+    c.par([&](int tid) {
+      if (tid < NA) accs[tid] = 0;
+      if (tid >= 32) { if (ntiles > 0) stage(0, tid - 32, nstage); if (ntiles > 1) stage(1, tid - 32, nstage); c.cp_async_wait(); }
+    });
     c.par([&](int tid) {
       int pl, pn; prod_lane(tid, &pl, &pn);
       if (pl >= 0 && ntiles > 0) produce(0, pl, pn);
-      if (tid >= 32 && ntiles > 1) stage(1, tid - 32, nstage);
+      if (tid >= 32 && ntiles > 2) stage(2, tid - 32, nstage);
     });
     for (long long t = 0; t < ntiles; t++) {
       c.par([&](int tid) {
@@ -376,10 +365,11 @@ struct KMomentsSerial {
           for (; sidx < cnt; sidx++) acc += bt[sidx * NA];
           accs[tid] = acc;
         }
-        // order matters for the shared buffers: produce(t+1) reads raw[(t+1)&1], stage(t+2) then overwrites raw[t&1]
+        // tile t+1: raw landed one phase ago -> addends; tile t+2: wait for its copies; tile t+3: start its copies
+        // (raw[(t+3) % 3] == raw[t % 3] was last read by produce(t) in the previous phase)
         int pl, pn; prod_lane(tid, &pl, &pn);
         if (pl >= 0 && t + 1 < ntiles) produce(t + 1, pl, pn);
-        if (tid >= 32 && t + 2 < ntiles) stage(t + 2, tid - 32, nstage);
+        if (tid >= 32) { c.cp_async_wait(); if (t + 3 < ntiles) stage(t + 3, tid - 32, nstage); }
       });
     }
     c.par([&](int tid) { if (tid < NA && qbase * 2 + tid < 2 * nq) out[qbase * 2 + tid] = accs[tid]; });

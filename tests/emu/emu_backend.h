@@ -32,6 +32,8 @@ struct EmuCtx {
   unsigned atomic_or(unsigned* p, unsigned v) { unsigned o = *p; *p |= v; return o; }
   unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
   int load_relaxed(const int* p) { return *p; }
+  void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+  void cp_async_wait() {}
 };
 
 struct EmuBackend {
@@ -57,6 +59,9 @@ struct EmuBackend {
       k.run(c);
     }
   }
+  void side_begin() {}
+  template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch(k, nblocks, nthreads, smem); }
+  void side_join() {}
   void sort_pairs(const unsigned long long* kin, unsigned long long* kout, const int* vin, int* vout, int n) {
     std::vector<int> idx(n); std::iota(idx.begin(), idx.end(), 0);
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return kin[a] < kin[b]; });

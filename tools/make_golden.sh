@@ -6,6 +6,7 @@ set -e
 cd "$(dirname "$0")/.."
 python tools/gen_scenarios.py tests/golden
 [ -f tests/golden/leo7.mces ] || oracle/_ref/ref_gen_leo7 tests/golden/leo7.mces 4
+[ -f tests/golden/leo5.mces ] || oracle/_ref/ref_gen_leo5 tests/golden/leo5.mces 7
 R=oracle/_ref/ref_run_cpu1
 $R tests/golden/lti3.mces         tests/golden/lti3.ref.mced         --full-upto 5
 $R tests/golden/lti2.mces         tests/golden/lti2.ref.mced         --full-upto 6
@@ -15,6 +16,7 @@ $R tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.ref.mced --full-upto
 $R tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.ref.mced  --full-upto 5
 for n in 2 3 4 5 6 7 8; do $R tests/golden/syn$n.mces tests/golden/syn$n.ref.mced --full-upto 3; done
 $R tests/golden/leo7.mces         tests/golden/leo7.ref.mced         --full-upto 3
+$R tests/golden/leo5.mces         tests/golden/leo5.ref.mced         --full-upto 4 --max-steps 13
 # the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
 oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
 ls -la tests/golden
