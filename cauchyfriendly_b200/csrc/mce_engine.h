@@ -32,6 +32,7 @@ struct StepStats {
   int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
   double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0;   // CUDA-event durations on the stream
   long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0;
+  int big_groups = 0;
 };
 
 template <class BE>
@@ -111,6 +112,9 @@ class Engine {
   DevBuf<BE> tvA, tvp, tvq, tvb, tvmeta, tvcmap, slotOfTerm;
   DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
   DevBuf<BE> ftrF, ftrWide, grpOrder, grpStart, aliveFlag, diagBuf, unkBuf, initBuf;
+  DevBuf<BE> bigGroups, bigParts, bigCnt, bigRows, bigFlags, bigKeys;
+  int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
+  long long big_scratch_cap = 6LL << 30;       // bytes of addend rows above which group splitting is skipped for a step
   // debug capture
   bool capture = false;
   struct CapShape { int m = 0, n = 0; std::vector<double> A, p, q, b, cd; std::vector<int> meta, F; std::vector<unsigned char> cmap; std::vector<signed char> csmap; };
@@ -137,7 +141,7 @@ class Engine {
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
                          &scratchI0, &scratchI1, &scratchI2, &scratchI3, &scratchK0, &scratchK1, &ftrF, &ftrWide, &grpOrder, &grpStart,
-                         &aliveFlag, &diagBuf, &unkBuf, &initBuf};
+                         &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys};
     for (auto* b : all) b->be = &be;
     gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0);
   }
@@ -446,6 +450,20 @@ class Engine {
     std::vector<int> n_groups(NSHAPE, 0), n_phase1(NSHAPE, 0), gstart_off(NSHAPE, 0);
     int goff = 0;
     if (capture) cap.clear();
+    // split-group bookkeeping (KBigGroups): per (phase, shape) a region of group/part descriptors and a counter block
+    std::vector<long long> big_slot_base(2 * NSHAPE, 0), big_part_base(2 * NSHAPE, 0);
+    long long big_slots = 0, big_parts = 0;
+    for (int ph = 0; ph < 2; ph++)
+      for (int m = 1; m < NSHAPE; m++) {
+        big_slot_base[ph * NSHAPE + m] = big_slots; big_part_base[ph * NSHAPE + m] = big_parts;
+        big_slots += tv.n[m] / big_T + 1; big_parts += tv.n[m] / BIG_PART + tv.n[m] / big_T + 2;
+      }
+    BigGroup* bgroups = (BigGroup*)bigGroups.ensure(sizeof(BigGroup) * (size_t)big_slots);
+    BigPart* bparts = (BigPart*)bigParts.ensure(sizeof(BigPart) * (size_t)big_parts);
+    const size_t bigcnt_bytes = (sizeof(unsigned long long) * 3 + sizeof(int) * 2) * 2 * NSHAPE;
+    unsigned long long* bcnt64 = (unsigned long long*)bigCnt.ensure(bigcnt_bytes);      // [2*NSHAPE][3], then int [2*NSHAPE][2]
+    int* bcnt = (int*)(bcnt64 + 3 * 2 * NSHAPE);
+    be.memset(bcnt64, 0, bigcnt_bytes);
     for (int m = 1; m < NSHAPE; m++) {
       const int n = tv.n[m];
       if (n == 0) continue;
@@ -484,6 +502,14 @@ class Engine {
       n_groups[m] = ng_m;
       n_phase1[m] = cr[1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
       be.launch(KGroupFill{n, i2, i3, gstart, ng_m}, nb, 128, 0);
+      if (max_shape <= 16 && n > big_T) {
+        const int Hm = cell_count_central_half(m, d);
+        for (int ph = 0; ph < 2; ph++) {
+          const int ga = ph == 0 ? 0 : n_phase1[m], gb = ph == 0 ? n_phase1[m] : ng_m, ix = ph * NSHAPE + m;
+          if (gb > ga)
+            be.launch(KBigGroups{gstart, ga, gb, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix}, (gb - ga + 127) / 128, 128, 0);
+        }
+      }
       goff += ng_m + 1;
       if (capture) capture_shape(tv, m, F, ws, with_tp);
     }
@@ -497,6 +523,30 @@ class Engine {
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
     const size_t gsm = KGTable::smem_bytes(HC2);
     long long total_groups = 0;
+    // split groups: sizes of the addend scratch (one D2H of the KBigGroups counters), scratch bases per (phase, shape)
+    std::vector<unsigned long long> h64(3 * 2 * NSHAPE, 0); std::vector<int> h32(2 * 2 * NSHAPE, 0);
+    std::vector<long long> rows_base(2 * NSHAPE, 0), flags_base(2 * NSHAPE, 0), keys_base(2 * NSHAPE, 0);
+    bool split = false;
+    cplx* brows = nullptr; int* bflags = nullptr; unsigned* bkeys = nullptr;
+    if (max_shape <= 16) {
+      std::vector<unsigned char> hb(bigcnt_bytes);
+      be.d2h(hb.data(), bcnt64, bigcnt_bytes);
+      memcpy(h64.data(), hb.data(), sizeof(unsigned long long) * h64.size());
+      memcpy(h32.data(), hb.data() + sizeof(unsigned long long) * h64.size(), sizeof(int) * h32.size());
+      long long tr = 0, tf = 0, tk = 0, nbig = 0;
+      for (int ix = 0; ix < 2 * NSHAPE; ix++) {
+        rows_base[ix] = tr; flags_base[ix] = tf; keys_base[ix] = tk;
+        tr += (long long)h64[3 * ix]; tf += (long long)h64[3 * ix + 1]; tk += (long long)h64[3 * ix + 2]; nbig += h32[2 * ix];
+      }
+      stats.big_groups = (int)nbig;
+      if (nbig > 0 && tr * (long long)sizeof(cplx) <= big_scratch_cap) {
+        split = true;
+        brows = (cplx*)bigRows.ensure(sizeof(cplx) * (size_t)tr);
+        bflags = (int*)bigFlags.ensure(sizeof(int) * (size_t)tf);
+        bkeys = (unsigned*)bigKeys.ensure(sizeof(unsigned) * (size_t)tk);
+        be.memset(bflags, 0, sizeof(int) * (size_t)tf);
+      }
+    }
     be.ev_record(2);
     for (int phase = 0; phase < 2; phase++)
       for (int m = 1; m < NSHAPE; m++) {
@@ -508,8 +558,22 @@ class Engine {
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
         if (max_shape <= 16) {
           const int NW = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
-          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], Hcap, NW, aflag, diag};
-          be.launch(k, g1 - g0, nth, KGTable2::smem_bytes(Hcap, NW));
+          const int ix = phase * NSHAPE + m;
+          BigArgs ba; memset(&ba, 0, sizeof(ba));
+          const int nbg = split ? h32[2 * ix] : 0, nbp = split ? h32[2 * ix + 1] : 0;
+          if (nbg > 0) {
+            ba.groups = bgroups + big_slot_base[ix]; ba.parts = bparts + big_part_base[ix];
+            ba.rows = brows + rows_base[ix]; ba.flags = bflags + flags_base[ix]; ba.keys = bkeys + keys_base[ix]; ba.row_stride = Hm;
+          }
+          const int* ord = order_all + tv.t_begin[m]; const int* gst = gstart_all + gstart_off[m];
+          const size_t smb = KGTable2::smem_bytes(Hcap, NW);
+          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba};
+          be.launch(k, g1 - g0, nth, smb);
+          if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
+            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbp, nth, smb);
+            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbg, nth, smb);
+          }
         } else {
           KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
           be.launch(k, g1 - g0, nth, gsm);

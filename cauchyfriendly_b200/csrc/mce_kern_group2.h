@@ -188,7 +188,27 @@ MCE_HD int bitmap_rank(const unsigned* bm, const unsigned short* pf, unsigned ke
   return (int)pf[key >> 5] + MCE_POPC(w & (bit - 1u));
 }
 
-struct KGTable2 {
+// Reduction groups with more than BIG_T members are split over several CTAs: one CTA elects the root (G2_BIG_ROOT), CTAs
+// of BIG_PART members each store their members' addends (G2_BIG_PARTS), one CTA adds them in member order (G2_BIG_FINAL).
+// A group of thousands of members (LTI problems: many children coincide) would otherwise serialise in one CTA.
+constexpr int BIG_T = 192, BIG_PART = 48;
+enum { G2_NORMAL = 0, G2_BIG_ROOT = 1, G2_BIG_PARTS = 2, G2_BIG_FINAL = 3 };
+struct BigGroup { int gi, ncomb, nparts, part_base; long long rows_off, flags_off, keys_off; int hdr[4]; /* nB, root term, accepted, accepted candidate */ };
+struct BigPart { int slot, part; };
+struct BigArgs { BigGroup* groups; const BigPart* parts; cplx* rows; int* flags; unsigned* keys; int row_stride; };
+
+// "member has no cell here" marker inside a stored addend row (adding +0.0 instead would not be exact for a -0.0 sum)
+MCE_HD cplx skip_addend() {
+  union { double d; unsigned long long u; } v; v.u = 0x7ff8dead0000beefULL;
+  return make_cplx(v.d, 0.0);
+}
+MCE_HD bool is_skip_addend(const cplx& x) {
+  union { double d; unsigned long long u; } v; v.d = x.re;
+  return v.u == 0x7ff8dead0000beefULL;
+}
+
+template <int MODE>
+struct KGTable2T {
   static constexpr int kMaxThreads = 128, kMinBlocks = 8;   // 64 registers: 8 CTAs (32 warps) per SM
   StepParams sp; GenView prev; GenView next; ParentWs ws; TermView tv;
   int m, g0;
@@ -196,6 +216,8 @@ struct KGTable2 {
   int HC;                       // capacity of the per-cell arrays (max cells of any table this step)
   int NW;                       // bitmap words: 2^max_shape / 32
   unsigned char* alive_flag; int* diag;
+  int big_T;                    // G2_NORMAL: groups with more members are left to the split launches
+  BigArgs big;
   static MCE_HD size_t smem_bytes(int HC, int NW) {
     return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + 1024) * sizeof(unsigned short) + 64;
   }
@@ -335,33 +357,26 @@ struct KGTable2 {
     return g;
   }
 
-  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int d = sp.d;
-    unsigned char* base = c.smem();
-    Group2Sm* sm = (Group2Sm*)base;
-    cplx* acc = (cplx*)(base + ((sizeof(Group2Sm) + 15) & ~(size_t)15));
-    cplx* Gm = acc + HC;
-    unsigned* Bk = (unsigned*)(Gm + HC);
-    unsigned* bmP = Bk + HC;             // parent-table rank structure of the staged member
-    unsigned* bmA = bmP + NW;            // scratch bitmap: parent B_mu / TP table / final keys
-    unsigned short* pfP = (unsigned short*)(bmA + NW);
-    unsigned short* pfA = pfP + NW + 16 + c.nthreads();   // prefix arrays carry chunk totals behind them
-    const int gi = g0 + c.block();
-    const int start = grp_start[gi], ncomb = grp_start[gi + 1] - start;
-    const int* members = order + start;
-    const int gid_out = next.gid_begin[m] + gi;
-    const unsigned rev_m = (1u << m) - 1u, top_m = 1u << (m - 1);
-    const int nwM = m >= 5 ? (1 << (m - 5)) : 1;
+  // Shared-memory carve-up and group description of one CTA.
+  struct Ws {
+    Group2Sm* sm; cplx* acc; cplx* Gm; unsigned* Bk; unsigned* bmP; unsigned* bmA; unsigned short* pfP; unsigned short* pfA;
+    const int* members; int ncomb, gid_out, nwM, cbase; unsigned rev_m, top_m;
+  };
 
-    // ---- chunk 0 of the member descriptions (root included) ----
-    int cbase = 0;
+  // ---- B-table of the root (K7) and the root's own table, with re-election when the candidate is negligible (flat:399-489).
+  // Returns false when every member is negligible.  `primary` = this CTA owns the group's side effects.
+  template <class Ctx> MCE_KERNEL_FN bool root_phase(Ctx& c, Ws& w, bool primary, int* nB_out, int* k_out, int* rsel_out) const {
+    const int d = sp.d;
+    Group2Sm* sm = w.sm; cplx* acc = w.acc; unsigned* Bk = w.Bk; unsigned* bmP = w.bmP; unsigned* bmA = w.bmA;
+    unsigned short* pfP = w.pfP;
+    const int ncomb = w.ncomb, nwM = w.nwM; const unsigned rev_m = w.rev_m, top_m = w.top_m;
+    const int* members = w.members;
     auto load_chunk = [&](int tid) {
-      if (tid < G2_CHUNK) { sm->flag[tid] = 0; if (cbase + tid < ncomb) load_member(&sm->mem[tid], members[cbase + tid]); }
+      if (tid < G2_CHUNK) { sm->flag[tid] = 0; if (w.cbase + tid < ncomb) load_member(&sm->mem[tid], members[w.cbase + tid]); }
     };
+    w.cbase = 0;
     c.par([&](int tid) { load_chunk(tid); if (tid == 0) sm->owner = -1; });
     const Group2Member* eR = &sm->mem[0];
-
-    // ---- B-table of the root (K7) ----
     int nB = 0;
     if (eR->is_child) {
       if (m <= d) {
@@ -403,9 +418,9 @@ struct KGTable2 {
         });
         bm_prefix(c, bmC, pfP, nwM, &sm->cnt);
         c.par([&](int tid) {            // enumerate the set bits: keys in ascending order
-          MCE_NOUNROLL for (int w = tid; w < nwM; w += c.nthreads()) {
-            unsigned bits = bmC[w]; int o = pfP[w];
-            while (bits) { const int b = MCE_FFS(bits); bits &= bits - 1u; Bk[o++] = (unsigned)(w * 32 + b); }
+          MCE_NOUNROLL for (int wd = tid; wd < nwM; wd += c.nthreads()) {
+            unsigned bits = bmC[wd]; int o = pfP[wd];
+            while (bits) { const int b = MCE_FFS(bits); bits &= bits - 1u; Bk[o++] = (unsigned)(wd * 32 + b); }
           }
         });
         nB = sm->cnt;                    // written two barriers ago; not modified again
@@ -416,14 +431,13 @@ struct KGTable2 {
       c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = eR->parent; });
     }
 
-    // ---- root table, with re-election when the candidate is negligible (flat:399-489) ----
     auto nothing = [](int) {};
     int k = 0, accepted = 0, lfr = -1;
     const Group2Member* e = eR;
     for (;;) {
       // candidate k (chunk-local index kk)
-      if (k - cbase >= G2_CHUNK) { c.par(nothing); cbase = k; c.par([&](int tid) { load_chunk(tid); }); }   // the empty phase keeps slow readers of the old chunk ahead of its reload
-      const int kk = k - cbase;
+      if (k - w.cbase >= G2_CHUNK) { c.par(nothing); w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); }   // the empty phase keeps slow readers of the old chunk ahead of its reload
+      const int kk = k - w.cbase;
       e = &sm->mem[kk];
       if (k > 0 && !e->is_child) {       // old term: its own table becomes the group's table (flat:443-473)
         const unsigned* src; unsigned mask;
@@ -438,27 +452,41 @@ struct KGTable2 {
       }
       c.par([&](int tid) {
         MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm, e, &sm->flag[kk], bmP, pfP, key); }
-        if (sigma && tid == 0 && sm->owner >= 0) c.atomic_xor(ws.bxor + sm->owner, sigma);   // the table is a parent's B memory, shared with its children
+        if (sigma && tid == 0 && sm->owner >= 0 && primary) c.atomic_xor(ws.bxor + sm->owner, sigma);   // the table is a parent's B memory, shared with its children
       });
       if (sm->flag[kk]) { accepted = 1; break; }
       lfr = e->ti;
       if (++k >= ncomb) break;
     }
-    if (!accepted) {
-      c.par([&](int tid) { if (tid == 0) { alive_flag[gid_out] = 0; next.cells[gid_out] = 0; next.g_m[gid_out] = (unsigned char)m; } });
-      return;
-    }
-    const int rsel = e->ti;
+    *nB_out = nB; *k_out = k; *rsel_out = accepted ? e->ti : -1;
+    return accepted != 0;
+  }
 
-    // ---- remaining members (flat:491-550): G table of the member, added cell by cell to the root's ----
-    int pend = 0; bool pend_cj = false;          // deferred "acc += Gm" of the previous member (runs inside the next phase)
+  // ---- members [k_from, k_to) (flat:491-550): G table of the member, added cell by cell to the root's.  When `rows` is
+  // given (split groups) the addends are stored instead -- row k, cell i = what member k adds to root cell i -- and summed
+  // later in member order by final_phase.
+  template <class Ctx> MCE_KERNEL_FN void members_phase(Ctx& c, Ws& w, int nB, int rsel, int k_from, int k_to, cplx* rows, int* rflags, int row_stride) const {
+    Group2Sm* sm = w.sm; cplx* acc = w.acc; cplx* Gm = w.Gm; unsigned* Bk = w.Bk; unsigned* bmP = w.bmP; unsigned* bmA = w.bmA;
+    unsigned short* pfP = w.pfP; unsigned short* pfA = w.pfA;
+    const int ncomb = w.ncomb, nwM = w.nwM; const unsigned rev_m = w.rev_m, top_m = w.top_m;
+    const int* members = w.members;
+    auto load_chunk = [&](int tid) {
+      if (tid < G2_CHUNK) { sm->flag[tid] = 0; if (w.cbase + tid < ncomb) load_member(&sm->mem[tid], members[w.cbase + tid]); }
+    };
+    int pend = 0, pend_k = 0; bool pend_cj = false;          // deferred "acc += Gm" of the previous member (runs inside the next phase)
     auto do_pending = [&](int tid) {
       if (!pend) return;
-      MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) acc[i] = cadd(acc[i], pend_cj ? cconj(Gm[i]) : Gm[i]);
+      if (rows) {
+        cplx* row = rows + (long long)pend_k * row_stride;
+        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) row[i] = pend_cj ? cconj(Gm[i]) : Gm[i];
+        if (tid == 0) rflags[pend_k] = 1;
+      } else {
+        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) acc[i] = cadd(acc[i], pend_cj ? cconj(Gm[i]) : Gm[i]);
+      }
     };
-    for (++k; k < ncomb; ++k) {
-      if (k - cbase >= G2_CHUNK) { c.par([&](int tid) { do_pending(tid); }); pend = 0; cbase = k; c.par([&](int tid) { load_chunk(tid); }); }
-      const int kk = k - cbase;
+    for (int k = k_from; k < k_to; ++k) {
+      if (k - w.cbase >= G2_CHUNK || k < w.cbase) { c.par([&](int tid) { do_pending(tid); }); pend = 0; w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); }
+      const int kk = k - w.cbase;
       const Group2Member* et = &sm->mem[kk];
       stage_member(c, sm, et, bmP, pfP, rsel, do_pending);
       pend = 0;
@@ -471,7 +499,7 @@ struct KGTable2 {
           MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, Bk[i] ^ sigma_n);
           if (!et->is_child && tid == 0) c.atomic_add(diag, 1);     // flat:516-539 also rewrites the parent's B memory: not modelled
         });
-        if (sm->flag[kk]) { pend = 1; pend_cj = cj; }
+        if (sm->flag[kk]) { pend = 1; pend_cj = cj; pend_k = k; }
       } else {
         // old term with its own table: cell i of its B_mu is position i of its (sorted) source table; add by key (flat:291-314)
         const unsigned* src; int nT; unsigned mask;
@@ -485,18 +513,26 @@ struct KGTable2 {
         c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, src[i] ^ mask); });
         if (sm->flag[kk])
           c.par([&](int tid) {
+            cplx* row = rows ? rows + (long long)k * row_stride : nullptr;
             MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) {
               unsigned kq = Bk[i] ^ sigma_raw; bool cjj = false;
               if (kq & top_m) { cjj = true; kq ^= rev_m; }
               const int jj = bitmap_rank(bmT, pfT, kq ^ mask);      // position of the member's cell with key kq
-              if (jj >= 0) acc[i] = cadd(acc[i], cjj ? cconj(Gm[jj]) : Gm[jj]);
+              if (row) row[i] = jj >= 0 ? (cjj ? cconj(Gm[jj]) : Gm[jj]) : skip_addend();
+              else if (jj >= 0) acc[i] = cadd(acc[i], cjj ? cconj(Gm[jj]) : Gm[jj]);
             }
+            if (row && tid == 0) rflags[k] = 1;
           });
       }
     }
+    if (pend) { c.par([&](int tid) { do_pending(tid); }); pend = 0; }
+  }
 
-    // ---- write the surviving term; rank of a key in the bitmap of the final keys = its sorted position (flat:251-252) ----
-    c.par([&](int tid) { do_pending(tid); MCE_NOUNROLL for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
+  // ---- write the surviving term; rank of a key in the bitmap of the final keys = its sorted position (flat:251-252) ----
+  template <class Ctx> MCE_KERNEL_FN void emit(Ctx& c, Ws& w, int nB, int rsel) const {
+    const int d = sp.d, nwM = w.nwM, gid_out = w.gid_out;
+    cplx* acc = w.acc; unsigned* Bk = w.Bk; unsigned* bmA = w.bmA; unsigned short* pfA = w.pfA;
+    c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nwM; i += c.nthreads()) bmA[i] = 0; });
     c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned b = Bk[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
     bm_prefix(c, bmA, pfA, nwM, (int*)nullptr);
     unsigned* ko = gen_keys(next, gid_out, m); cplx* Go = gen_G(next, gid_out, m);
@@ -511,6 +547,104 @@ struct KGTable2 {
         alive_flag[gid_out] = 1; next.cells[gid_out] = nB; next.g_m[gid_out] = (unsigned char)m;
         c.atomic_add_u64((unsigned long long*)(diag + 2), (unsigned long long)nB);
       }
+    });
+  }
+
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    unsigned char* base = c.smem();
+    Ws w;
+    w.sm = (Group2Sm*)base;
+    w.acc = (cplx*)(base + ((sizeof(Group2Sm) + 15) & ~(size_t)15));
+    w.Gm = w.acc + HC;
+    w.Bk = (unsigned*)(w.Gm + HC);
+    w.bmP = w.Bk + HC;             // parent-table rank structure of the staged member
+    w.bmA = w.bmP + NW;            // scratch bitmap: parent B_mu / TP table / final keys
+    w.pfP = (unsigned short*)(w.bmA + NW);
+    w.pfA = w.pfP + NW + 16 + c.nthreads();   // prefix arrays carry chunk totals behind them
+    int gi, part = 0; BigGroup* bg = nullptr;
+    if (MODE == G2_NORMAL) gi = g0 + c.block();
+    else if (MODE == G2_BIG_PARTS) { const BigPart bp = big.parts[c.block()]; bg = big.groups + bp.slot; part = bp.part; gi = bg->gi; }
+    else { bg = big.groups + c.block(); gi = bg->gi; }
+    const int start = grp_start[gi];
+    w.ncomb = grp_start[gi + 1] - start;
+    w.members = order + start;
+    w.gid_out = next.gid_begin[m] + gi;
+    w.rev_m = (1u << m) - 1u; w.top_m = 1u << (m - 1);
+    w.nwM = m >= 5 ? (1 << (m - 5)) : 1;
+    w.cbase = 0;
+    if (MODE == G2_NORMAL) {
+      if (w.ncomb > big_T) return;               // split groups are handled by the G2_BIG_* launches
+      int nB, k, rsel;
+      if (!root_phase(c, w, true, &nB, &k, &rsel)) {
+        c.par([&](int tid) { if (tid == 0) { alive_flag[w.gid_out] = 0; next.cells[w.gid_out] = 0; next.g_m[w.gid_out] = (unsigned char)m; } });
+        return;
+      }
+      members_phase(c, w, nB, rsel, k + 1, w.ncomb, (cplx*)nullptr, (int*)nullptr, 0);
+      emit(c, w, nB, rsel);
+      return;
+    }
+    cplx* rows = big.rows + bg->rows_off; int* rflags = big.flags + bg->flags_off; unsigned* keys = big.keys + bg->keys_off;
+    if (MODE == G2_BIG_ROOT) {                   // root election; the group's keys and the root's own table go to scratch
+      int nB, k, rsel;
+      const bool ok = root_phase(c, w, true, &nB, &k, &rsel);
+      c.par([&](int tid) {
+        if (tid == 0) {
+          bg->hdr[0] = nB; bg->hdr[1] = rsel; bg->hdr[2] = ok ? 1 : 0; bg->hdr[3] = k;
+          if (!ok) { alive_flag[w.gid_out] = 0; next.cells[w.gid_out] = 0; next.g_m[w.gid_out] = (unsigned char)m; }
+        }
+        if (ok) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { keys[i] = w.Bk[i]; rows[i] = w.acc[i]; } }
+      });
+      return;
+    }
+    const int nB = bg->hdr[0], rsel = bg->hdr[1], ok = bg->hdr[2], kacc = bg->hdr[3];
+    if (!ok) return;
+    if (MODE == G2_BIG_PARTS) {                  // BIG_PART members of one split group; their addends go to scratch rows
+      const int lo = 1 + part * BIG_PART, hi = lo + BIG_PART < w.ncomb ? lo + BIG_PART : w.ncomb;
+      const int from = lo > kacc + 1 ? lo : kacc + 1;
+      if (from >= hi) return;
+      c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) w.Bk[i] = keys[i]; });
+      w.cbase = from + 1;                        // forces the first iteration to load its chunk
+      members_phase(c, w, nB, rsel, from, hi, rows, rflags, big.row_stride);
+      return;
+    }
+    // G2_BIG_FINAL: root table + every stored addend, in member order (the order fixes the floating-point sums)
+    c.par([&](int tid) {
+      MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) {
+        w.Bk[i] = keys[i];
+        cplx a = rows[i];
+        MCE_NOUNROLL for (int k = kacc + 1; k < w.ncomb; k++) {
+          if (!rflags[k]) continue;
+          const cplx v = rows[(long long)k * big.row_stride + i];
+          if (!is_skip_addend(v)) a = cadd(a, v);
+        }
+        w.acc[i] = a;
+      }
+    });
+    emit(c, w, nB, rsel);
+  }
+};
+
+using KGTable2 = KGTable2T<G2_NORMAL>;
+
+// Lists the reduction groups of [ga, gb) with more than T members and cuts them into parts of BIG_PART members.
+struct KBigGroups {
+  const int* grp_start; int ga, gb, T, Hm; BigGroup* groups; BigPart* parts; int* cnt /*[2]: groups, parts*/; unsigned long long* cnt64 /*[3]: rows, flags, keys*/;
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      const int gi = ga + c.block() * c.nthreads() + tid;
+      if (gi >= gb) return;
+      const int size = grp_start[gi + 1] - grp_start[gi];
+      if (size <= T) return;
+      BigGroup g;
+      g.gi = gi; g.ncomb = size; g.nparts = (size - 1 + BIG_PART - 1) / BIG_PART;
+      const int slot = c.atomic_add(cnt, 1);
+      g.part_base = c.atomic_add(cnt + 1, g.nparts);
+      g.rows_off = (long long)c.atomic_add_u64(cnt64, (unsigned long long)size * Hm);
+      g.flags_off = (long long)c.atomic_add_u64(cnt64 + 1, (unsigned long long)size);
+      g.keys_off = (long long)c.atomic_add_u64(cnt64 + 2, (unsigned long long)Hm);
+      g.hdr[0] = g.hdr[1] = g.hdr[2] = g.hdr[3] = 0;
+      groups[slot] = g;
+      for (int p = 0; p < g.nparts; p++) { BigPart bp; bp.slot = slot; bp.part = p; parts[g.part_base + p] = bp; }
     });
   }
 };

@@ -40,7 +40,9 @@ typedef struct mce_options {
   int print_basic_info;       /* reference quirk A.9(iii): when set, moments are re-evaluated after FTR      */
   int fast_moments;           /* 0 (default): mean/covariance summed in the reference's serial order (bit-identical to
                                  NUM_CPUS=1); 1: two-level tree reduction (deterministic, differs in the last bits)      */
-  int reserved[7];
+  int group_split_threshold;  /* reduction groups with more members are split over several CTAs; 0 = default (192),
+                                 -1 = never split.  The results do not depend on it.                          */
+  int reserved[6];
 } mce_options;
 
 /* Fills `o` with the defaults (device -1, identity search order). */
@@ -104,6 +106,7 @@ typedef struct mce_step_stats {
   double ev_gtable_ms;                  /* CUDA-event time of the group (B-table + G-table) kernel launches     */
   long long gtable_launches;
   long long cells_parents, cells_survivors;   /* actual table cells read / written by the group kernel          */
+  long long split_groups;               /* reduction groups large enough to be split over several CTAs          */
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 

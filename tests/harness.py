@@ -37,7 +37,7 @@ def load_product():
 
 
 class Session:
-    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False):
+    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0):
         self.lib, self.sc = lib, sc
         o = MceOptions()
         lib.mce_default_options(ct.byref(o))
@@ -46,6 +46,7 @@ class Session:
         o.print_basic_info = int(print_basic_info)
         o.device = int(device)
         o.fast_moments = int(fast_moments)
+        o.group_split_threshold = int(split)
         self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
         self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
         if not self.h:
@@ -117,9 +118,14 @@ class Session:
         return dict(A=A, p=p, q=q, b=b, cd=cd, meta=meta, cmap=cmap, csmap=csmap, F=F)
 
 
-def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False):
+def _ssum(a):
+    a = np.asarray(a, np.float64).ravel()
+    return float(np.add.accumulate(a)[-1]) if a.size else 0.0
+
+
+def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc, print_basic_info=print_basic_info)
+    s = Session(lib, sc, print_basic_info=print_basic_info, split=split)
     out = {}
     d = sc.d
     MS = s.shape_range - 1
@@ -144,7 +150,7 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
             out[sp + "/moments"] = mom
             out[sp + "/gscale"] = np.array([mo.g_scale_factor])
             out[sp + "/stats"] = np.array([st.ms_total, st.ms_tp, st.ms_mu, st.ms_moments, st.ms_regroup, st.ms_ftr, st.ms_gtable, st.ms_compact,
-                                           st.ftr_rounds_max, st.diag_unmodelled_alias, st.diag_hash_overflow, st.kernel_launches])
+                                           st.ftr_rounds_max, st.diag_unmodelled_alias, st.diag_hash_overflow, st.kernel_launches, st.split_groups])
             full = (k + 1) <= full_upto
             if not mo.skip_post_mu:
                 cnt = s.counts(False)
@@ -155,7 +161,7 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
                     e = s.export_shape(m)
                     pre = "%s/ftr/m%d" % (sp, m)
                     out[pre + "/digest"] = key_digest(e["cells"], e["keys"])
-                    out[pre + "/fdigest"] = np.array([np.abs(e["G"]).sum(), e["p"].sum(), np.abs(e["b"]).sum()])
+                    out[pre + "/fdigest"] = np.array([_ssum(np.abs(e["G"])), _ssum(e["p"]), _ssum(np.abs(e["b"]))])   # serial sums, like ref_run.cpp
                     if full:
                         for nm in ("A", "p", "b", "cells", "keys", "G"):
                             out[pre + "/" + nm] = e[nm]

@@ -32,3 +32,16 @@ def test_emulated_kernels_match_golden(emu, name):
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
     assert not probs, "\n".join(probs[:20])
+
+
+@pytest.mark.parametrize("name,steps,full,split", [("lti3", 8, 5, 3), ("lti2", 10, 6, 2), ("lti4_2msmts", 8, 5, 5), ("syn3", 8, 3, 4)])
+def test_split_reduction_groups_match_golden(emu, name, steps, full, split):
+    """Reduction groups above the split threshold take the multi-CTA path (root election / member parts / ordered sum);
+    with a tiny threshold most groups do, and every array must still equal the reference's."""
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
+    got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, split=split)
+    assert max(got["s%d/stats" % k][12] for k in range(2, steps + 1)) > 0, "no group was split"
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
+    assert not probs, "\n".join(probs[:20])
