@@ -99,6 +99,10 @@ struct CudaBackend {
     if (!evs[i]) MCE_CUDA_CHECK(cudaEventCreate(&evs[i]));
     MCE_CUDA_CHECK(cudaEventRecord(evs[i], stream));
   }
+  void ev_record_side(int i) {
+    if (!evs[i]) MCE_CUDA_CHECK(cudaEventCreate(&evs[i]));
+    MCE_CUDA_CHECK(cudaEventRecord(evs[i], side));
+  }
   double ev_elapsed(int i0, int i1) {
     float ms = 0;
     MCE_CUDA_CHECK(cudaEventSynchronize(evs[i1]));

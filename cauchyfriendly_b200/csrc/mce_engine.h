@@ -7,6 +7,7 @@
 
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -30,7 +31,7 @@ struct StepStats {
   long long parents = 0, slots = 0, terms_after_muc = 0, groups = 0, survivors = 0;
   long long bytes_gtable = 0, bytes_step = 0, launches = 0;
   int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
-  double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0;   // CUDA-event durations on the stream
+  double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0, ev_moments_ms = 0;   // CUDA-event durations on the stream
   long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0;
   int big_groups = 0;
 };
@@ -113,6 +114,7 @@ class Engine {
   DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
   DevBuf<BE> ftrF, ftrWide, grpOrder, grpStart, aliveFlag, diagBuf, unkBuf, initBuf;
   DevBuf<BE> bigGroups, bigParts, bigCnt, bigRows, bigFlags, bigKeys;
+  bool phase_timing = false;                    // mce_options.phase_timing
   int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
   long long big_scratch_cap = 6LL << 30;       // bytes of addend rows above which group splitting is skipped for a step
   // debug capture
@@ -313,7 +315,10 @@ class Engine {
     const int nq = 1 + d + d * d;
     stats.parents = n_alive;
     int* diag = (int*)diagBuf.ensure(64); be.memset(diag, 0, 64);
-    double tph = be.tic();
+    // per-phase host timers synchronise the stream; they are off unless mce_options.phase_timing is set
+    auto tic = [&]() { return phase_timing ? be.tic() : 0.0; };
+    auto toc = [&](double t) { return phase_timing ? be.toc(t) : 0.0; };
+    double tph = tic();
 
     // ---- K1/K2: time propagation, Gamma coalignment, B^{k|k-1} ----
     ParentWs ws; memset(&ws, 0, sizeof(ws));
@@ -338,13 +343,13 @@ class Engine {
         const int nth = 128;
         if (max_shape <= 16) {
           const int NWt = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
-          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag}, n_alive, nth, KTpDce2::smem_bytes(NWt, nth));
+          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag}, n_alive, nth, KTpDce2::smem_bytes(NWt, nth, d));
         } else {
           be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag}, n_alive, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
         }
       }
     }
-    stats.ms_tp = be.toc(tph); tph = be.tic();
+    stats.ms_tp = toc(tph); tph = tic();
 
     // ---- K3/K4: measurement update, moment contributions, MU coalignment ----
     SlotView sl; memset(&sl, 0, sizeof(sl));
@@ -373,12 +378,17 @@ class Engine {
       const long long n = (long long)pg.alive_per_shape[m] * (sl.MT[m] + 1);
       if (n > 0) be.launch(KMsmtUpdate{sp, pg.v, ws, sl, m}, (int)((n + 127) / 128), 128, 0);
     }
-    stats.ms_mu = be.toc(tph); tph = be.tic();
+    stats.ms_mu = toc(tph); tph = tic();
 
     // ---- moments (K3 tail): serial-order fz, two-level mean/covariance sums ----
     // The sums run on the side stream: nothing before the G-table build needs them, so they overlap regroup + FTR.
     double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    // The moment kernel isolates its accumulator warp on one scheduler partition (warp id % 4); that mapping only holds when
+    // its CTAs are placed on idle SMs, so the main stream is drained first (measured: 8.4 ms instead of 11.6 ms at 1.1 M slots).
+    be.ev_record(6);
+    be.sync();
     be.side_begin();
+    be.ev_record_side(4);
     if (fast_moments) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
@@ -388,9 +398,11 @@ class Engine {
     } else {
       be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
+    be.ev_record_side(5);
     auto finish_moments = [&]() {
       std::vector<double> raw(2 * nq);
       be.side_join();
+      stats.ev_moments_ms = be.ev_elapsed(4, 5); stats.ev_mu_ms = be.ev_elapsed(0, 6);
       be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
       finalize_moments(raw.data(), true);
       sp.gscale = G_SCALE_FACTOR;
@@ -404,7 +416,7 @@ class Engine {
     be.launch(KRankScan{nchunks, counts, totals}, 2 * NSHAPE, 32, 0);
     std::vector<int> tot(2 * NSHAPE);
     be.d2h(tot.data(), totals, sizeof(int) * 2 * NSHAPE);
-    stats.ms_moments = be.toc(tph); tph = be.tic();
+    stats.ms_moments = toc(tph); tph = tic();
 
     TermView tv; memset(&tv, 0, sizeof(tv));
     long long nterms = 0, tA = 0, tpq = 0;
@@ -430,23 +442,26 @@ class Engine {
     tv.meta = (SlotMeta*)tvmeta.ensure(sizeof(SlotMeta) * (size_t)(nterms + 1));
     tv.cmap = (unsigned char*)tvcmap.ensure((size_t)(nterms + 1) * MAXM);
     long long* sot = (long long*)slotOfTerm.ensure(sizeof(long long) * (size_t)(nterms + 1));
-    be.launch(KRegroup{sp, sl, tv, nchunks, counts, sot}, nchunks, RANK_CHUNK, sizeof(int) * RANK_CHUNK);
-    stats.ms_regroup = be.toc(tph); tph = be.tic();
+    be.launch(KRegroup{sp, sl, tv, nchunks, counts, sot}, nchunks, RANK_CHUNK, KRegroup::smem_bytes());
+    stats.ms_regroup = toc(tph); tph = tic();
 
     // ---- K5/K6: fast term reduction per new shape, reduction groups ----
     int* F_all = (int*)ftrF.ensure(sizeof(int) * (size_t)(nterms + 4));
     unsigned char* wide_all = (unsigned char*)ftrWide.ensure((size_t)nterms + 16);
     int* order_all = (int*)grpOrder.ensure(sizeof(int) * (size_t)(nterms + 4));
     int* gstart_all = (int*)grpStart.ensure(sizeof(int) * (size_t)(nterms + NSHAPE + 4));
-    int max_n = 0;
-    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > max_n) max_n = tv.n[m];
-    unsigned long long* k0 = (unsigned long long*)scratchK0.ensure(sizeof(unsigned long long) * (size_t)(max_n + 4));
-    unsigned long long* k1 = (unsigned long long*)scratchK1.ensure(sizeof(unsigned long long) * (size_t)(max_n + 4));
-    int* i0 = (int*)scratchI0.ensure(sizeof(int) * (size_t)(max_n + 4));
-    int* i1 = (int*)scratchI1.ensure(sizeof(int) * (size_t)(max_n + 4));
-    int* i2 = (int*)scratchI2.ensure(sizeof(int) * (size_t)(max_n + 4));
-    int* i3 = (int*)scratchI3.ensure(sizeof(int) * (size_t)(max_n + 4));
-    int* unk = (int*)unkBuf.ensure(sizeof(int) * (NSHAPE + 8));
+    // The shapes advance in lock-step (every stage is launched for all shapes before its counters are read back), so a step
+    // costs 2 + max_rounds host round trips instead of (2 + rounds) per shape; scratch is laid out per shape by term offset.
+    unsigned long long* k0_all = (unsigned long long*)scratchK0.ensure(sizeof(unsigned long long) * (size_t)(nterms + 4));
+    unsigned long long* k1_all = (unsigned long long*)scratchK1.ensure(sizeof(unsigned long long) * (size_t)(nterms + 4));
+    int* i0_all = (int*)scratchI0.ensure(sizeof(int) * (size_t)(nterms + 4));
+    int* i1_all = (int*)scratchI1.ensure(sizeof(int) * (size_t)(nterms + 4));
+    int* i2_all = (int*)scratchI2.ensure(sizeof(int) * (size_t)(nterms + 4));
+    int* i3_all = (int*)scratchI3.ensure(sizeof(int) * (size_t)(nterms + 4));
+    const size_t unk_bytes = (sizeof(unsigned long long) + 3 * sizeof(int)) * NSHAPE;
+    unsigned long long* dens_d = (unsigned long long*)unkBuf.ensure(unk_bytes + 64);    // [NSHAPE] window populations
+    int* nu_d = (int*)(dens_d + NSHAPE);                                                // [NSHAPE] undecided terms of the round
+    int* cr_d = nu_d + NSHAPE;                                                          // [NSHAPE][2] roots, old-term roots
     std::vector<int> n_groups(NSHAPE, 0), n_phase1(NSHAPE, 0), gstart_off(NSHAPE, 0);
     int goff = 0;
     if (capture) cap.clear();
@@ -464,44 +479,55 @@ class Engine {
     unsigned long long* bcnt64 = (unsigned long long*)bigCnt.ensure(bigcnt_bytes);      // [2*NSHAPE][3], then int [2*NSHAPE][2]
     int* bcnt = (int*)(bcnt64 + 3 * 2 * NSHAPE);
     be.memset(bcnt64, 0, bigcnt_bytes);
-    for (int m = 1; m < NSHAPE; m++) {
-      const int n = tv.n[m];
-      if (n == 0) continue;
-      int* F = F_all + tv.t_begin[m]; unsigned char* wide = wide_all + tv.t_begin[m];
-      int* order = order_all + tv.t_begin[m]; int* gstart = gstart_all + goff;
-      gstart_off[m] = goff;
-      const int nb = (n + 127) / 128;
-      be.launch(KFtrKeys{tv, m, d, tr_order[0], k0, i0, F}, nb, 128, 0);
-      be.sort_pairs(k0, k1, i0, i1, n);                     // k1 = sorted keys, i1 = term index at each sorted position
-      be.memset(unk + 2, 0, 2 * sizeof(int));
-      be.launch(KFtrWide{tv, m, d, tr_order[0], k1, wide, (unsigned long long*)(unk + 2)}, nb, 128, 0);
-      unsigned long long dens = 0; be.d2h(&dens, unk + 2, sizeof(dens));
-      // mean epsilon-window population on the sorted axis decides the round kernel: dense clusters (many candidates per
-      // term) amortise the shared-memory staging of the tiled kernel, sparse data is faster with direct scans
-      const bool tiled = (double)dens * 16.0 / (double)n > 24.0;
-      int rounds = 0;
-      for (;;) {
-        be.memset(unk, 0, sizeof(int));
-        if (tiled) be.launch(KFtrRoundTiled{tv, sp, m, k1, i1, wide, F, unk}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
-        else be.launch(KFtrRound{tv, sp, m, k1, i1, wide, F, unk}, nb, 128, 0);
-        int nu = 0; be.d2h(&nu, unk, sizeof(int));
-        rounds++;
-        if (nu == 0) break;
-        if (rounds > n + 2) { error = "FTR resolution did not converge"; return -3; }
+    std::vector<int> shapes;
+    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > 0) shapes.push_back(m);
+    be.memset(dens_d, 0, unk_bytes);
+    for (int m : shapes) {
+      const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+      be.launch(KFtrKeys{tv, m, d, tr_order[0], k0_all + tb, i0_all + tb, F_all + tb}, nb, 128, 0);
+      be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, i1_all + tb, n);      // k1 = sorted keys, i1 = term index at each sorted position
+      be.launch(KFtrWide{tv, m, d, tr_order[0], k1_all + tb, wide_all + tb, dens_d + m}, nb, 128, 0);
+    }
+    std::vector<unsigned long long> dens(NSHAPE, 0);
+    if (!shapes.empty()) be.d2h(dens.data(), dens_d, sizeof(unsigned long long) * NSHAPE);
+    std::vector<int> active = shapes, nu(NSHAPE, 0);
+    int rounds = 0;
+    while (!active.empty()) {
+      be.memset(nu_d, 0, sizeof(int) * NSHAPE);
+      for (int m : active) {
+        const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+        // mean epsilon-window population on the sorted axis decides the round kernel: dense clusters (many candidates per
+        // term) amortise the shared-memory staging of the tiled kernel, sparse data is faster with direct scans
+        const bool tiled = (double)dens[m] * 16.0 / (double)n > 24.0;
+        if (tiled) be.launch(KFtrRoundTiled{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
+        else be.launch(KFtrRound{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, nb, 128, 0);
       }
-      if (rounds > stats.ftr_rounds_max) stats.ftr_rounds_max = rounds;
-      be.launch(KRootKeys{n, F, k0, i0}, nb, 128, 0);
-      be.sort_pairs(k0, k1, i0, order, n);
-      be.launch(KGroupHeads{n, F, order, i2}, nb, 128, 0);
-      be.exclusive_scan(i2, i3, n);
-      be.memset(unk, 0, 2 * sizeof(int));
-      be.launch(KCountRoots{n, tv.n_old[m], F, unk}, nb, 128, 2 * sizeof(int));
-      int cr[2] = {0, 0};
-      be.d2h(cr, unk, 2 * sizeof(int));
-      const int ng_m = cr[0];
+      be.d2h(nu.data(), nu_d, sizeof(int) * NSHAPE);
+      rounds++;
+      std::vector<int> still;
+      for (int m : active) if (nu[m] != 0) still.push_back(m);
+      active.swap(still);
+      if (rounds > (int)nterms + 2) { error = "FTR resolution did not converge"; return -3; }
+    }
+    stats.ftr_rounds_max = rounds;
+    for (int m : shapes) {
+      const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+      be.launch(KRootKeys{n, F_all + tb, k0_all + tb, i0_all + tb}, nb, 128, 0);
+      be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, order_all + tb, n);
+      be.launch(KGroupHeads{n, F_all + tb, order_all + tb, i2_all + tb}, nb, 128, 0);
+      be.exclusive_scan(i2_all + tb, i3_all + tb, n);
+      be.launch(KCountRoots{n, tv.n_old[m], F_all + tb, cr_d + 2 * m}, nb, 128, 2 * sizeof(int));
+    }
+    std::vector<int> cr(2 * NSHAPE, 0);
+    if (!shapes.empty()) be.d2h(cr.data(), cr_d, sizeof(int) * 2 * NSHAPE);
+    for (int m : shapes) {
+      const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+      const int ng_m = cr[2 * m];
       n_groups[m] = ng_m;
-      n_phase1[m] = cr[1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
-      be.launch(KGroupFill{n, i2, i3, gstart, ng_m}, nb, 128, 0);
+      n_phase1[m] = cr[2 * m + 1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
+      int* gstart = gstart_all + goff;
+      gstart_off[m] = goff;
+      be.launch(KGroupFill{n, i2_all + tb, i3_all + tb, gstart, ng_m}, nb, 128, 0);
       if (max_shape <= 16 && n > big_T) {
         const int Hm = cell_count_central_half(m, d);
         for (int ph = 0; ph < 2; ph++) {
@@ -511,13 +537,13 @@ class Engine {
         }
       }
       goff += ng_m + 1;
-      if (capture) capture_shape(tv, m, F, ws, with_tp);
+      if (capture) capture_shape(tv, m, F_all + tb, ws, with_tp);
     }
-    stats.ms_ftr = be.toc(tph); tph = be.tic();
+    stats.ms_ftr = toc(tph); tph = tic();
 
     // ---- K7/K8: child B-tables and G-tables, one CTA per reduction group ----
     finish_moments();            // G_SCALE_FACTOR = 1 / (2 pi Re fz) scales every new G (flat:227)
-    stats.ms_moments += be.toc(tph); tph = be.tic();
+    stats.ms_moments += toc(tph); tph = tic();
     fill_gen_layout(ng, n_groups);
     unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
@@ -583,7 +609,7 @@ class Engine {
     be.ev_record(3);
     stats.ev_gtable_ms = be.ev_elapsed(2, 3);
     stats.groups = total_groups;
-    stats.ms_gtable = be.toc(tph); tph = be.tic();
+    stats.ms_gtable = toc(tph); tph = tic();
 
     // ---- K9: survivor list of the new generation, parent/child generation swap (util:895) ----
     const int ngr = ng.v.n_groups;
@@ -612,7 +638,7 @@ class Engine {
     Nt = n_surv;
     cur = 1 - cur;
     if (print_basic_info) post_ftr_moments(sp); else fz = make_cplx(1, 0);           // est:1166-1176 (quirk A.9 iii)
-    stats.ms_compact = be.toc(tph);
+    stats.ms_compact = toc(tph);
     // algorithmic bytes with the ACTUAL table sizes: every compulsory input read once, every output
     // written once, the post-MUC term payload written + read once (FTR is a global barrier). A table cell is
     // 4 B key + 16 B complex value in this layout (the reference's padded KeyCValue + B entry is 28 B).

@@ -92,21 +92,21 @@ struct KFtrRound {
       // conservative scan bounds around b_j on the primary axis; ftr_match applies the exact interval test
       const double slack = 4.0 * REDUCTION_EPS + 8.0 * fabs(bj[ax0]) * 2.3e-16;
       const unsigned long long klo = f64_sort_key(bj[ax0] - slack), khi = f64_sort_key(bj[ax0] + slack);
+      // Ascending scan of the window.  Only the lowest-index matching candidate matters (a root there decides j, an undecided
+      // term there postpones j), so candidates at or above the best index so far are skipped without touching their data;
+      // the sort is stable, hence a cluster of coincident terms is visited in index order and costs one match per term.
       int min_root = 0x7fffffff, min_unknown = 0x7fffffff;
-      for (int dir = 0; dir < 2; dir++) {
-        int q = dir ? pos + 1 : pos - 1;
-        while (q >= 0 && q < n) {
-          const unsigned long long kq = skeys[q];
-          if (dir ? (kq > khi) : (kq < klo)) break;
-          const int i = sidx[q];
-          if (i < j && i < min_root && wide[i]) {
-            const int Fi = c.load_relaxed(F + i);
-            if ((Fi == i || Fi == -1) && ftr_match(term_b(tv, m, i, d), bj, term_p(tv, m, i), pj, term_A(tv, m, i, d), Aj, m, d, sp.tr_order)) {
-              if (Fi == i) { if (i < min_root) min_root = i; }
-              else if (i < min_unknown) min_unknown = i;
-            }
+      int qs = pos;
+      while (qs > 0 && skeys[qs - 1] >= klo) qs--;
+      for (int q = qs; q < n; q++) {
+        if (q == pos) continue;
+        if (skeys[q] > khi) break;
+        const int i = sidx[q];
+        if (i < j && i < min_root && i < min_unknown && wide[i]) {
+          const int Fi = c.load_relaxed(F + i);
+          if ((Fi == i || Fi == -1) && ftr_match(term_b(tv, m, i, d), bj, term_p(tv, m, i), pj, term_A(tv, m, i, d), Aj, m, d, sp.tr_order)) {
+            if (Fi == i) min_root = i; else min_unknown = i;
           }
-          q += dir ? 1 : -1;
         }
       }
       if (min_unknown < min_root) { c.atomic_add(n_unknown, 1); return; }   // an undecided lower term could still claim j
@@ -184,13 +184,12 @@ struct KFtrRoundTiled {
           int min_root = tmin[2 * t], min_unknown = tmin[2 * t + 1];
           for (int q = 0; q < cn; q++) {
             const int i = cidx[q];
-            if (!(i < j && i < min_root) || ckey[q] < klo || ckey[q] > khi || !cw[q]) continue;
+            if (!(i < j && i < min_root && i < min_unknown) || ckey[q] < klo || ckey[q] > khi || !cw[q]) continue;   // only the lowest matching index matters
             const int Fi = cF[q];
             if (Fi != i && Fi != -1) continue;
             const double* ri = cdat + q * W;
             if (!ftr_match(ri, rj, ri + d, rj + d, ri + d + m, rj + d + m, m, d, sp.tr_order)) continue;
-            if (Fi == i) { if (i < min_root) min_root = i; }
-            else if (i < min_unknown) min_unknown = i;
+            if (Fi == i) min_root = i; else min_unknown = i;
           }
           tmin[2 * t] = min_root; tmin[2 * t + 1] = min_unknown;
         }

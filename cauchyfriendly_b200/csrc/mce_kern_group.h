@@ -116,6 +116,50 @@ MCE_HD bool solve_vertex(double* Ac, const double* bc, double* vertex, int n) {
   return true;
 }
 
+// Strided variants for matrices kept in shared memory, one matrix per thread: element (i, j) lives at A[(i*n + j) * st],
+// so that consecutive threads touch consecutive words (no bank conflicts, no local-memory traffic).
+MCE_HD int plu_small_s(double* A, int st, int* P, int n, double tol) {
+  for (int j = 0; j < n; ++j) {
+    double pivot = tol; int pivot_ind = -1;
+    for (int i = j; i < n; ++i) { const double v = A[(i * n + j) * st]; if (fabs(v) > fabs(pivot)) { pivot = v; pivot_ind = i; } }
+    if (pivot_ind == -1) return 1;
+    if (pivot_ind != j) for (int q = 0; q < n; q++) { const double t = A[(j * n + q) * st]; A[(j * n + q) * st] = A[(pivot_ind * n + q) * st]; A[(pivot_ind * n + q) * st] = t; }
+    P[j] = pivot_ind;
+    const double piv = A[(j * n + j) * st];
+    for (int k = j + 1; k < n; ++k) {
+      const double temp = A[(k * n + j) * st] / piv;
+      A[(k * n + j) * st] = temp;
+      for (int q = j + 1; q < n; q++) A[(k * n + q) * st] -= temp * A[(j * n + q) * st];
+    }
+  }
+  return 0;
+}
+MCE_HD void fwd_back_solve_s(const double* LU, int st, double* b, int n) {
+  for (int i = 0; i < n; i++) { double sol = b[i]; for (int j = 0; j < i; j++) sol -= LU[(i * n + j) * st] * b[j]; b[i] = sol; }
+  for (int i = n - 1; i >= 0; i--) { double sol = b[i]; for (int j = n - 1; j > i; j--) sol -= LU[(i * n + j) * st] * b[j]; b[i] = sol / LU[(i * n + i) * st]; }
+}
+MCE_HD bool solve_vertex_s(double* Ac, int st, const double* bc, double* vertex, int n) {
+  int P[MAXD], P_T[MAXD];
+  double norm_val = -1;
+  for (int i = 0; i < n; i++) { double v = 0; for (int j = 0; j < n; j++) v += fabs(Ac[(j * n + i) * st]); if (v > norm_val) norm_val = v; }
+  if (plu_small_s(Ac, st, P, n, PLU_EPS)) return false;
+  perm_transpose(P, P_T, n);
+  double inv_norm = -1;
+  for (int i = 0; i < n; i++) {
+    double w[MAXD];
+    for (int j = 0; j < n; j++) w[j] = 0;
+    w[P_T[i]] = 1;
+    fwd_back_solve_s(Ac, st, w, n);
+    double v = 0;
+    for (int j = 0; j < n; j++) v += fabs(w[j]);
+    if (v > inv_norm) inv_norm = v;
+  }
+  if (norm_val * inv_norm > COND_EPS) return false;
+  for (int i = 0; i < n; i++) vertex[P_T[i]] = bc[i];
+  fwd_back_solve_s(Ac, st, vertex, n);
+  return true;
+}
+
 struct KTpDce {
   StepParams sp; GenView gen; ParentWs ws; int vis_cap /*pow2*/, acc_cap /*pow2*/; int* diag;
   static MCE_HD size_t smem_bytes(int vis_cap, int acc_cap, int nthreads) {

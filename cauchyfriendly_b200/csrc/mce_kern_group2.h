@@ -36,8 +36,8 @@ namespace mce {
 struct KTpDce2 {
   static constexpr int kMaxThreads = 128, kMinBlocks = 6;
   StepParams sp; GenView gen; ParentWs ws; int NW /* 2^max_shape / 32 */; int* diag;
-  static MCE_HD size_t smem_bytes(int NW, int nthreads) {
-    return sizeof(double) * MAXM * MAXD + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
+  static MCE_HD size_t smem_bytes(int NW, int nthreads, int d) {
+    return sizeof(double) * (MAXM * MAXD + (size_t)d * d * nthreads) + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
   }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     const int r = c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
@@ -56,7 +56,8 @@ struct KTpDce2 {
       return;
     }
     double* sA = (double*)c.smem();
-    unsigned* bmVis = (unsigned*)(sA + MAXM * MAXD);      // visited sign vectors (m bits)
+    double* sAc = sA + MAXM * MAXD;                      // [d*d][nthreads] one vertex system per thread
+    unsigned* bmVis = (unsigned*)(sAc + (size_t)d * d * c.nthreads());      // visited sign vectors (m bits)
     unsigned* bmAcc = bmVis + NW;                        // accepted sign vectors
     unsigned* bmPar = bmAcc + NW;                        // parent keys (phc bits)
     unsigned* niv = bmPar + NW;
@@ -72,21 +73,23 @@ struct KTpDce2 {
     });
     c.par([&](int tid) { for (int i = tid; i < pcells; i += c.nthreads()) { const unsigned k = pkeys[i]; c.atomic_or(&bmPar[k >> 5], 1u << (k & 31)); } });
     const long long ncombo = (long long)binom_u64(m, d);
-    const int two_to_d = 1 << d;
     const unsigned phc_mask = (1u << phc) - 1u, top_phc = 1u << (phc - 1);
-    for (long long base = 0; base < ncombo; base += c.nthreads()) {
+    const int NT = c.nthreads();
+    const int LB = d < 4 ? d : 4, per_slot = 1 << (d - LB);           // a thread walks 2^LB sign patterns of one vertex in Gray-code order
+    for (long long base = 0; base < ncombo; base += NT) {
       c.par([&](int tid) {                 // vertex of d hyperplanes with the perturbed offsets (ce:741-776)
         cmask[tid] = 0;
         const long long ci = base + tid;
         if (ci >= ncombo) return;
-        int combo[MAXD]; double Ac[MAXD * MAXD], bc[MAXD], vertex[MAXD];
+        int combo[MAXD]; double bc[MAXD], vertex[MAXD];
+        double* Ac = sAc + tid;            // this thread's d x d system, element e at Ac[e * NT]
         unrank_combo(ci, m, d, combo);
         unsigned cm = 0;
         for (int j = 0; j < d; j++) {
-          for (int l = 0; l < d; l++) Ac[j * d + l] = sA[combo[j] * d + l];
+          for (int l = 0; l < d; l++) Ac[(j * d + l) * NT] = sA[combo[j] * d + l];
           bc[j] = sp.b_pert[combo[j]]; cm |= (1u << combo[j]);
         }
-        if (!solve_vertex(Ac, bc, vertex, d)) return;
+        if (!solve_vertex_s(Ac, NT, bc, vertex, d)) return;
         unsigned sgn = 0;
         for (int ac = 0; ac < m; ac++) {
           if ((cm >> ac) & 1u) continue;
@@ -95,20 +98,26 @@ struct KTpDce2 {
         niv[tid] = sgn; cmask[tid] = cm;
       });
       c.par([&](int tid) {                 // encircle every vertex: 2^d sign patterns on the combo rows (ce:778-812)
-        const long long items = (long long)c.nthreads() * two_to_d;
-        MCE_NOUNROLL for (long long it = tid; it < items; it += c.nthreads()) {
-          const int slot = (int)(it / two_to_d), pat = (int)(it % two_to_d);
+        const int items = NT * per_slot;
+        MCE_NOUNROLL for (int it = tid; it < items; it += NT) {
+          const int slot = it / per_slot, blk = it - slot * per_slot;
           const unsigned cm = cmask[slot];
           if (!cm) continue;
-          unsigned sv = niv[slot], rest = cm; int bit = 0;
-          while (rest) { const int row = MCE_FFS(rest); rest &= rest - 1u; if ((pat >> bit) & 1) sv |= (1u << row); bit++; }
-          const unsigned vbit = 1u << (sv & 31);
-          if (bmVis[sv >> 5] & vbit) continue;                       // cheap pre-test
-          if (c.atomic_or(&bmVis[sv >> 5], vbit) & vbit) continue;   // somebody else was first
-          unsigned psv = sv & phc_mask;
-          if (psv & top_phc) psv ^= phc_mask;
-          if (!((bmPar[psv >> 5] >> (psv & 31)) & 1u)) continue;     // Check 1: restriction must be a parent cell
-          c.atomic_or(&bmAcc[sv >> 5], vbit);
+          unsigned long long rowpos = 0; unsigned rest = cm;            // 5-bit positions of the combo rows, ascending
+          for (int b = 0; rest; b++) { const int row = MCE_FFS(rest); rest &= rest - 1u; rowpos |= (unsigned long long)row << (5 * b); }
+          const unsigned g0 = (unsigned)blk << LB, gray0 = g0 ^ (g0 >> 1);
+          unsigned sv = niv[slot];
+          for (int b = 0; b < d; b++) if ((gray0 >> b) & 1u) sv |= 1u << (unsigned)((rowpos >> (5 * b)) & 31u);
+          MCE_NOUNROLL for (int i = 0; i < (1 << LB); i++) {
+            if (i) { const int b = MCE_FFS((unsigned)i); sv ^= 1u << (unsigned)((rowpos >> (5 * b)) & 31u); }   // Gray code: one row flips
+            const unsigned vbit = 1u << (sv & 31);
+            if (bmVis[sv >> 5] & vbit) continue;                       // cheap pre-test
+            if (c.atomic_or(&bmVis[sv >> 5], vbit) & vbit) continue;   // somebody else was first
+            unsigned psv = sv & phc_mask;
+            if (psv & top_phc) psv ^= phc_mask;
+            if (!((bmPar[psv >> 5] >> (psv & 31)) & 1u)) continue;     // Check 1: restriction must be a parent cell
+            c.atomic_or(&bmAcc[sv >> 5], vbit);
+          }
         }
       });
     }

@@ -457,42 +457,63 @@ struct KRankScan {      // exclusive scan over chunks for every bin; one block p
     });
   }
 };
-struct KRegroup {       // one block per chunk; thread 0 assigns ranks in slot order, then all threads copy payloads
+// One block per chunk of RANK_CHUNK slots.  Phase 1: the bin (kind, new shape) of every slot.  Phase 2: the canonical rank of
+// every slot = chunk base of its bin + number of earlier slots of the chunk in the same bin; the small per-term fields
+// (meta, b, coalignment map) move here.  Phase 3: the hyperplane payload moves as one flattened (slot, element) loop, so
+// every thread has many independent loads in flight (the copy is pure HBM traffic).
+struct RegroupDesc { int rank, m; long long a_src, a_dst, pq_src, pq_dst; };
+struct KRegroup {
   StepParams sp; SlotView sl; TermView tv; int nchunks; const int* counts; long long* slot_of_term;
+  static MCE_HD size_t smem_bytes() { return (sizeof(RegroupDesc) + sizeof(int)) * RANK_CHUNK + 16; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    int* dst = (int*)c.smem();       // [RANK_CHUNK] destination rank (-1 = unused slot)
+    RegroupDesc* desc = (RegroupDesc*)c.smem();            // [RANK_CHUNK]
+    int* bin = (int*)(desc + RANK_CHUNK);                  // [RANK_CHUNK] kind * NSHAPE + new shape, -1 = unused slot
+    const int d = sp.d;
+    const long long slot0 = (long long)c.block() * RANK_CHUNK;
     c.par([&](int tid) {
-      if (tid != 0) return;
-      int run[2 * NSHAPE];
-      for (int i = 0; i < 2 * NSHAPE; i++) run[i] = counts[(long long)i * nchunks + c.block()];
-      for (int k = 0; k < RANK_CHUNK; k++) {
-        const long long slot = (long long)c.block() * RANK_CHUNK + k;
-        dst[k] = -1;
-        if (slot >= sl.n_slots) continue;
-        const SlotMeta& me = sl.meta[slot];
-        if (!me.newm) continue;
-        const int kind = me.flags & 1;
-        dst[k] = (kind ? tv.n_old[me.newm] : 0) + run[kind * NSHAPE + me.newm]++;
+      for (int k = tid; k < RANK_CHUNK; k += c.nthreads()) {
+        const long long slot = slot0 + k;
+        int b = -1;
+        if (slot < sl.n_slots) { const SlotMeta& me = sl.meta[slot]; if (me.newm) b = (me.flags & 1) * NSHAPE + me.newm; }
+        bin[k] = b;
       }
     });
-    const int d = sp.d;
-    c.par([&](int tid) {          // a 32-thread team per slot: coalesced row copies, no barriers needed
-      const int team = tid >> 5, lane = tid & 31, nteams = c.nthreads() >> 5;
-      for (int k = team; k < RANK_CHUNK; k += nteams) {
-        const int rank = dst[k];
-        if (rank < 0) continue;
-        const long long slot = (long long)c.block() * RANK_CHUNK + k;
-        const SlotMeta me = sl.meta[slot];
-        const int m = me.newm, ms = slot_region(sl, slot), MT = sl.MT[ms];
-        const long long ls = slot - sl.slot_begin[ms];
-        const double* Ai = sl.A + sl.A_off[ms] + ls * (long long)MT * d; const double* pi = sl.p + sl.pq_off[ms] + ls * MT; const double* qi = sl.q + sl.pq_off[ms] + ls * MT;
-        double* Ao = term_A(tv, m, rank, d); double* po = term_p(tv, m, rank); double* qo = term_q(tv, m, rank); double* bo = term_b(tv, m, rank, d);
-        for (int i = lane; i < m * d; i += 32) Ao[i] = Ai[i];
-        for (int i = lane; i < m; i += 32) { po[i] = pi[i]; qo[i] = qi[i]; }
-        for (int i = lane; i < d; i += 32) bo[i] = sl.b[slot * d + i];
-        const long long gt = tv.t_begin[m] + rank;
-        if (lane < MAXM) tv.cmap[gt * MAXM + lane] = sl.cmap[slot * MAXM + lane];
-        if (lane == 0) { tv.meta[gt] = me; slot_of_term[gt] = slot; }
+    c.par([&](int tid) {
+      for (int k = tid; k < RANK_CHUNK; k += c.nthreads()) {
+        const int b = bin[k];
+        RegroupDesc e; e.rank = -1; e.m = 0; e.a_src = e.a_dst = e.pq_src = e.pq_dst = 0;
+        if (b >= 0) {
+          int before = 0;
+          for (int j = 0; j < k; j++) before += (bin[j] == b);
+          const long long slot = slot0 + k;
+          const SlotMeta me = sl.meta[slot];
+          const int m = me.newm, kind = me.flags & 1, ms = slot_region(sl, slot), MT = sl.MT[ms];
+          const int rank = (kind ? tv.n_old[m] : 0) + counts[(long long)b * nchunks + c.block()] + before;
+          const long long ls = slot - sl.slot_begin[ms];
+          e.rank = rank; e.m = m;
+          e.a_src = sl.A_off[ms] + ls * (long long)MT * d; e.a_dst = tv.A_base[m] + (long long)rank * m * d;
+          e.pq_src = sl.pq_off[ms] + ls * MT; e.pq_dst = tv.pq_base[m] + (long long)rank * m;
+          const long long gt = tv.t_begin[m] + rank;
+          double* bo = tv.b + gt * d; const double* bi = sl.b + slot * d;
+          for (int i = 0; i < d; i++) bo[i] = bi[i];
+          const unsigned long long* ci = (const unsigned long long*)(sl.cmap + slot * MAXM); unsigned long long* co = (unsigned long long*)(tv.cmap + gt * MAXM);
+          for (int i = 0; i < MAXM / 8; i++) co[i] = ci[i];
+          tv.meta[gt] = me; slot_of_term[gt] = slot;
+        }
+        desc[k] = e;
+      }
+    });
+    const int EA = sp.max_shape * d, EP = sp.max_shape;
+    c.par([&](int tid) {
+      for (int e = tid; e < RANK_CHUNK * EA; e += c.nthreads()) {
+        const int k = e / EA, i = e - k * EA;
+        const RegroupDesc& ds = desc[k];
+        if (ds.rank >= 0 && i < ds.m * d) tv.A[ds.a_dst + i] = sl.A[ds.a_src + i];
+      }
+      for (int e = tid; e < RANK_CHUNK * EP; e += c.nthreads()) {
+        const int k = e / EP, i = e - k * EP;
+        const RegroupDesc& ds = desc[k];
+        if (ds.rank >= 0 && i < ds.m) { tv.p[ds.pq_dst + i] = sl.p[ds.pq_src + i]; tv.q[ds.pq_dst + i] = sl.q[ds.pq_src + i]; }
       }
     });
   }

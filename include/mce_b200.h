@@ -42,7 +42,9 @@ typedef struct mce_options {
                                  NUM_CPUS=1); 1: two-level tree reduction (deterministic, differs in the last bits)      */
   int group_split_threshold;  /* reduction groups with more members are split over several CTAs; 0 = default (192),
                                  -1 = never split.  The results do not depend on it.                          */
-  int reserved[6];
+  int phase_timing;           /* 1: fill the per-phase ms_* fields of mce_step_stats (adds a stream synchronisation
+                                 after every phase of a step); 0 (default): only the CUDA-event totals are measured */
+  int reserved[5];
 } mce_options;
 
 /* Fills `o` with the defaults (device -1, identity search order). */
@@ -107,6 +109,8 @@ typedef struct mce_step_stats {
   long long gtable_launches;
   long long cells_parents, cells_survivors;   /* actual table cells read / written by the group kernel          */
   long long split_groups;               /* reduction groups large enough to be split over several CTAs          */
+  double ev_moments_ms;                 /* CUDA-event time of the moment sums on the side stream                  */
+  double ev_mu_ms;                      /* CUDA-event time from the start of the step to the end of the measurement update */
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 

@@ -50,6 +50,7 @@ struct EmuBackend {
   double toc(double t0) { return tic() - t0; }
   double ev_t[8] = {0};
   void ev_record(int i) { ev_t[i] = tic(); }
+  void ev_record_side(int i) { ev_t[i] = tic(); }
   double ev_elapsed(int i0, int i1) { return ev_t[i1] - ev_t[i0]; }
   template <class K> void launch(const K& k, int nblocks, int nthreads, size_t smem) {
     launch_count++;
@@ -59,6 +60,7 @@ struct EmuBackend {
       k.run(c);
     }
   }
+  void sync() {}
   void side_begin() {}
   template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch(k, nblocks, nthreads, smem); }
   void side_join() {}

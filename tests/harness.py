@@ -37,7 +37,7 @@ def load_product():
 
 
 class Session:
-    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0):
+    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0, phase_timing=False):
         self.lib, self.sc = lib, sc
         o = MceOptions()
         lib.mce_default_options(ct.byref(o))
@@ -47,6 +47,7 @@ class Session:
         o.device = int(device)
         o.fast_moments = int(fast_moments)
         o.group_split_threshold = int(split)
+        o.phase_timing = int(phase_timing)
         self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
         self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
         if not self.h:
