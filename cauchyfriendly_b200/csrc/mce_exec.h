@@ -44,7 +44,18 @@ struct DevCtx {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
   }
   __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.commit_group;\ncp.async.wait_all;" ::: "memory"); }
+  // group-wise completion: commit closes the group of copies issued so far; wait_pending2 returns once at most the two
+  // youngest groups of this thread are still in flight
+  __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  __device__ __forceinline__ void cp_async_wait_pending2() { asm volatile("cp.async.wait_group 2;" ::: "memory"); }
 };
+#endif
+
+// Compiler-level fence: memory accesses are not moved across it (no instruction is emitted).
+#if defined(__CUDA_ARCH__)
+#define MCE_SCHED_FENCE() asm volatile("" ::: "memory")
+#else
+#define MCE_SCHED_FENCE() do {} while (0)
 #endif
 
 // Kernel functors expose: template <class Ctx> void run(Ctx&) const.

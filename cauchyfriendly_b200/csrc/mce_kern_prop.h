@@ -283,17 +283,22 @@ struct KMsmtUpdate {
 // slot 0, 1, 2, ... in slot order, the order of the reference's cache_moments loop (parents in shape/index order,
 // each followed by its children).  Unused slots hold g = y = 0 and leave the accumulators unchanged, so the sums
 // are bit-identical to the NUM_CPUS = 1 reference.
-// Layout: block b owns MOM_QB complex quantities; lanes 0..2*MOM_QB-1 of warp 0 keep their running sums and walk the
-// slots serially: that dependent DADD chain (8 cycles per slot on B200) is the critical path.  The other warps run a
-// software pipeline ahead of it: cp.async stages the raw (g, y) of tile t+3 while the addends of tile t+1 are computed
-// from shared memory; only warps that do not share warp 0's scheduler partition (warp id % 4 != 0) do fp64 work.
-constexpr int MOM_QB = 2, MOM_TILE = 256, MOM_RAW = 3;
+// Layout: block q owns ONE complex quantity; lanes 0 and 1 of warp 0 keep its running (re, im) sums and walk the slots
+// serially: that dependent DADD chain (8 cycles per slot on B200) is the critical path.  The other warps run a software
+// pipeline ahead of it: cp.async stages the columns the quantity needs (g, y_j, y_k: 48-byte rows, conflict-free for
+// 16-byte shared loads) of tile t+4 while the addends of tile t+1 are computed from shared memory; only warps that do not
+// share warp 0's scheduler partition (warp id % 4 != 0) do fp64 work.  Large tiles amortise the per-phase barrier.
+constexpr int MOM_QB = 1, MOM_TILE = 768, MOM_RAW = 4, MOM_W = 6;
 struct KMomentsSerial {
   const cplx* g; const double* y; long long n; int d; double* out /*[2*(1+d+d*d)]*/;
-  static MCE_HD size_t smem_bytes(int d) { return sizeof(double) * (2 * MOM_QB + 2 * MOM_TILE * 2 * MOM_QB + MOM_RAW * MOM_TILE * (2 + 2 * d)) + 64; }
+  int dbg = 0;      // tools/ubench/mom_bench.cu only: bit 0 skips the chain, bit 1 the addend production, bit 2 the staging copies
+  static MCE_HD size_t smem_bytes(int) { return sizeof(double) * (2 + 2 * MOM_TILE * 2 + MOM_RAW * MOM_TILE * MOM_W) + 64; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int nq = 1 + d + d * d, qbase = c.block() * MOM_QB, NA = 2 * MOM_QB, W = 2 + 2 * d;
-    double* raw = (double*)c.smem();                  // [MOM_RAW][MOM_TILE][W]   (g.re, g.im, y[0..2d)); 16-byte aligned rows
+    const int nq = 1 + d + d * d, qbase = c.block(), NA = 2, W = MOM_W;
+    const int q = qbase;                              // 0: fz = sum g; 1..d: sum g y_j; d+1..: -sum (g y_j) y_k
+    const int j = q == 0 ? 0 : (q <= d ? q - 1 : (q - 1 - d) / d), k = q <= d ? 0 : (q - 1 - d) % d;
+    const int ncol = q == 0 ? 1 : (q <= d ? 2 : 3);
+    double* raw = (double*)c.smem();                  // [MOM_RAW][MOM_TILE][W]   (g.re, g.im, y_j.re, y_j.im, y_k.re, y_k.im)
     double* buf = raw + MOM_RAW * MOM_TILE * W;       // [2][MOM_TILE][NA]  addends
     double* accs = buf + 2 * MOM_TILE * NA;
     const long long ntiles = (n + MOM_TILE - 1) / MOM_TILE;
@@ -302,31 +307,26 @@ struct KMomentsSerial {
       const long long s0 = t * MOM_TILE; const int cnt = tile_cnt(t);
       double* rt = raw + (t % MOM_RAW) * MOM_TILE * W;
       const cplx* gs = g + s0; const cplx* ys = (const cplx*)(y + s0 * 2 * d);   // y rows are d (re, im) pairs
-      const int nvec = cnt * (1 + d);
-      for (int e = lane; e < nvec; e += nlanes) {
-        if (e < cnt) c.cp_async16(rt + e * W, gs + e);
-        else { const int r = (e - cnt) / d, k = (e - cnt) % d; c.cp_async16(rt + r * W + 2 + 2 * k, ys + (e - cnt)); }
-      }
+      for (int r = lane; r < cnt; r += nlanes) c.cp_async16(rt + r * W, gs + r);
+      if (ncol > 1) for (int r = lane; r < cnt; r += nlanes) c.cp_async16(rt + r * W + 2, ys + (long long)r * d + j);
+      if (ncol > 2) for (int r = lane; r < cnt; r += nlanes) c.cp_async16(rt + r * W + 4, ys + (long long)r * d + k);
     };
-    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t % MOM_RAW] -> buf[t & 1]; a lane keeps one quantity
+    auto produce = [&](long long t, int lane, int nlanes) {          // raw[t % MOM_RAW] -> buf[t & 1]
       const int cnt = tile_cnt(t);
       const double* rt = raw + (t % MOM_RAW) * MOM_TILE * W;
       double* bt = buf + (t & 1) * MOM_TILE * NA;
-      const int ql = lane % MOM_QB, q = qbase + ql, step = nlanes / MOM_QB;
-      if (lane >= step * MOM_QB) return;
-      const int j = q == 0 ? 0 : (q <= d ? q - 1 : (q - 1 - d) / d), k = q <= d ? 0 : (q - 1 - d) % d;
-      for (int sidx = lane / MOM_QB; sidx < cnt; sidx += step) {
+      for (int sidx = lane; sidx < cnt; sidx += nlanes) {
         cplx w = make_cplx(0, 0);
         if (q < nq) {
           const double* row = rt + sidx * W;
           const cplx gv = make_cplx(row[0], row[1]);
           if (q == 0) w = gv;
           else {
-            w = cmul(gv, make_cplx(row[2 + 2 * j], row[3 + 2 * j]));
-            if (q > d) { w = cmul(w, make_cplx(row[2 + 2 * k], row[3 + 2 * k])); w.re = -w.re; w.im = -w.im; }
+            w = cmul(gv, make_cplx(row[2], row[3]));
+            if (q > d) { w = cmul(w, make_cplx(row[4], row[5])); w.re = -w.re; w.im = -w.im; }
           }
         }
-        bt[sidx * NA + 2 * ql] = w.re; bt[sidx * NA + 2 * ql + 1] = w.im;
+        bt[sidx * NA] = w.re; bt[sidx * NA + 1] = w.im;
       }
     };
     const int nstage = c.nthreads() - 32;
@@ -335,28 +335,31 @@ struct KMomentsSerial {
       *nlanes = ((c.nthreads() >> 5) - ((c.nthreads() >> 5) + 3) / 4) * 32;
       *lane = (w & 3) ? ((w - 1 - (w >> 2)) * 32 + (tid & 31)) : -1;
     };
-    // prologue: tiles 0 and 1 staged and landed, tile 2 in flight, addends of tile 0 ready
+    // prologue: tiles 0..3 requested (one cp.async group each), tiles 0 and 1 landed, addends of tile 0 ready
     c.par([&](int tid) {
       if (tid < NA) accs[tid] = 0;
-      if (tid >= 32) { if (ntiles > 0) stage(0, tid - 32, nstage); if (ntiles > 1) stage(1, tid - 32, nstage); c.cp_async_wait(); }
+      if (tid >= 32) {
+        for (int t0 = 0; t0 < MOM_RAW; t0++) { if (t0 < ntiles) stage(t0, tid - 32, nstage); c.cp_async_commit(); }
+        c.cp_async_wait_pending2();
+      }
     });
     c.par([&](int tid) {
       int pl, pn; prod_lane(tid, &pl, &pn);
       if (pl >= 0 && ntiles > 0) produce(0, pl, pn);
-      if (tid >= 32 && ntiles > 2) stage(2, tid - 32, nstage);
     });
     for (long long t = 0; t < ntiles; t++) {
       c.par([&](int tid) {
-        if (tid < NA) {
+        if (tid < NA && !(dbg & 1)) {
           const int cnt = tile_cnt(t);
           const double* bt = buf + (t & 1) * MOM_TILE * NA + tid;
           double acc = accs[tid];
           int sidx = 0;
-          if (cnt >= 8) {      // register double-buffering: the next 8 addends are in flight while the current 8 are added
+          if (cnt >= 8) {      // register double-buffering: the next 8 addends are loaded, THEN the current 8 are added
             double v0 = bt[0 * NA], v1 = bt[1 * NA], v2 = bt[2 * NA], v3 = bt[3 * NA], v4 = bt[4 * NA], v5 = bt[5 * NA], v6 = bt[6 * NA], v7 = bt[7 * NA];
             for (sidx = 8; sidx + 8 <= cnt; sidx += 8) {
               const double w0 = bt[(sidx + 0) * NA], w1 = bt[(sidx + 1) * NA], w2 = bt[(sidx + 2) * NA], w3 = bt[(sidx + 3) * NA];
               const double w4 = bt[(sidx + 4) * NA], w5 = bt[(sidx + 5) * NA], w6 = bt[(sidx + 6) * NA], w7 = bt[(sidx + 7) * NA];
+              MCE_SCHED_FENCE();   // keeps every load a full batch (>= 64 cycles) ahead of its use: the chain never waits on shared memory
               acc += v0; acc += v1; acc += v2; acc += v3; acc += v4; acc += v5; acc += v6; acc += v7;
               v0 = w0; v1 = w1; v2 = w2; v3 = w3; v4 = w4; v5 = w5; v6 = w6; v7 = w7;
             }
@@ -365,14 +368,15 @@ struct KMomentsSerial {
           for (; sidx < cnt; sidx++) acc += bt[sidx * NA];
           accs[tid] = acc;
         }
-        // tile t+1: raw landed one phase ago -> addends; tile t+2: wait for its copies; tile t+3: start its copies
-        // (raw[(t+3) % 3] == raw[t % 3] was last read by produce(t) in the previous phase)
+        // tile t+1: raw landed a phase ago -> addends; tile t+4: start its copies (raw[(t+4) % 4] == raw[t % 4] was last read by
+        // produce(t) in the previous phase); then wait until at most the two youngest groups (t+3, t+4) are pending, i.e. tile
+        // t+2 has landed: every copy has two full phases to arrive.
         int pl, pn; prod_lane(tid, &pl, &pn);
-        if (pl >= 0 && t + 1 < ntiles) produce(t + 1, pl, pn);
-        if (tid >= 32) { c.cp_async_wait(); if (t + 3 < ntiles) stage(t + 3, tid - 32, nstage); }
+        if (pl >= 0 && t + 1 < ntiles && !(dbg & 2)) produce(t + 1, pl, pn);
+        if (tid >= 32 && !(dbg & 4)) { if (t + MOM_RAW < ntiles) stage(t + MOM_RAW, tid - 32, nstage); c.cp_async_commit(); c.cp_async_wait_pending2(); }
       });
     }
-    c.par([&](int tid) { if (tid < NA && qbase * 2 + tid < 2 * nq) out[qbase * 2 + tid] = accs[tid]; });
+    c.par([&](int tid) { if (tid < NA && q < nq) out[q * 2 + tid] = accs[tid]; });
   }
 };
 

@@ -34,6 +34,8 @@ struct EmuCtx {
   int load_relaxed(const int* p) { return *p; }
   void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
   void cp_async_wait() {}
+  void cp_async_commit() {}
+  void cp_async_wait_pending2() {}
 };
 
 struct EmuBackend {
