@@ -103,7 +103,7 @@ class Engine {
 
   // ---- device state ----
   struct GenStore {
-    GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G;
+    GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G, rbm, rpf;
     std::vector<int> alive_per_shape;   // survivors per shape
     long long sum_cells = 0;            // total table cells of the survivors
   } gen[2];
@@ -138,7 +138,7 @@ class Engine {
     fz = last_fz = make_cplx(0, 0);
     terms_per_shape.assign(shape_range, 0); muc_per_shape.assign(shape_range, 0);
     terms_per_shape[d] = 1;
-    DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G,
+    DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G, &gen[0].rbm, &gen[0].rpf, &gen[1].rbm, &gen[1].rpf,
                          &gen[1].g_m, &gen[1].cells, &gen[1].alive, &gen[1].A, &gen[1].p, &gen[1].b, &gen[1].keys, &gen[1].G,
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
@@ -159,13 +159,14 @@ class Engine {
   // ------------------------------------------------------------------------------------------
   void fill_gen_layout(GenStore& g, const std::vector<int>& groups_per_shape) {
     GenView& v = g.v;
-    long long gA = 0, gp = 0, gt = 0; int gid = 0;
+    long long gA = 0, gp = 0, gt = 0, gr = 0; int gid = 0;
     for (int m = 0; m < NSHAPE; m++) {
-      v.gid_begin[m] = gid; v.A_base[m] = gA; v.p_base[m] = gp; v.tab_base[m] = gt;
+      v.gid_begin[m] = gid; v.A_base[m] = gA; v.p_base[m] = gp; v.tab_base[m] = gt; v.rk_base[m] = gr;
       const int n = m < (int)groups_per_shape.size() ? groups_per_shape[m] : 0;
       const int stride = m >= 1 ? cell_count_central_half(m, d) : 0;
       v.tab_stride[m] = stride;
       gid += n; gA += (long long)n * m * d; gp += (long long)n * m; gt += (long long)n * stride;
+      if (max_shape <= 16 && m <= 16) gr += (long long)n * rank_words(m);
     }
     v.gid_begin[NSHAPE] = gid; v.n_groups = gid;
     v.g_m = (unsigned char*)g.g_m.ensure((size_t)gid + 16);
@@ -176,6 +177,8 @@ class Engine {
     v.b = (double*)g.b.ensure(sizeof(double) * ((size_t)gid * d + 8));
     v.keys = (unsigned*)g.keys.ensure(sizeof(unsigned) * (size_t)(gt + 8));
     v.G = (cplx*)g.G.ensure(sizeof(cplx) * (size_t)(gt + 8));
+    v.rbm = (unsigned*)g.rbm.ensure(sizeof(unsigned) * (size_t)(gr + 8));
+    v.rpf = (unsigned short*)g.rpf.ensure(sizeof(unsigned short) * (size_t)(gr + 8));
   }
 
   StepParams make_params(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
@@ -315,6 +318,10 @@ class Engine {
     const int nq = 1 + d + d * d;
     stats.parents = n_alive;
     int* diag = (int*)diagBuf.ensure(64); be.memset(diag, 0, 64);
+    if (max_shape <= 16 && n_alive > 0) {        // rank structures of the parents' tables (lookups without binary search)
+      int mmax = 1; for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) mmax = m;
+      be.launch(KBuildRank{pg.v}, n_alive, 64, KBuildRank::smem_bytes(rank_words(mmax), 64));
+    }
     // per-phase host timers synchronise the stream; they are off unless mce_options.phase_timing is set
     auto tic = [&]() { return phase_timing ? be.tic() : 0.0; };
     auto toc = [&](double t) { return phase_timing ? be.toc(t) : 0.0; };

@@ -15,18 +15,6 @@
 
 namespace mce {
 
-#if defined(__CUDA_ARCH__)
-#define MCE_POPC(x) __popc(x)
-#define MCE_FFS(x) (__ffs((int)(x)) - 1)
-#define MCE_NOINLINE __noinline__
-#define MCE_NOUNROLL _Pragma("unroll 1")
-#else
-#define MCE_NOUNROLL
-#define MCE_POPC(x) __builtin_popcount(x)
-#define MCE_FFS(x) (__builtin_ffs((int)(x)) - 1)
-#define MCE_NOINLINE
-#endif
-
 // ---------------------------------------------------------------------------------------------
 // K2 for max_shape <= 16: DCE-TP with bitmaps.  The visited set F[2^m] of cell_enumeration.hpp:735 is a 2^m-bit
 // bitmap (atomicOr tells the first visitor), "restriction is a parent cell" (ce:790-798) is a bit test in the
@@ -167,6 +155,7 @@ constexpr int G2_CHUNK = 32;      // members staged per chunk
 
 struct Group2Member {              // everything the kernel needs to know about one member, gathered in one parallel phase
   int ti, parent, gidp, phc, pc, own_cells;
+  long long rk_off;                // parent's rank structure inside prev.rbm / prev.rpf
   unsigned hflag, enc_lhp, csneg, mask, kflip;
   unsigned char z, is_child, has_cmap, pbc;
   double c, d, psq;
@@ -175,9 +164,9 @@ struct Group2Member {              // everything the kernel needs to know about 
 
 struct Group2Sm {
   int cnt, owner, pad0, pad1;
-  unsigned sgbits[MAXM];           // per-row orientation bits of the member being staged (update_btable's sigma)
+  unsigned sgbits[2][MAXM];        // per-row orientation bits of a staged member (update_btable's sigma); slot = member index & 1
   int flag[G2_CHUNK];              // per member: some cell is not negligible
-  double q[MAXM];
+  double q[2][MAXM];
   Group2Member mem[G2_CHUNK];
 };
 
@@ -190,12 +179,57 @@ MCE_HD double flip_sign(double x, unsigned neg) {
 #endif
 }
 
-// rank of `key` among the set bits of bm (pf = exclusive prefix popcounts per word), or -1 when absent
-MCE_HD int bitmap_rank(const unsigned* bm, const unsigned short* pf, unsigned key) {
-  const unsigned w = bm[key >> 5], bit = 1u << (key & 31);
-  if (!(w & bit)) return -1;
-  return (int)pf[key >> 5] + MCE_POPC(w & (bit - 1u));
+// exclusive prefix popcounts of a bitmap; *total (may be null) receives the number of set bits
+template <class Ctx> MCE_KERNEL_FN MCE_NOINLINE void bm_prefix_any(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) {
+  if (nw <= 64) {               // one phase: word w sums the popcounts below it
+    c.par([&](int tid) {
+      if (tid >= nw) return;
+      int s = 0;
+      for (int i = 0; i < tid; i++) s += MCE_POPC(bm[i]);
+      pf[tid] = (unsigned short)s;
+      if (tid == nw - 1 && total) *total = s + MCE_POPC(bm[tid]);
+    });
+    return;
+  }
+  const int nt = c.nthreads(), chunk = (nw + nt - 1) / nt;
+  c.par([&](int tid) {
+    const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
+    int s = 0;
+    for (int i = lo; i < hi; i++) { pf[i] = (unsigned short)s; s += MCE_POPC(bm[i]); }
+    if (lo < nw) pf[nw + tid] = (unsigned short)s;       // chunk totals live behind the prefix array
+  });
+  c.par([&](int tid) {
+    if (tid != 0) return;
+    int acc = 0;
+    const int nchunks = (nw + chunk - 1) / chunk;
+    for (int k = 0; k < nchunks; k++) { const int v = pf[nw + k]; pf[nw + k] = (unsigned short)acc; acc += v; }
+    if (total) *total = acc;
+  });
+  c.par([&](int tid) {
+    const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
+    if (lo >= nw) return;
+    const unsigned short base = pf[nw + tid];
+    if (base) for (int i = lo; i < hi; i++) pf[i] = (unsigned short)(pf[i] + base);
+  });
 }
+
+
+// Rank structure of every parent table (GenView::rbm / rpf): one CTA per surviving parent.
+struct KBuildRank {
+  GenView gen;
+  static MCE_HD size_t smem_bytes(int nw_max, int nthreads) { return sizeof(unsigned) * (size_t)nw_max + sizeof(unsigned short) * ((size_t)nw_max + nthreads + 16) + 16; }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int gid = gen.alive[c.block()], m = gen_m(gen, gid), nw = rank_words(m), cells = gen.cells[gid];
+    const unsigned* keys = gen_keys(gen, gid, m);
+    const long long off = gen_rk_off(gen, gid, m);
+    unsigned* sbm = (unsigned*)c.smem();
+    unsigned short* spf = (unsigned short*)(sbm + nw);
+    c.par([&](int tid) { for (int i = tid; i < nw; i += c.nthreads()) sbm[i] = 0; });
+    c.par([&](int tid) { for (int i = tid; i < cells; i += c.nthreads()) { const unsigned k = keys[i]; c.atomic_or(&sbm[k >> 5], 1u << (k & 31)); } });
+    bm_prefix_any(c, sbm, spf, nw, (int*)nullptr);
+    c.par([&](int tid) { for (int i = tid; i < nw; i += c.nthreads()) { gen.rbm[off + i] = sbm[i]; gen.rpf[off + i] = spf[i]; } });
+  }
+};
 
 // Reduction groups with more than BIG_T members are split over several CTAs: one CTA elects the root (G2_BIG_ROOT), CTAs
 // of BIG_PART members each store their members' addends (G2_BIG_PARTS), one CTA adds them in member order (G2_BIG_FINAL).
@@ -231,39 +265,7 @@ struct KGTable2T {
     return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + 1024) * sizeof(unsigned short) + 64;
   }
 
-  // exclusive prefix popcounts of a bitmap; *total (may be null) receives the number of set bits
-  template <class Ctx> MCE_KERNEL_FN MCE_NOINLINE void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const {
-    if (nw <= 64) {               // one phase: word w sums the popcounts below it
-      c.par([&](int tid) {
-        if (tid >= nw) return;
-        int s = 0;
-        for (int i = 0; i < tid; i++) s += MCE_POPC(bm[i]);
-        pf[tid] = (unsigned short)s;
-        if (tid == nw - 1 && total) *total = s + MCE_POPC(bm[tid]);
-      });
-      return;
-    }
-    const int nt = c.nthreads(), chunk = (nw + nt - 1) / nt;
-    c.par([&](int tid) {
-      const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
-      int s = 0;
-      for (int i = lo; i < hi; i++) { pf[i] = (unsigned short)s; s += MCE_POPC(bm[i]); }
-      if (lo < nw) pf[nw + tid] = (unsigned short)s;       // chunk totals live behind the prefix array
-    });
-    c.par([&](int tid) {
-      if (tid != 0) return;
-      int acc = 0;
-      const int nchunks = (nw + chunk - 1) / chunk;
-      for (int k = 0; k < nchunks; k++) { const int v = pf[nw + k]; pf[nw + k] = (unsigned short)acc; acc += v; }
-      if (total) *total = acc;
-    });
-    c.par([&](int tid) {
-      const int lo = tid * chunk, hi = lo + chunk < nw ? lo + chunk : nw;
-      if (lo >= nw) return;
-      const unsigned short base = pf[nw + tid];
-      if (base) for (int i = lo; i < hi; i++) pf[i] = (unsigned short)(pf[i] + base);
-    });
-  }
+  template <class Ctx> MCE_KERNEL_FN void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const { bm_prefix_any(c, bm, pf, nw, total); }
 
   // B_mu of a parent as (source keys, count, xor mask): B^{k|k-1} ^ sign(A H) ^ in-place re-orientations
   MCE_HD void parent_B_src(int r, const unsigned** src, int* n, unsigned* mask) const {
@@ -280,6 +282,7 @@ struct KGTable2T {
     const int gidp = prev.alive[me.parent], phc = gen_m(prev, gidp);
     e->ti = ti; e->parent = me.parent; e->gidp = gidp; e->phc = phc; e->pc = prev.cells[gidp];
     e->own_cells = sp.with_tp ? ws.tpB_cells[me.parent] : e->pc;
+    e->rk_off = gen_rk_off(prev, gidp, phc);
     e->hflag = me.hflag; e->enc_lhp = me.enc_lhp; e->csneg = me.csneg; e->mask = ws.sgnmask[me.parent];   // bxor is read when needed (it can change)
     e->z = me.z; e->is_child = me.flags & 1; e->has_cmap = (me.flags >> 1) & 1; e->pbc = me.pbc;
     e->c = me.c_val; e->d = me.d_val;
@@ -299,27 +302,18 @@ struct KGTable2T {
     }
   }
 
-  // Stage member `e`: q, the rank structure (bmP, pfP) of its parent's table, and -- when `ref` >= 0 -- the per-row
-  // orientation bits between term `ref` and this member (ce:586-599).  `pending` is executed by every thread first.
-  template <class Ctx, class Pending> MCE_KERNEL_FN void stage_member(Ctx& c, Group2Sm* sm, const Group2Member* e, unsigned* bmP, unsigned short* pfP, int ref, Pending pending) const {
-    const int phc = e->phc, pc = e->pc;
-    const int nwP = phc >= 5 ? (1 << (phc - 5)) : 1;
-    const unsigned* pk = gen_keys(prev, e->gidp, phc);
-    c.par([&](int tid) {
-      pending(tid);
-      if (tid < m) {
-        sm->q[tid] = ((e->hflag >> tid) & 1u) ? 0.0 : term_q(tv, m, e->ti)[tid];
-        if (ref >= 0) sm->sgbits[tid] = orient_bit(term_A(tv, m, ref, sp.d), term_A(tv, m, e->ti, sp.d), tid, sp.d);
-      }
-      MCE_NOUNROLL for (int i = tid; i < nwP; i += c.nthreads()) bmP[i] = 0;
-    });
-    c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < pc; i += c.nthreads()) { const unsigned k = pk[i]; c.atomic_or(&bmP[k >> 5], 1u << (k & 31)); } });
-    bm_prefix(c, bmP, pfP, nwP, (int*)nullptr);
+  // Stage member `e` into slot `sl`: q and -- when `ref` >= 0 -- the per-row orientation bits between term `ref` and this
+  // member (ce:586-599).  Runs inside a phase (threads < m take part); the parent's rank structure is read from HBM/L1.
+  MCE_HD void stage_qs(Group2Sm* sm, const Group2Member* e, int sl, int ref, int tid) const {
+    if (tid < m) {
+      sm->q[sl][tid] = ((e->hflag >> tid) & 1u) ? 0.0 : term_q(tv, m, e->ti)[tid];
+      if (ref >= 0) sm->sgbits[sl][tid] = orient_bit(term_A(tv, m, ref, sp.d), term_A(tv, m, e->ti, sp.d), tid, sp.d);
+    }
   }
-  MCE_HD unsigned sigma_of(const Group2Sm* sm) const { unsigned s = 0; for (int i = 0; i < m; i++) s |= sm->sgbits[i]; return s; }
+  MCE_HD unsigned sigma_of(const Group2Sm* sm, int sl) const { unsigned s = 0; for (int i = 0; i < m; i++) s |= sm->sgbits[sl][i]; return s; }
 
   // G_p lookup through the rank structure (eval_gs.hpp:94-153 semantics: half storage, conjugate of the opposite cell, 0 when absent)
-  MCE_HD cplx lookup(const Group2Member* e, const cplx* pG, const unsigned* bmP, const unsigned short* pfP, int enc_l) const {
+  MCE_HD cplx lookup(const Group2Member* e, const cplx* pG, const unsigned* bmP, const unsigned short* pfP, int enc_l) const {   // bmP / pfP: the parent's rank structure
     const int phc = e->phc, top = 1 << (phc - 1), rev = (1 << phc) - 1;
     const bool cj = (enc_l & top) != 0;
     const int r = bitmap_rank(bmP, pfP, (unsigned)(cj ? (rev ^ enc_l) : enc_l));
@@ -329,12 +323,13 @@ struct KGTable2T {
   }
 
   // G of one cell of the staged member, flattening.hpp:129-247
-  MCE_HDN MCE_NOINLINE cplx eval_cell(Group2Sm* sm, const Group2Member* e, int* flag, const unsigned* bmP, const unsigned short* pfP, unsigned key) const {
+  MCE_HDN MCE_NOINLINE cplx eval_cell(const double* q, const Group2Member* e, int* flag, unsigned key) const {
     const int phc = e->phc;
+    const unsigned* bmP = prev.rbm + e->rk_off; const unsigned short* pfP = prev.rpf + e->rk_off;
     // ygi = sum over non-H-orthogonal rows of q_k s_k, in row order (flat:137-154).  sm->q holds +0.0 for the H-orthogonal
     // rows (adding +0.0 never changes a running sum that started at +0.0), so the loop is branch-free; s_k flips the sign bit.
     double ygi = 0;
-    MCE_NOUNROLL for (int k = 0; k < m; k++) ygi += flip_sign(sm->q[k], (key >> k) & 1u);
+    MCE_NOUNROLL for (int k = 0; k < m; k++) ygi += flip_sign(q[k], (key >> k) & 1u);
     int lp, lm;
     const int phc_mask = (1 << phc) - 1;
     if (!e->is_child) { lp = (int)(key & (unsigned)phc_mask); lm = lp; }
@@ -453,14 +448,14 @@ struct KGTable2T {
         parent_B_src(e->parent, &src, &nB, &mask);
         c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] = src[i] ^ mask; if (tid == 0) sm->owner = e->parent; });
       }
-      stage_member(c, sm, e, bmP, pfP, (k > 0 && e->is_child) ? lfr : -1, nothing);
+      { const int ref = (k > 0 && e->is_child) ? lfr : -1; c.par([&](int tid) { stage_qs(sm, e, 0, ref, tid); }); }
       unsigned sigma = 0;
       if (k > 0 && e->is_child) {        // new child: re-orient the group's table in place (flat:433-441)
-        sigma = sigma_of(sm);
+        sigma = sigma_of(sm, 0);
         if (sigma & top_m) sigma ^= rev_m;
       }
       c.par([&](int tid) {
-        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm, e, &sm->flag[kk], bmP, pfP, key); }
+        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm->q[0], e, &sm->flag[kk], key); }
         if (sigma && tid == 0 && sm->owner >= 0 && primary) c.atomic_xor(ws.bxor + sm->owner, sigma);   // the table is a parent's B memory, shared with its children
       });
       if (sm->flag[kk]) { accepted = 1; break; }
@@ -493,21 +488,33 @@ struct KGTable2T {
         MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) acc[i] = cadd(acc[i], pend_cj ? cconj(Gm[i]) : Gm[i]);
       }
     };
+    // One barrier per member: the phase that evaluates member k also adds member k-1's table (same thread, same cells) and
+    // stages q / orientation bits of member k+1 into the other slot.
+    bool staged = false;                 // member k's q / sgbits already sit in slot k & 1
     for (int k = k_from; k < k_to; ++k) {
-      if (k - w.cbase >= G2_CHUNK || k < w.cbase) { c.par([&](int tid) { do_pending(tid); }); pend = 0; w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); }
-      const int kk = k - w.cbase;
+      if (k - w.cbase >= G2_CHUNK || k < w.cbase) { c.par([&](int tid) { do_pending(tid); }); pend = 0; w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); staged = false; }
+      const int kk = k - w.cbase, sl = k & 1;
       const Group2Member* et = &sm->mem[kk];
-      stage_member(c, sm, et, bmP, pfP, rsel, do_pending);
-      pend = 0;
-      const unsigned sigma_raw = sigma_of(sm);
+      if (!staged) c.par([&](int tid) { stage_qs(sm, et, sl, rsel, tid); });
+      const bool next_here = (k + 1 < k_to) && (kk + 1 < G2_CHUNK);       // member k+1 is in the loaded chunk: stage it during this phase
+      const Group2Member* en = et + 1;
+      const unsigned sigma_raw = sigma_of(sm, sl);
       const bool cj = (sigma_raw & top_m) != 0;
       if (et->is_child || et->own_cells != nB) {
         // table = root's table re-oriented (update_btable, ce:584-625): cell i of the member is cell i of the root
         const unsigned sigma_n = cj ? (sigma_raw ^ rev_m) : sigma_raw;
+        const int pd = pend, pk = pend_k; const bool pcj = pend_cj;
+        cplx* prow = rows ? rows + (long long)pk * row_stride : nullptr;
         c.par([&](int tid) {
-          MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, Bk[i] ^ sigma_n);
+          MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) {
+            if (pd) { const cplx a = pcj ? cconj(Gm[i]) : Gm[i]; if (prow) prow[i] = a; else acc[i] = cadd(acc[i], a); }
+            Gm[i] = eval_cell(sm->q[sl], et, &sm->flag[kk], Bk[i] ^ sigma_n);
+          }
+          if (pd && prow && tid == 0) rflags[pk] = 1;
           if (!et->is_child && tid == 0) c.atomic_add(diag, 1);     // flat:516-539 also rewrites the parent's B memory: not modelled
+          if (next_here) stage_qs(sm, en, sl ^ 1, rsel, tid);
         });
+        pend = 0;
         if (sm->flag[kk]) { pend = 1; pend_cj = cj; pend_k = k; }
       } else {
         // old term with its own table: cell i of its B_mu is position i of its (sorted) source table; add by key (flat:291-314)
@@ -518,8 +525,13 @@ struct KGTable2T {
           c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) { const unsigned b = src[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
           bm_prefix(c, bmA, pfA, nwM, (int*)nullptr);
         }
-        const unsigned* bmT = sp.with_tp ? bmA : bmP; const unsigned short* pfT = sp.with_tp ? pfA : pfP;
-        c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) Gm[i] = eval_cell(sm, et, &sm->flag[kk], bmP, pfP, src[i] ^ mask); });
+        const unsigned* bmT = sp.with_tp ? bmA : prev.rbm + et->rk_off; const unsigned short* pfT = sp.with_tp ? pfA : prev.rpf + et->rk_off;
+        c.par([&](int tid) {
+          do_pending(tid);
+          MCE_NOUNROLL for (int i = tid; i < nT; i += c.nthreads()) Gm[i] = eval_cell(sm->q[sl], et, &sm->flag[kk], src[i] ^ mask);
+          if (next_here) stage_qs(sm, en, sl ^ 1, rsel, tid);
+        });
+        pend = 0;
         if (sm->flag[kk])
           c.par([&](int tid) {
             cplx* row = rows ? rows + (long long)k * row_stride : nullptr;
@@ -533,6 +545,7 @@ struct KGTable2T {
             if (row && tid == 0) rflags[k] = 1;
           });
       }
+      staged = next_here;
     }
     if (pend) { c.par([&](int tid) { do_pending(tid); }); pend = 0; }
   }

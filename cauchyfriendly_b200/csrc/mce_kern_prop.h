@@ -108,7 +108,8 @@ MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsign
 // y gets 2d doubles: (re_j, im_j) = (-sum_l p_l s_l a_lj, b_j).
 MCE_HD cplx eval_g_yei(const double* A, const double* p, const double* b, int m, int d, unsigned hflag, double c_val, double d_val,
                        const double* root_point, bool first_update, int phc, int z, unsigned enc_lhp,
-                       const unsigned* pkeys, const cplx* pG, int pcells, double* y) {
+                       const unsigned* pkeys, const cplx* pG, int pcells, double* y,
+                       const unsigned* rbm = nullptr, const unsigned short* rpf = nullptr) {
   double tmp[MAXD];
   for (int j = 0; j < d; j++) tmp[j] = 0;
   unsigned signs = 0;
@@ -125,8 +126,13 @@ MCE_HD cplx eval_g_yei(const double* A, const double* p, const double* b, int m,
   else {
     int lp, lm;
     parent_keys(signs, m, phc, z, true, nullptr, 0, &lp, &lm);   // the old term has z = m >= phc: no inserted bit
-    gp = g_lookup(lp ^ (int)enc_lhp, phc, pkeys, pG, pcells);
-    gm = g_lookup(lm ^ (int)enc_lhp, phc, pkeys, pG, pcells);
+    if (rbm) {                // rank structure of the parent's table: a bit test instead of a binary search
+      gp = g_lookup_rank(lp ^ (int)enc_lhp, phc, rbm, rpf, pG);
+      gm = g_lookup_rank(lm ^ (int)enc_lhp, phc, rbm, rpf, pG);
+    } else {
+      gp = g_lookup(lp ^ (int)enc_lhp, phc, pkeys, pG, pcells);
+      gm = g_lookup(lm ^ (int)enc_lhp, phc, pkeys, pG, pcells);
+    }
   }
   cplx g = csub(cdiv(gp, make_cplx(ygi + d_val, c_val)), cdiv(gm, make_cplx(ygi - d_val, c_val)));
   g = cscale(g, 1.0 / (2.0 * M_PI));
@@ -247,7 +253,9 @@ struct KMsmtUpdate {
       me.z = (unsigned char)t; me.flags = (s == 0) ? 0 : 1; me.hflag = hofs; me.enc_lhp = enc_lhp; me.c_val = zeta; me.d_val = rho[t];
       // --- moment contribution, cauchy_estimator.hpp:307-338 (summed by KMoments) ---
       const unsigned* pkeys = gen_keys(gen, gid, phc); const cplx* pG = gen_G(gen, gid, phc);
-      sl.g[slot] = eval_g_yei(cA, cp, cb, m, d, hofs, zeta, rho[t], sp.root_point, false, phc, t, enc_lhp, pkeys, pG, gen.cells[gid], yout);
+      const long long rko = sp.max_shape <= 16 ? gen_rk_off(gen, gid, phc) : 0;
+      sl.g[slot] = eval_g_yei(cA, cp, cb, m, d, hofs, zeta, rho[t], sp.root_point, false, phc, t, enc_lhp, pkeys, pG, gen.cells[gid], yout,
+                              sp.max_shape <= 16 ? gen.rbm + rko : nullptr, sp.max_shape <= 16 ? gen.rpf + rko : nullptr);
       if (s == 0) {
         unsigned e = sgn;                                   // parent B ^= enc_sgn_AH, half-normalised (term:229-250)
         if (e & (1u << (m - 1))) e ^= (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));

@@ -42,6 +42,25 @@ struct StepParams {
 // One generation of parent terms (the survivors of the previous step).  A parent is addressed by its
 // group id `gid` (groups of one shape are contiguous); `alive` lists the surviving gids in canonical
 // order (shape ascending, then root index) -- the order the NUM_CPUS=1 reference walks them.
+#if defined(__CUDA_ARCH__)
+#define MCE_POPC(x) __popc(x)
+#define MCE_FFS(x) (__ffs((int)(x)) - 1)
+#define MCE_NOINLINE __noinline__
+#define MCE_NOUNROLL _Pragma("unroll 1")
+#else
+#define MCE_NOUNROLL
+#define MCE_POPC(x) __builtin_popcount(x)
+#define MCE_FFS(x) (__builtin_ffs((int)(x)) - 1)
+#define MCE_NOINLINE
+#endif
+
+// rank of `key` among the set bits of bm (pf = exclusive prefix popcounts per word), or -1 when absent
+MCE_HD int bitmap_rank(const unsigned* bm, const unsigned short* pf, unsigned key) {
+  const unsigned w = bm[key >> 5], bit = 1u << (key & 31);
+  if (!(w & bit)) return -1;
+  return (int)pf[key >> 5] + MCE_POPC(w & (bit - 1u));
+}
+
 struct GenView {
   int n_groups, n_alive;
   int gid_begin[NSHAPE + 1];          // gids of shape m: [gid_begin[m], gid_begin[m+1])
@@ -53,8 +72,15 @@ struct GenView {
   double *A, *p, *b;
   unsigned* keys;
   cplx* G;
+  // rank structure of every table (KBuildRank): bitmap over the 2^m possible keys + exclusive prefix popcounts per word;
+  // the rank of a key is its position in the sorted table, so a lookup is two loads and a popcount (no binary search)
+  long long rk_base[NSHAPE];
+  unsigned* rbm;
+  unsigned short* rpf;
 };
 MCE_HD int gen_m(const GenView& g, int gid) { return g.g_m[gid]; }
+MCE_HD int rank_words(int m) { return m >= 5 ? (1 << (m - 5)) : 1; }
+MCE_HD long long gen_rk_off(const GenView& g, int gid, int m) { return g.rk_base[m] + (long long)(gid - g.gid_begin[m]) * rank_words(m); }
 MCE_HD double* gen_A(const GenView& g, int gid, int m, int d) { return g.A + g.A_base[m] + (long long)(gid - g.gid_begin[m]) * m * d; }
 MCE_HD double* gen_p(const GenView& g, int gid, int m) { return g.p + g.p_base[m] + (long long)(gid - g.gid_begin[m]) * m; }
 MCE_HD double* gen_b(const GenView& g, int gid, int d) { return g.b + (long long)gid * d; }
@@ -150,6 +176,14 @@ MCE_HD int key_search(const unsigned* keys, int n, unsigned target) {
 }
 
 // G_p lookup with half storage: the opposite cell's value is the complex conjugate (eval_gs.hpp:94-153).
+// same lookup through the table's rank structure (GenView::rbm / rpf)
+MCE_HD cplx g_lookup_rank(int enc_l, int phc, const unsigned* bm, const unsigned short* pf, const cplx* pG) {
+  const int top = 1 << (phc - 1), rev = (1 << phc) - 1;
+  const bool cj = (enc_l & top) != 0;
+  const int r = bitmap_rank(bm, pf, (unsigned)(cj ? (rev ^ enc_l) : enc_l));
+  if (r < 0) return make_cplx(0, 0);
+  return cj ? cconj(pG[r]) : pG[r];
+}
 MCE_HD cplx g_lookup(int enc_l, int phc, const unsigned* pkeys, const cplx* pG, int pcells) {
   const int two_to_phc_minus1 = 1 << (phc - 1), rev_phc_mask = (1 << phc) - 1;
   if (enc_l & two_to_phc_minus1) {
