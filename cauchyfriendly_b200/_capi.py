@@ -24,7 +24,7 @@ class MceStepStats(ct.Structure):
                                              "bytes_step_algorithmic", "kernel_launches")] + \
                [("ftr_rounds_max", ct.c_int), ("diag_unmodelled_alias", ct.c_int), ("diag_hash_overflow", ct.c_int),
                 ("ev_step_ms", ct.c_double), ("ev_gtable_ms", ct.c_double), ("gtable_launches", ct.c_longlong),
-                ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_mu_ms", ct.c_double)]
+                ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_ftr_ms", ct.c_double), ("ev_mu_ms", ct.c_double)]
 
 
 # every symbol include/mce_b200.h declares

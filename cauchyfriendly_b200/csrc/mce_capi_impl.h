@@ -109,7 +109,7 @@ int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
   out->parents = s.parents; out->slots = s.slots; out->terms_after_muc = s.terms_after_muc; out->groups = s.groups; out->survivors = s.survivors;
   out->bytes_gtable_algorithmic = s.bytes_gtable; out->bytes_step_algorithmic = s.bytes_step; out->kernel_launches = s.launches;
   out->ev_step_ms = s.ev_step_ms; out->ev_gtable_ms = s.ev_gtable_ms; out->gtable_launches = s.gtable_launches;
-  out->cells_parents = s.cells_parents; out->cells_survivors = s.cells_survivors; out->split_groups = s.big_groups; out->ev_moments_ms = s.ev_moments_ms; out->ev_mu_ms = s.ev_mu_ms;
+  out->cells_parents = s.cells_parents; out->cells_survivors = s.cells_survivors; out->split_groups = s.big_groups; out->ev_moments_ms = s.ev_moments_ms; out->ev_ftr_ms = s.ev_ftr_ms; out->ev_mu_ms = s.ev_mu_ms;
   out->ftr_rounds_max = s.ftr_rounds_max; out->diag_unmodelled_alias = s.diag_alias; out->diag_hash_overflow = s.diag_hash;
   return 0;
 }

@@ -31,7 +31,7 @@ struct StepStats {
   long long parents = 0, slots = 0, terms_after_muc = 0, groups = 0, survivors = 0;
   long long bytes_gtable = 0, bytes_step = 0, launches = 0;
   int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
-  double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0, ev_moments_ms = 0;   // CUDA-event durations on the stream
+  double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0, ev_moments_ms = 0, ev_ftr_ms = 0;   // CUDA-event durations on the stream
   long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0;
   int big_groups = 0;
 };
@@ -317,7 +317,7 @@ class Engine {
     const int n_alive = pg.v.n_alive;
     const int nq = 1 + d + d * d;
     stats.parents = n_alive;
-    int* diag = (int*)diagBuf.ensure(64); be.memset(diag, 0, 64);
+    int* diag = (int*)diagBuf.ensure(sizeof(int) * (16 + NSHAPE + 8)); be.memset(diag, 0, sizeof(int) * (16 + NSHAPE + 8));   // [16] diagnostics, then the survivor bounds per shape
     if (max_shape <= 16 && n_alive > 0) {        // rank structures of the parents' tables (lookups without binary search)
       int mmax = 1; for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) mmax = m;
       be.launch(KBuildRank{pg.v}, n_alive, 64, KBuildRank::smem_bytes(rank_words(mmax), 64));
@@ -452,6 +452,7 @@ class Engine {
     be.launch(KRegroup{sp, sl, tv, nchunks, counts, sot}, nchunks, RANK_CHUNK, KRegroup::smem_bytes());
     stats.ms_regroup = toc(tph); tph = tic();
 
+    be.ev_record(7);
     // ---- K5/K6: fast term reduction per new shape, reduction groups ----
     int* F_all = (int*)ftrF.ensure(sizeof(int) * (size_t)(nterms + 4));
     unsigned char* wide_all = (unsigned char*)ftrWide.ensure((size_t)nterms + 16);
@@ -465,12 +466,10 @@ class Engine {
     int* i1_all = (int*)scratchI1.ensure(sizeof(int) * (size_t)(nterms + 4));
     int* i2_all = (int*)scratchI2.ensure(sizeof(int) * (size_t)(nterms + 4));
     int* i3_all = (int*)scratchI3.ensure(sizeof(int) * (size_t)(nterms + 4));
-    const size_t unk_bytes = (sizeof(unsigned long long) + 3 * sizeof(int)) * NSHAPE;
+    const size_t unk_bytes = (sizeof(unsigned long long) + sizeof(int)) * NSHAPE;
     unsigned long long* dens_d = (unsigned long long*)unkBuf.ensure(unk_bytes + 64);    // [NSHAPE] window populations
     int* nu_d = (int*)(dens_d + NSHAPE);                                                // [NSHAPE] undecided terms of the round
-    int* cr_d = nu_d + NSHAPE;                                                          // [NSHAPE][2] roots, old-term roots
     std::vector<int> n_groups(NSHAPE, 0), n_phase1(NSHAPE, 0), gstart_off(NSHAPE, 0);
-    int goff = 0;
     if (capture) cap.clear();
     // split-group bookkeeping (KBigGroups): per (phase, shape) a region of group/part descriptors and a counter block
     std::vector<long long> big_slot_base(2 * NSHAPE, 0), big_part_base(2 * NSHAPE, 0);
@@ -482,9 +481,10 @@ class Engine {
       }
     BigGroup* bgroups = (BigGroup*)bigGroups.ensure(sizeof(BigGroup) * (size_t)big_slots);
     BigPart* bparts = (BigPart*)bigParts.ensure(sizeof(BigPart) * (size_t)big_parts);
-    const size_t bigcnt_bytes = (sizeof(unsigned long long) * 3 + sizeof(int) * 2) * 2 * NSHAPE;
-    unsigned long long* bcnt64 = (unsigned long long*)bigCnt.ensure(bigcnt_bytes);      // [2*NSHAPE][3], then int [2*NSHAPE][2]
+    const size_t bigcnt_bytes = (sizeof(unsigned long long) * 3 + sizeof(int) * 2) * 2 * NSHAPE + sizeof(int) * 2 * NSHAPE;
+    unsigned long long* bcnt64 = (unsigned long long*)bigCnt.ensure(bigcnt_bytes);      // [2*NSHAPE][3], then int [2*NSHAPE][2], then cr
     int* bcnt = (int*)(bcnt64 + 3 * 2 * NSHAPE);
+    int* cr_d = bcnt + 2 * 2 * NSHAPE;                                                  // [NSHAPE][2] roots, old-term roots (KCountRoots)
     be.memset(bcnt64, 0, bigcnt_bytes);
     std::vector<int> shapes;
     for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > 0) shapes.push_back(m);
@@ -495,77 +495,83 @@ class Engine {
       be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, i1_all + tb, n);      // k1 = sorted keys, i1 = term index at each sorted position
       be.launch(KFtrWide{tv, m, d, tr_order[0], k1_all + tb, wide_all + tb, dens_d + m}, nb, 128, 0);
     }
+    // small shapes always take the direct-scan round kernel: no need to read the window populations back
+    int max_n = 0;
+    for (int m : shapes) if (tv.n[m] > max_n) max_n = tv.n[m];
     std::vector<unsigned long long> dens(NSHAPE, 0);
-    if (!shapes.empty()) be.d2h(dens.data(), dens_d, sizeof(unsigned long long) * NSHAPE);
+    if (max_n >= 4096) be.d2h(dens.data(), dens_d, sizeof(unsigned long long) * NSHAPE);
     std::vector<int> active = shapes, nu(NSHAPE, 0);
     int rounds = 0;
     while (!active.empty()) {
-      be.memset(nu_d, 0, sizeof(int) * NSHAPE);
-      for (int m : active) {
-        const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
-        // mean epsilon-window population on the sorted axis decides the round kernel: dense clusters (many candidates per
-        // term) amortise the shared-memory staging of the tiled kernel, sparse data is faster with direct scans
-        const bool tiled = (double)dens[m] * 16.0 / (double)n > 24.0;
-        if (tiled) be.launch(KFtrRoundTiled{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
-        else be.launch(KFtrRound{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, nb, 128, 0);
+      // rounds that find nothing to do are cheap, host round trips are not: the first batch runs several rounds per readback
+      const int batch = rounds == 0 ? (nterms < 65536 ? 3 : 2) : 1;
+      for (int b = 0; b < batch; b++) {
+        be.memset(nu_d, 0, sizeof(int) * NSHAPE);
+        for (int m : active) {
+          const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+          // mean epsilon-window population on the sorted axis decides the round kernel: dense clusters (many candidates per
+          // term) amortise the shared-memory staging of the tiled kernel, sparse data is faster with direct scans
+          const bool tiled = (double)dens[m] * 16.0 / (double)n > 24.0;
+          if (tiled) be.launch(KFtrRoundTiled{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, (n + FTR_TB - 1) / FTR_TB, FTR_TB, KFtrRoundTiled::smem_bytes(m, d));
+          else be.launch(KFtrRound{tv, sp, m, k1_all + tb, i1_all + tb, wide_all + tb, F_all + tb, nu_d + m}, nb, 128, 0);
+        }
+        rounds++;
       }
       be.d2h(nu.data(), nu_d, sizeof(int) * NSHAPE);
-      rounds++;
       std::vector<int> still;
       for (int m : active) if (nu[m] != 0) still.push_back(m);
       active.swap(still);
-      if (rounds > (int)nterms + 2) { error = "FTR resolution did not converge"; return -3; }
+      if (rounds > (int)nterms + 4) { error = "FTR resolution did not converge"; return -3; }
     }
     stats.ftr_rounds_max = rounds;
+    if (capture) for (int m : shapes) capture_shape(tv, m, F_all + tv.t_begin[m], ws, with_tp);
     for (int m : shapes) {
       const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
+      int* gstart = gstart_all + tb + m;                       // at most n + 1 entries per shape
+      gstart_off[m] = (int)(tb + m);
       be.launch(KRootKeys{n, F_all + tb, k0_all + tb, i0_all + tb}, nb, 128, 0);
       be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, order_all + tb, n);
       be.launch(KGroupHeads{n, F_all + tb, order_all + tb, i2_all + tb}, nb, 128, 0);
       be.exclusive_scan(i2_all + tb, i3_all + tb, n);
       be.launch(KCountRoots{n, tv.n_old[m], F_all + tb, cr_d + 2 * m}, nb, 128, 2 * sizeof(int));
-    }
-    std::vector<int> cr(2 * NSHAPE, 0);
-    if (!shapes.empty()) be.d2h(cr.data(), cr_d, sizeof(int) * 2 * NSHAPE);
-    for (int m : shapes) {
-      const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
-      const int ng_m = cr[2 * m];
-      n_groups[m] = ng_m;
-      n_phase1[m] = cr[2 * m + 1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
-      int* gstart = gstart_all + goff;
-      gstart_off[m] = goff;
-      be.launch(KGroupFill{n, i2_all + tb, i3_all + tb, gstart, ng_m}, nb, 128, 0);
+      be.launch(KGroupFill{n, i2_all + tb, i3_all + tb, gstart, cr_d + 2 * m}, nb, 128, 0);
       if (max_shape <= 16 && n > big_T) {
         const int Hm = cell_count_central_half(m, d);
         for (int ph = 0; ph < 2; ph++) {
-          const int ga = ph == 0 ? 0 : n_phase1[m], gb = ph == 0 ? n_phase1[m] : ng_m, ix = ph * NSHAPE + m;
-          if (gb > ga)
-            be.launch(KBigGroups{gstart, ga, gb, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix}, (gb - ga + 127) / 128, 128, 0);
+          const int ix = ph * NSHAPE + m;
+          be.launch(KBigGroups{gstart, cr_d + 2 * m, ph, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix}, nb, 128, 0);
         }
       }
-      goff += ng_m + 1;
-      if (capture) capture_shape(tv, m, F_all + tb, ws, with_tp);
     }
+    be.ev_record(8);
     stats.ms_ftr = toc(tph); tph = tic();
 
     // ---- K7/K8: child B-tables and G-tables, one CTA per reduction group ----
     finish_moments();            // G_SCALE_FACTOR = 1 / (2 pi Re fz) scales every new G (flat:227)
     stats.ms_moments += toc(tph); tph = tic();
+    // one D2H brings the root counts of every shape (KCountRoots) and the split-group counters (KBigGroups)
+    std::vector<unsigned long long> h64(3 * 2 * NSHAPE, 0); std::vector<int> h32(2 * 2 * NSHAPE, 0), cr(2 * NSHAPE, 0);
+    {
+      std::vector<unsigned char> hb(bigcnt_bytes);
+      be.d2h(hb.data(), bcnt64, bigcnt_bytes);
+      memcpy(h64.data(), hb.data(), sizeof(unsigned long long) * h64.size());
+      memcpy(h32.data(), hb.data() + sizeof(unsigned long long) * h64.size(), sizeof(int) * h32.size());
+      memcpy(cr.data(), hb.data() + sizeof(unsigned long long) * h64.size() + sizeof(int) * h32.size(), sizeof(int) * cr.size());
+    }
+    for (int m : shapes) {
+      n_groups[m] = cr[2 * m];
+      n_phase1[m] = cr[2 * m + 1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
+    }
     fill_gen_layout(ng, n_groups);
     unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
     const size_t gsm = KGTable::smem_bytes(HC2);
     long long total_groups = 0;
-    // split groups: sizes of the addend scratch (one D2H of the KBigGroups counters), scratch bases per (phase, shape)
-    std::vector<unsigned long long> h64(3 * 2 * NSHAPE, 0); std::vector<int> h32(2 * 2 * NSHAPE, 0);
+    // split groups: sizes of the addend scratch, scratch bases per (phase, shape)
     std::vector<long long> rows_base(2 * NSHAPE, 0), flags_base(2 * NSHAPE, 0), keys_base(2 * NSHAPE, 0);
     bool split = false;
     cplx* brows = nullptr; int* bflags = nullptr; unsigned* bkeys = nullptr;
     if (max_shape <= 16) {
-      std::vector<unsigned char> hb(bigcnt_bytes);
-      be.d2h(hb.data(), bcnt64, bigcnt_bytes);
-      memcpy(h64.data(), hb.data(), sizeof(unsigned long long) * h64.size());
-      memcpy(h32.data(), hb.data() + sizeof(unsigned long long) * h64.size(), sizeof(int) * h32.size());
       long long tr = 0, tf = 0, tk = 0, nbig = 0;
       for (int ix = 0; ix < 2 * NSHAPE; ix++) {
         rows_base[ix] = tr; flags_base[ix] = tf; keys_base[ix] = tk;
@@ -614,7 +620,7 @@ class Engine {
         stats.gtable_launches++;
       }
     be.ev_record(3);
-    stats.ev_gtable_ms = be.ev_elapsed(2, 3);
+    stats.ev_gtable_ms = be.ev_elapsed(2, 3); stats.ev_ftr_ms = be.ev_elapsed(7, 8);
     stats.groups = total_groups;
     stats.ms_gtable = toc(tph); tph = tic();
 
@@ -628,15 +634,16 @@ class Engine {
       be.launch(KFlagsToInt{ngr, aflag, fi}, (ngr + 127) / 128, 128, 0);
       be.exclusive_scan(fi, fr, ngr);
       be.launch(KAliveCompact{ngr, aflag, fr, ng.v.alive}, (ngr + 127) / 128, 128, 0);
-      std::vector<int> bounds(NSHAPE + 1, 0);
-      int* dbounds = (int*)unkBuf.ensure(sizeof(int) * (NSHAPE + 8));
-      be.launch(KShapeBounds{ng.v, ngr, fi, fr, dbounds}, 1, 64, 0);
-      be.d2h(bounds.data(), dbounds, sizeof(int) * (NSHAPE + 1));
+      be.launch(KShapeBounds{ng.v, ngr, fi, fr, diag + 16}, 1, 64, 0);
+    }
+    std::vector<int> hd(16 + NSHAPE + 1, 0);
+    be.d2h(hd.data(), diag, sizeof(int) * hd.size());          // diagnostics + survivor bounds in one read
+    if (ngr > 0) {
+      const int* bounds = hd.data() + 16;
       for (int m = 1; m < NSHAPE; m++) ng.alive_per_shape[m] = bounds[m + 1] - bounds[m];
       n_surv = bounds[NSHAPE];
     }
     ng.v.n_alive = n_surv;
-    int hd[16]; be.d2h(hd, diag, sizeof(int) * 4);
     stats.diag_alias = hd[0]; stats.diag_hash = hd[1];
     stats.cells_parents = pg.sum_cells; ng.sum_cells = (long long)(unsigned)hd[2] | ((long long)hd[3] << 32); stats.cells_survivors = ng.sum_cells;
     stats.survivors = n_surv;
@@ -744,6 +751,7 @@ class Engine {
     master_step = 0; Nt = 1; numeric_moment_errors = 0; finished = false; skip_post_mu = 0;
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = 1;
     gen[0].v.n_alive = 0; gen[1].v.n_alive = 0;
+    cur = 0;          // same buffer parity on every pass of a window: the grow-only buffers settle after the first pass
   }
 
   // Host copy of the parents of shape m (canonical order).

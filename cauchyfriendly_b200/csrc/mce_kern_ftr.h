@@ -219,13 +219,13 @@ struct KGroupHeads {
   }
 };
 struct KGroupFill {     // head_rank = exclusive scan of is_head; grp_start[rank] = position of the head in order[]
-  int n; const int* is_head; const int* head_rank; int* grp_start; int n_groups;
+  int n; const int* is_head; const int* head_rank; int* grp_start; const int* n_groups /* device: KCountRoots */;
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
       const int k = c.block() * c.nthreads() + tid;
       if (k >= n) return;
       if (is_head[k]) grp_start[head_rank[k]] = k;
-      if (k == 0) grp_start[n_groups] = n;
+      if (k == 0) grp_start[n_groups[0]] = n;
     });
   }
 };

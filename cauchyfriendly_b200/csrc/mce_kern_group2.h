@@ -650,9 +650,11 @@ using KGTable2 = KGTable2T<G2_NORMAL>;
 
 // Lists the reduction groups of [ga, gb) with more than T members and cuts them into parts of BIG_PART members.
 struct KBigGroups {
-  const int* grp_start; int ga, gb, T, Hm; BigGroup* groups; BigPart* parts; int* cnt /*[2]: groups, parts*/; unsigned long long* cnt64 /*[3]: rows, flags, keys*/;
+  const int* grp_start; const int* roots /* device: [0] groups, [1] groups rooted at an old term */; int phase, T, Hm;
+  BigGroup* groups; BigPart* parts; int* cnt /*[2]: groups, parts*/; unsigned long long* cnt64 /*[3]: rows, flags, keys*/;
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
+      const int ga = phase == 0 ? 0 : roots[1], gb = phase == 0 ? roots[1] : roots[0];
       const int gi = ga + c.block() * c.nthreads() + tid;
       if (gi >= gb) return;
       const int size = grp_start[gi + 1] - grp_start[gi];

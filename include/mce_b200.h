@@ -110,6 +110,7 @@ typedef struct mce_step_stats {
   long long cells_parents, cells_survivors;   /* actual table cells read / written by the group kernel          */
   long long split_groups;               /* reduction groups large enough to be split over several CTAs          */
   double ev_moments_ms;                 /* CUDA-event time of the moment sums on the side stream                  */
+  double ev_ftr_ms;                     /* CUDA-event time of the term reduction (sorts, rounds, group lists)      */
   double ev_mu_ms;                      /* CUDA-event time from the start of the step to the end of the measurement update */
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
