@@ -383,7 +383,10 @@ class Engine {
     }
     for (int m = 1; m < NSHAPE; m++) {
       const long long n = (long long)pg.alive_per_shape[m] * (sl.MT[m] + 1);
-      if (n > 0) be.launch(KMsmtUpdate{sp, pg.v, ws, sl, m}, (int)((n + 127) / 128), 128, 0);
+      if (n > 0) {
+        const int npar = pg.alive_per_shape[m];
+        be.launch(KMsmtUpdate2{sp, pg.v, ws, sl, m}, (npar + MU_PB - 1) / MU_PB, 128, KMsmtUpdate2::smem_bytes(sl.MT[m], d));
+      }
     }
     stats.ms_mu = toc(tph); tph = tic();
 
@@ -486,21 +489,28 @@ class Engine {
     int* bcnt = (int*)(bcnt64 + 3 * 2 * NSHAPE);
     int* cr_d = bcnt + 2 * 2 * NSHAPE;                                                  // [NSHAPE][2] roots, old-term roots (KCountRoots)
     be.memset(bcnt64, 0, bigcnt_bytes);
-    std::vector<int> shapes;
-    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > 0) shapes.push_back(m);
+    std::vector<int> shapes, reg_shapes;          // shapes present this step; those too large for the single-CTA kernel
+    KFtrSmall ks; memset(&ks, 0, sizeof(ks));
+    int n_small = 0;
+    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > 0) {
+      shapes.push_back(m);
+      if (tv.n[m] <= FTR_SMALL_N) ks.shapes[n_small++] = m; else reg_shapes.push_back(m);
+    }
     be.memset(dens_d, 0, unk_bytes);
-    for (int m : shapes) {
+    if (n_small > 0) {       // small shapes: the whole reduction in one launch, no host round trip
+      ks.tv = tv; ks.sp = sp; ks.k1_all = k1_all; ks.i1_all = i1_all; ks.wide_all = wide_all; ks.F_all = F_all; ks.order_all = order_all;
+      ks.gstart_all = gstart_all; ks.cr = cr_d;
+      be.launch(ks, n_small, 512, KFtrSmall::smem_bytes());
+    }
+    for (int m : reg_shapes) {
       const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
       be.launch(KFtrKeys{tv, m, d, tr_order[0], k0_all + tb, i0_all + tb, F_all + tb}, nb, 128, 0);
       be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, i1_all + tb, n);      // k1 = sorted keys, i1 = term index at each sorted position
       be.launch(KFtrWide{tv, m, d, tr_order[0], k1_all + tb, wide_all + tb, dens_d + m}, nb, 128, 0);
     }
-    // small shapes always take the direct-scan round kernel: no need to read the window populations back
-    int max_n = 0;
-    for (int m : shapes) if (tv.n[m] > max_n) max_n = tv.n[m];
     std::vector<unsigned long long> dens(NSHAPE, 0);
-    if (max_n >= 4096) be.d2h(dens.data(), dens_d, sizeof(unsigned long long) * NSHAPE);
-    std::vector<int> active = shapes, nu(NSHAPE, 0);
+    if (!reg_shapes.empty()) be.d2h(dens.data(), dens_d, sizeof(unsigned long long) * NSHAPE);
+    std::vector<int> active = reg_shapes, nu(NSHAPE, 0);
     int rounds = 0;
     while (!active.empty()) {
       // rounds that find nothing to do are cheap, host round trips are not: the first batch runs several rounds per readback
@@ -529,12 +539,14 @@ class Engine {
       const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
       int* gstart = gstart_all + tb + m;                       // at most n + 1 entries per shape
       gstart_off[m] = (int)(tb + m);
-      be.launch(KRootKeys{n, F_all + tb, k0_all + tb, i0_all + tb}, nb, 128, 0);
-      be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, order_all + tb, n);
-      be.launch(KGroupHeads{n, F_all + tb, order_all + tb, i2_all + tb}, nb, 128, 0);
-      be.exclusive_scan(i2_all + tb, i3_all + tb, n);
-      be.launch(KCountRoots{n, tv.n_old[m], F_all + tb, cr_d + 2 * m}, nb, 128, 2 * sizeof(int));
-      be.launch(KGroupFill{n, i2_all + tb, i3_all + tb, gstart, cr_d + 2 * m}, nb, 128, 0);
+      if (n > FTR_SMALL_N) {
+        be.launch(KRootKeys{n, F_all + tb, k0_all + tb, i0_all + tb}, nb, 128, 0);
+        be.sort_pairs(k0_all + tb, k1_all + tb, i0_all + tb, order_all + tb, n);
+        be.launch(KGroupHeads{n, F_all + tb, order_all + tb, i2_all + tb}, nb, 128, 0);
+        be.exclusive_scan(i2_all + tb, i3_all + tb, n);
+        be.launch(KCountRoots{n, tv.n_old[m], F_all + tb, cr_d + 2 * m}, nb, 128, 2 * sizeof(int));
+        be.launch(KGroupFill{n, i2_all + tb, i3_all + tb, gstart, cr_d + 2 * m}, nb, 128, 0);
+      }
       if (max_shape <= 16 && n > big_T) {
         const int Hm = cell_count_central_half(m, d);
         for (int ph = 0; ph < 2; ph++) {

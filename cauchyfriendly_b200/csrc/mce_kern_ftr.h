@@ -55,62 +55,75 @@ struct KFtrKeys {
 };
 
 // wide[i]: the root's own axis-0 window holds at least two points (the `(gti - lti) > 2` gate, tr:121)
+// window bounds of term i on the sorted axis: wide flag + (sampled) window population
+MCE_HD int ftr_wide_term(const TermView& tv, int m, int d, int axis0, const unsigned long long* skeys, int i, int* win) {
+  const int n = tv.n[m];
+  const double qp = term_b(tv, m, i, d)[axis0];
+  const unsigned long long klo = f64_sort_key(qp - REDUCTION_EPS), khi = f64_sort_key(qp + REDUCTION_EPS);
+  // lti = last index with value <= lo ; gti = first index with value > hi   (tr:89-106)
+  int lo = 0, hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= klo) lo = mid + 1; else hi = mid; }
+  const int lti = lo - 1;
+  lo = 0; hi = n;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= khi) lo = mid + 1; else hi = mid; }
+  const int gti = lo;
+  *win = gti - lti - 1;
+  return (gti - lti) > 2;
+}
 struct KFtrWide {
   TermView tv; int m, d, axis0; const unsigned long long* skeys; unsigned char* wide; unsigned long long* density /* sum of window sizes */;
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
       const int i = c.block() * c.nthreads() + tid;
-      const int n = tv.n[m];
-      if (i >= n) return;
-      const double qp = term_b(tv, m, i, d)[axis0];
-      const unsigned long long klo = f64_sort_key(qp - REDUCTION_EPS), khi = f64_sort_key(qp + REDUCTION_EPS);
-      // lti = last index with value <= lo ; gti = first index with value > hi   (tr:89-106)
-      int lo = 0, hi = n;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= klo) lo = mid + 1; else hi = mid; }
-      const int lti = lo - 1;
-      lo = 0; hi = n;
-      while (lo < hi) { int mid = (lo + hi) >> 1; if (skeys[mid] <= khi) lo = mid + 1; else hi = mid; }
-      const int gti = lo;
-      wide[i] = (gti - lti) > 2;
-      if ((i & 15) == 0) c.atomic_add_u64(density, (unsigned long long)(gti - lti - 1));   // 1/16 sample of the window sizes
+      if (i >= tv.n[m]) return;
+      int win;
+      wide[i] = (unsigned char)ftr_wide_term(tv, m, d, axis0, skeys, i, &win);
+      if ((i & 15) == 0) c.atomic_add_u64(density, (unsigned long long)win);   // 1/16 sample of the window sizes
     });
   }
 };
 
 // One resolution round; `n_unknown` counts terms still undecided after the round.
+// One term (sorted position `pos`) of one resolution round: returns 1 when the term stays undecided.
+template <class Ctx>
+MCE_KERNEL_FN int ftr_round_pos(Ctx& c, const TermView& tv, const StepParams& sp, int m, const unsigned long long* skeys, const int* sidx,
+                                const unsigned char* wide, int* F, int pos) {
+  const int n = tv.n[m], d = sp.d;
+  const int j = sidx[pos];
+  if (c.load_relaxed(F + j) != -1) return 0;
+  const double* bj = term_b(tv, m, j, d); const double* pj = term_p(tv, m, j); const double* Aj = term_A(tv, m, j, d);
+  const int ax0 = sp.tr_order[0];
+  // conservative scan bounds around b_j on the primary axis; ftr_match applies the exact interval test
+  const double slack = 4.0 * REDUCTION_EPS + 8.0 * fabs(bj[ax0]) * 2.3e-16;
+  const unsigned long long klo = f64_sort_key(bj[ax0] - slack), khi = f64_sort_key(bj[ax0] + slack);
+  // Ascending scan of the window.  Only the lowest-index matching candidate matters (a root there decides j, an undecided
+  // term there postpones j), so candidates at or above the best index so far are skipped without touching their data;
+  // the sort is stable, hence a cluster of coincident terms is visited in index order and costs one match per term.
+  int min_root = 0x7fffffff, min_unknown = 0x7fffffff;
+  int qs = pos;
+  while (qs > 0 && skeys[qs - 1] >= klo) qs--;
+  for (int q = qs; q < n; q++) {
+    if (q == pos) continue;
+    if (skeys[q] > khi) break;
+    const int i = sidx[q];
+    if (i < j && i < min_root && i < min_unknown && wide[i]) {
+      const int Fi = c.load_relaxed(F + i);
+      if ((Fi == i || Fi == -1) && ftr_match(term_b(tv, m, i, d), bj, term_p(tv, m, i), pj, term_A(tv, m, i, d), Aj, m, d, sp.tr_order)) {
+        if (Fi == i) min_root = i; else min_unknown = i;
+      }
+    }
+  }
+  if (min_unknown < min_root) return 1;   // an undecided lower term could still claim j
+  F[j] = (min_root != 0x7fffffff) ? min_root : j;
+  return 0;
+}
 struct KFtrRound {
   TermView tv; StepParams sp; int m; const unsigned long long* skeys; const int* sidx; const unsigned char* wide; int* F; int* n_unknown;
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
       const int pos = c.block() * c.nthreads() + tid;
-      const int n = tv.n[m], d = sp.d;
-      if (pos >= n) return;
-      const int j = sidx[pos];
-      if (c.load_relaxed(F + j) != -1) return;
-      const double* bj = term_b(tv, m, j, d); const double* pj = term_p(tv, m, j); const double* Aj = term_A(tv, m, j, d);
-      const int ax0 = sp.tr_order[0];
-      // conservative scan bounds around b_j on the primary axis; ftr_match applies the exact interval test
-      const double slack = 4.0 * REDUCTION_EPS + 8.0 * fabs(bj[ax0]) * 2.3e-16;
-      const unsigned long long klo = f64_sort_key(bj[ax0] - slack), khi = f64_sort_key(bj[ax0] + slack);
-      // Ascending scan of the window.  Only the lowest-index matching candidate matters (a root there decides j, an undecided
-      // term there postpones j), so candidates at or above the best index so far are skipped without touching their data;
-      // the sort is stable, hence a cluster of coincident terms is visited in index order and costs one match per term.
-      int min_root = 0x7fffffff, min_unknown = 0x7fffffff;
-      int qs = pos;
-      while (qs > 0 && skeys[qs - 1] >= klo) qs--;
-      for (int q = qs; q < n; q++) {
-        if (q == pos) continue;
-        if (skeys[q] > khi) break;
-        const int i = sidx[q];
-        if (i < j && i < min_root && i < min_unknown && wide[i]) {
-          const int Fi = c.load_relaxed(F + i);
-          if ((Fi == i || Fi == -1) && ftr_match(term_b(tv, m, i, d), bj, term_p(tv, m, i), pj, term_A(tv, m, i, d), Aj, m, d, sp.tr_order)) {
-            if (Fi == i) min_root = i; else min_unknown = i;
-          }
-        }
-      }
-      if (min_unknown < min_root) { c.atomic_add(n_unknown, 1); return; }   // an undecided lower term could still claim j
-      F[j] = (min_root != 0x7fffffff) ? min_root : j;
+      if (pos >= tv.n[m]) return;
+      if (ftr_round_pos(c, tv, sp, m, skeys, sidx, wide, F, pos)) c.atomic_add(n_unknown, 1);
     });
   }
 };
@@ -259,6 +272,97 @@ struct KRootKeys {      // sort key for grouping: (root index << 32) | term inde
       if (j >= n) return;
       keys[j] = ((unsigned long long)(unsigned)F[j] << 32) | (unsigned)j;
       vals[j] = j;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Whole term reduction of one SMALL shape (n <= FTR_SMALL_N) in one CTA: sort of the primary axis, window flags, resolution
+// rounds until the fixed point, grouping sort, group heads / starts and root counts.  Replaces ~25 launches and every host
+// round trip of the general path for the early steps of a window, which are launch-latency bound.  Same results: the sorts
+// order by (key, index), which is what the stable radix sort of the general path produces.
+// ---------------------------------------------------------------------------------------------
+constexpr int FTR_SMALL_N = 4096;
+struct KFtrSmall {
+  TermView tv; StepParams sp; int shapes[NSHAPE];        // block b handles shape shapes[b]
+  unsigned long long* k1_all; int* i1_all; unsigned char* wide_all; int* F_all; int* order_all; int* gstart_all; int* cr /*[NSHAPE][2]*/;
+  static MCE_HD size_t smem_bytes() { return (sizeof(unsigned long long) + sizeof(int)) * FTR_SMALL_N + 64; }
+  template <class Ctx> MCE_KERNEL_FN void sort_pairs(Ctx& c, unsigned long long* key, int* val, int n2) const {   // bitonic, ascending by (key, val)
+    for (int k = 2; k <= n2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1)
+        c.par([&](int tid) {
+          for (int i = tid; i < n2; i += c.nthreads()) {
+            const int ixj = i ^ j;
+            if (ixj > i) {
+              const unsigned long long ka = key[i], kb = key[ixj]; const int va = val[i], vb = val[ixj];
+              const bool gt = ka > kb || (ka == kb && va > vb);
+              const bool up = (i & k) == 0;
+              if (up ? gt : !gt) { key[i] = kb; key[ixj] = ka; val[i] = vb; val[ixj] = va; }
+            }
+          }
+        });
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int m = shapes[c.block()], n = tv.n[m], d = sp.d;
+    const long long tb = tv.t_begin[m];
+    unsigned long long* skeys = k1_all + tb; int* sidx = i1_all + tb; unsigned char* wide = wide_all + tb;
+    int* F = F_all + tb; int* order = order_all + tb; int* gstart = gstart_all + tb + m;
+    unsigned long long* key = (unsigned long long*)c.smem();
+    int* val = (int*)(key + FTR_SMALL_N);
+    int* ctl = val + FTR_SMALL_N;                            // [0] undecided terms of the round, [1] roots, [2] old-term roots
+    int n2 = 1; while (n2 < n) n2 <<= 1;
+    // ---- primary-axis sort ----
+    c.par([&](int tid) {
+      for (int i = tid; i < n2; i += c.nthreads()) {
+        if (i < n) { key[i] = f64_sort_key(term_b(tv, m, i, d)[sp.tr_order[0]]); val[i] = i; F[i] = -1; }
+        else { key[i] = ~0ull; val[i] = 0x7fffffff; }
+      }
+    });
+    sort_pairs(c, key, val, n2);
+    c.par([&](int tid) { for (int i = tid; i < n; i += c.nthreads()) { skeys[i] = key[i]; sidx[i] = val[i]; } });
+    c.par([&](int tid) { for (int i = tid; i < n; i += c.nthreads()) { int win; wide[i] = (unsigned char)ftr_wide_term(tv, m, d, sp.tr_order[0], key, i, &win); } });
+    // ---- resolution rounds ----
+    for (int round = 0; round <= n + 1; round++) {
+      c.par([&](int tid) { if (tid == 0) ctl[0] = 0; });
+      c.par([&](int tid) {
+        int unk = 0;
+        for (int pos = tid; pos < n; pos += c.nthreads()) unk += ftr_round_pos(c, tv, sp, m, key, val, wide, F, pos);
+        if (unk) c.atomic_add(&ctl[0], unk);
+      });
+      if (c.uniform(ctl[0]) == 0) break;
+    }
+    // ---- groups: terms sorted by (root, index); heads, starts, root counts ----
+    c.par([&](int tid) {
+      for (int i = tid; i < n2; i += c.nthreads()) {
+        if (i < n) { key[i] = ((unsigned long long)(unsigned)F[i] << 32) | (unsigned)i; val[i] = i; }
+        else { key[i] = ~0ull; val[i] = 0x7fffffff; }
+      }
+      if (tid == 0) { ctl[1] = 0; ctl[2] = 0; }
+    });
+    sort_pairs(c, key, val, n2);
+    int* is_head = (int*)key;                                // the keys are dead once order[] is written: reuse as int scratch
+    int* head_rank = is_head + FTR_SMALL_N;
+    c.par([&](int tid) { for (int i = tid; i < n; i += c.nthreads()) order[i] = val[i]; });
+    c.par([&](int tid) { for (int i = tid; i < n; i += c.nthreads()) { const int t = val[i]; is_head[i] = (F[t] == t) ? 1 : 0; } });
+    const int chunk = (n + c.nthreads() - 1) / c.nthreads();
+    c.par([&](int tid) {                                     // exclusive scan, chunk per thread (totals go to val[], dead by now)
+      const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+      int acc = 0, old = 0;
+      for (int i = lo; i < hi; i++) { head_rank[i] = acc; acc += is_head[i]; if (is_head[i] && order[i] < tv.n_old[m]) old++; }
+      val[tid] = acc;
+      if (old) c.atomic_add(&ctl[2], old);
+    });
+    c.par([&](int tid) {
+      if (tid != 0) return;
+      int acc = 0;
+      for (int t = 0; t < c.nthreads(); t++) { const int v = val[t]; val[t] = acc; acc += v; }
+      ctl[1] = acc;
+    });
+    c.par([&](int tid) {
+      const int lo = tid * chunk, hi = lo + chunk < n ? lo + chunk : n;
+      const int base = val[tid];
+      for (int i = lo; i < hi; i++) if (is_head[i]) gstart[head_rank[i] + base] = i;
+      if (tid == 0) { gstart[ctl[1]] = n; cr[2 * m] = ctl[1]; cr[2 * m + 1] = ctl[2]; }
     });
   }
 };

@@ -43,8 +43,9 @@ MCE_HD void coalign_gates(const double* r, const double* c, int d, bool* pos, bo
 }
 
 // mu_coalign, cauchy_term.hpp:533-745.  Rows are compacted in place; returns the new shape.
-MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsigned* hflag_io, unsigned char* cmap, unsigned* csneg_out) {
-  normalize_rows(A, p, q, m, d, true);
+// `gate(j, k, &pos, &neg)` answers whether the L1-normalised rows j < k are parallel / anti-parallel.
+template <class Gate>
+MCE_HD int mu_coalign_core(double* A, double* p, double* q, int m, int d, unsigned* hflag_io, unsigned char* cmap, unsigned* csneg_out, Gate gate) {
   unsigned F = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);   // bit set: row still unique
   unsigned hf = *hflag_io, csneg = 0;
   const bool any_h = hf != 0;
@@ -56,7 +57,7 @@ MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsign
     for (int k = j + 1; k < m; k++) {
       if (!((F >> k) & 1u)) continue;
       bool pos, neg;
-      coalign_gates(A + j * d, A + k * d, d, &pos, &neg);
+      gate(j, k, &pos, &neg);
       if (pos) {
         if (any_h) {
           const bool hj = (hf >> j) & 1u, hk = (hf >> k) & 1u;
@@ -102,6 +103,11 @@ MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsign
   }
   *hflag_io = hf; *csneg_out = csneg;
   return new_shape;
+}
+
+MCE_HD int mu_coalign_rows(double* A, double* p, double* q, int m, int d, unsigned* hflag_io, unsigned char* cmap, unsigned* csneg_out) {
+  normalize_rows(A, p, q, m, d, true);
+  return mu_coalign_core(A, p, q, m, d, hflag_io, cmap, csneg_out, [&](int j, int k, bool* pos, bool* neg) { coalign_gates(A + j * d, A + k * d, d, pos, neg); });
 }
 
 // eval_g_yei, cauchy_term.hpp:312-401, for a term that has not been L1-normalised yet.
@@ -277,6 +283,200 @@ struct KMsmtUpdate {
       for (int i = 0; i < newm; i++) { po[i] = cp[i]; qo[i] = cq[i]; }
       for (int i = 0; i < d; i++) bo[i] = cb[i];
       sl.meta[slot] = me;
+    });
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K3+K4, cooperative version: a CTA takes MU_PB parents at a time and keeps their mu rows and all their children in shared
+// memory; the work is spread as (parent, row), (parent, child, row) and (parent, child) items, so no thread holds a
+// hyperplane array of its own (KMsmtUpdate keeps ~5 KB per thread in local memory, which turns into HBM traffic).
+// Arithmetic and its order are those of KMsmtUpdate / the reference, item by item.
+// ---------------------------------------------------------------------------------------------
+constexpr int MU_PB = 4;
+struct KMsmtUpdate2 {
+  StepParams sp; GenView gen; ParentWs ws; SlotView sl; int ms;
+  struct Par { int r, gid, phc, m, pad; unsigned F_int, sgn; double zeta; const double *Ap, *pp, *bp; };
+  struct Slot { int valid, t, newm; unsigned hofs, csneg, flags2; };
+  static MCE_HD size_t per_parent_doubles(int MT, int d) { return (size_t)(MT + 1) * d + (MT + 1) + (size_t)(MT + 1) * ((size_t)MT * d + 2 * MT + d); }
+  static MCE_HD size_t smem_bytes(int MT, int d) {
+    return MU_PB * (sizeof(double) * per_parent_doubles(MT, d) + sizeof(Par) + (MT + 1) * (sizeof(Slot) + 2 * MT * sizeof(unsigned))) + 64;
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int MT = sl.MT[ms], spp = MT + 1, d = sp.d, NT = c.nthreads();
+    const int npar = sl.par_begin[ms + 1] - sl.par_begin[ms];
+    const int pb0 = c.block() * MU_PB, npb = (npar - pb0) < MU_PB ? (npar - pb0) : MU_PB;
+    // shared-memory carve-up (per parent pb)
+    const size_t ppd = per_parent_doubles(MT, d);
+    double* dbase = (double*)c.smem();
+    Par* par = (Par*)(dbase + MU_PB * ppd);
+    Slot* slot = (Slot*)(par + MU_PB);
+    unsigned* gates = (unsigned*)(slot + MU_PB * spp);             // [pb][s][2][MT] parallel / anti-parallel masks of row j
+    auto MU = [&](int pb) { return dbase + pb * ppd; };              // [(MT+1)][d]
+    auto RHO = [&](int pb) { return MU(pb) + (MT + 1) * d; };        // [MT+1]
+    auto CA = [&](int pb, int s) { return RHO(pb) + (MT + 1) + (size_t)s * ((size_t)MT * d + 2 * MT + d); };   // [MT][d]
+    auto CP = [&](int pb, int s) { return CA(pb, s) + MT * d; };
+    auto CQ = [&](int pb, int s) { return CP(pb, s) + MT; };
+    auto CB = [&](int pb, int s) { return CQ(pb, s) + MT; };
+    auto GP = [&](int pb, int s) { return gates + ((size_t)(pb * spp + s) * 2) * MT; };
+    // ---- P0: parent descriptors ----
+    c.par([&](int tid) {
+      if (tid >= npb) return;
+      Par& P = par[tid];
+      P.r = sl.par_begin[ms] + pb0 + tid; P.gid = gen.alive[P.r]; P.phc = gen_m(gen, P.gid); P.F_int = 0; P.sgn = 0;
+      if (sp.with_tp) { P.m = ws.m_tp[P.r]; P.Ap = ws.A + (long long)P.r * sp.max_shape * d; P.pp = ws.p + (long long)P.r * sp.max_shape; P.bp = ws.b + (long long)P.r * d; }
+      else { P.m = P.phc; P.Ap = gen_A(gen, P.gid, P.phc, d); P.pp = gen_p(gen, P.gid, P.phc); P.bp = gen_b(gen, P.gid, d); }
+      P.zeta = sp.msmt - dot_lr(sp.H, P.bp, d);
+    });
+    // ---- P1: mu_l = a_l / (H a_l), rho_l = p_l |H a_l| (term:104-134), one (parent, row) per thread ----
+    c.par([&](int tid) {
+      for (int it = tid; it < npb * (MT + 1); it += NT) {
+        const int pb = it / (MT + 1), l = it - pb * (MT + 1);
+        Par& P = par[pb];
+        if (l > P.m) continue;
+        double* mu_l = MU(pb) + l * d;
+        if (l == P.m) { RHO(pb)[l] = sp.gamma; for (int i = 0; i < d; i++) mu_l[i] = 0; c.atomic_or(&P.F_int, 1u << l); continue; }
+        double row[MAXD];
+        for (int i = 0; i < d; i++) row[i] = P.Ap[l * d + i];
+        const double H_mu = dot_lr(sp.H, row, d), a = fabs(H_mu);
+        if (a < MU_EPS) { RHO(pb)[l] = P.pp[l]; for (int i = 0; i < d; i++) mu_l[i] = row[i]; }
+        else {
+          const double sc = 1.0 / H_mu;
+          for (int i = 0; i < d; i++) mu_l[i] = row[i] * sc;
+          RHO(pb)[l] = P.pp[l] * a; c.atomic_or(&P.F_int, 1u << l);
+          if (!(H_mu > 0)) c.atomic_or(&P.sgn, 1u << l);
+        }
+      }
+      for (int it = tid; it < npb * spp; it += NT) { Slot& S = slot[it]; S.valid = 0; S.t = 0; S.newm = 0; S.hofs = 0; S.csneg = 0; S.flags2 = 0; }
+    });
+    // ---- P2: child rows (term:158-211), one (parent, child, row) per thread ----
+    c.par([&](int tid) {
+      for (int it = tid; it < npb * spp * MT; it += NT) {
+        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+        const Par& P = par[pb];
+        const int m = P.m, t = (s == 0) ? m : s - 1;
+        if (t > m || (s != 0 && t >= m) || !((P.F_int >> t) & 1u)) continue;        // no such child
+        if (l >= m) continue;
+        const int _l = l < t ? l : l + 1;
+        const double* mu_l = MU(pb) + _l * d; const double* mu_t = MU(pb) + t * d;
+        double* ca = CA(pb, s) + l * d;
+        CP(pb, s)[l] = RHO(pb)[_l];
+        if ((P.F_int >> _l) & 1u) for (int i = 0; i < d; i++) ca[i] = mu_l[i] - mu_t[i];
+        else { for (int i = 0; i < d; i++) ca[i] = mu_l[i]; c.atomic_or(&slot[ps].hofs, 1u << l); }
+        if (l == 0) {
+          double* cb = CB(pb, s);
+          for (int i = 0; i < d; i++) cb[i] = P.bp[i] + P.zeta * mu_t[i];
+          slot[ps].valid = 1; slot[ps].t = t;
+        }
+      }
+    });
+    // ---- P3: moment contribution (est:307-338) + slot meta, one (parent, child) per thread ----
+    c.par([&](int tid) {
+      for (int ps = tid; ps < npb * spp; ps += NT) {
+        const int pb = ps / spp, s = ps - pb * spp;
+        const Par& P = par[pb]; Slot& S = slot[ps];
+        const long long ls = (long long)(pb0 + pb) * spp + s, gslot = sl.slot_begin[ms] + ls;
+        double* yout = sl.y + gslot * 2 * d;
+        if (!S.valid) {
+          SlotMeta me; me.newm = 0; me.pbc = (unsigned char)P.m; me.z = 0; me.flags = 0; me.hflag = 0; me.enc_lhp = 0; me.csneg = 0; me.parent = P.r; me.pad_ = 0; me.c_val = 0; me.d_val = 0;
+          sl.g[gslot] = make_cplx(0, 0);
+          for (int j = 0; j < 2 * d; j++) yout[j] = 0;
+          sl.meta[gslot] = me;
+          continue;
+        }
+        const int m = P.m, t = S.t, phc = P.phc;
+        unsigned enc_lhp = P.sgn;
+        if (phc < m) enc_lhp &= (1u << phc) - 1u;
+        const unsigned* pkeys = gen_keys(gen, P.gid, phc); const cplx* pG = gen_G(gen, P.gid, phc);
+        const long long rko = sp.max_shape <= 16 ? gen_rk_off(gen, P.gid, phc) : 0;
+        sl.g[gslot] = eval_g_yei(CA(pb, s), CP(pb, s), CB(pb, s), m, d, S.hofs, P.zeta, RHO(pb)[t], sp.root_point, false, phc, t, enc_lhp, pkeys, pG,
+                                 gen.cells[P.gid], yout, sp.max_shape <= 16 ? gen.rbm + rko : nullptr, sp.max_shape <= 16 ? gen.rpf + rko : nullptr);
+        if (s == 0) {
+          unsigned e = P.sgn;                                   // parent B ^= enc_sgn_AH, half-normalised (term:229-250)
+          if (e & (1u << (m - 1))) e ^= (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
+          ws.sgnmask[P.r] = e; ws.bxor[P.r] = 0;
+        }
+        S.flags2 = enc_lhp;
+        if (sp.skip_post_mu) {
+          SlotMeta me; me.newm = (unsigned char)m; me.pbc = (unsigned char)m; me.z = (unsigned char)t; me.flags = (s == 0) ? 0 : 1; me.hflag = S.hofs; me.enc_lhp = enc_lhp;
+          me.csneg = 0; me.parent = P.r; me.pad_ = 0; me.c_val = P.zeta; me.d_val = RHO(pb)[t];
+          sl.meta[gslot] = me;
+        }
+      }
+    });
+    if (sp.skip_post_mu) return;
+    // ---- P4: L1 normalisation (normalize_hps, term:458-472), one (parent, child, row) per thread ----
+    c.par([&](int tid) {
+      for (int it = tid; it < npb * spp * MT; it += NT) {
+        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+        if (!slot[ps].valid || l >= par[pb].m) continue;
+        double* ca = CA(pb, s) + l * d;
+        CQ(pb, s)[l] = CP(pb, s)[l];
+        double norm1 = 0;
+        for (int j = 0; j < d; j++) norm1 += fabs(ca[j]);
+        CP(pb, s)[l] *= norm1;
+        for (int j = 0; j < d; j++) ca[j] /= norm1;
+        GP(pb, s)[l] = 0; GP(pb, s)[MT + l] = 0;
+      }
+    });
+    // ---- P5: (anti)parallel gates of every row pair of a new child (term:563-575), one (parent, child, row j) per thread ----
+    c.par([&](int tid) {
+      for (int it = tid; it < npb * spp * MT; it += NT) {
+        const int ps = it / MT, j = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+        const int m = par[pb].m;
+        if (s == 0 || !slot[ps].valid || j >= m - 1) continue;
+        const double* A = CA(pb, s);
+        unsigned pm = 0, nm = 0;
+        for (int k = j + 1; k < m; k++) {
+          bool pos, neg;
+          coalign_gates(A + j * d, A + k * d, d, &pos, &neg);
+          if (pos) pm |= 1u << k;
+          if (neg) nm |= 1u << k;
+        }
+        GP(pb, s)[j] = pm; GP(pb, s)[MT + j] = nm;
+      }
+    });
+    // ---- P6: sequential merge of coaligned rows (mu_coalign, term:533-745), one (parent, child) per thread ----
+    c.par([&](int tid) {
+      for (int ps = tid; ps < npb * spp; ps += NT) {
+        const int pb = ps / spp, s = ps - pb * spp;
+        Slot& S = slot[ps];
+        if (!S.valid) continue;
+        const int m = par[pb].m;
+        const long long gslot = sl.slot_begin[ms] + (long long)(pb0 + pb) * spp + s;
+        int newm = m; unsigned csneg = 0, hofs = S.hofs;
+        if (s != 0) {
+          const unsigned* gp = GP(pb, s);
+          newm = mu_coalign_core(CA(pb, s), CP(pb, s), CQ(pb, s), m, d, &hofs, sl.cmap + gslot * MAXM, &csneg,
+                                 [&](int j, int k, bool* pos, bool* neg) { *pos = (gp[j] >> k) & 1u; *neg = (gp[MT + j] >> k) & 1u; });
+        }
+        S.newm = newm; S.csneg = csneg;
+        SlotMeta me; me.newm = (unsigned char)newm; me.pbc = (unsigned char)m; me.z = (unsigned char)S.t; me.flags = (unsigned char)(((s == 0) ? 0 : 1) | ((s != 0 && newm < m) ? 2 : 0));
+        me.hflag = hofs; me.enc_lhp = S.flags2; me.csneg = csneg; me.parent = par[pb].r; me.pad_ = 0; me.c_val = par[pb].zeta; me.d_val = RHO(pb)[S.t];
+        sl.meta[gslot] = me;
+      }
+    });
+    // ---- P7: store the slots (coalesced over each slot's rows) ----
+    c.par([&](int tid) {
+      for (int it = tid; it < npb * spp * MT * d; it += NT) {
+        const int ps = it / (MT * d), e = it - ps * (MT * d), pb = ps / spp, s = ps - pb * spp;
+        const Slot& S = slot[ps];
+        if (!S.valid || e >= S.newm * d) continue;
+        const long long ls = (long long)(pb0 + pb) * spp + s;
+        sl.A[sl.A_off[ms] + ls * (long long)MT * d + e] = CA(pb, s)[e];
+      }
+      for (int it = tid; it < npb * spp * MT; it += NT) {
+        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+        const Slot& S = slot[ps];
+        if (!S.valid) continue;
+        const long long ls = (long long)(pb0 + pb) * spp + s;
+        if (l < S.newm) { sl.p[sl.pq_off[ms] + ls * MT + l] = CP(pb, s)[l]; sl.q[sl.pq_off[ms] + ls * MT + l] = CQ(pb, s)[l]; }
+      }
+      for (int it = tid; it < npb * spp * d; it += NT) {
+        const int ps = it / d, i = it - ps * d, pb = ps / spp, s = ps - pb * spp;
+        if (!slot[ps].valid) continue;
+        sl.b[(sl.slot_begin[ms] + (long long)(pb0 + pb) * spp + s) * d + i] = CB(pb, s)[i];
+      }
     });
   }
 };
