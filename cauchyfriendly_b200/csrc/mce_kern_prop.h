@@ -293,7 +293,13 @@ struct KMsmtUpdate {
 // hyperplane array of its own (KMsmtUpdate keeps ~5 KB per thread in local memory, which turns into HBM traffic).
 // Arithmetic and its order are those of KMsmtUpdate / the reference, item by item.
 // ---------------------------------------------------------------------------------------------
-constexpr int MU_PB = 4;
+constexpr int MU_PB = 4;      // one warp per parent: 32 * MU_PB threads per CTA
+// (child s, element l) items of one parent walked by a lane with stride 32, without integer divisions
+struct RowIt {
+  int s, l, qd, rd, W;
+  MCE_HD RowIt(int lane, int W_) : W(W_) { s = lane / W_; l = lane - s * W_; qd = 32 / W_; rd = 32 - qd * W_; }
+  MCE_HD void next() { s += qd; l += rd; if (l >= W) { l -= W; s++; } }
+};
 struct KMsmtUpdate2 {
   StepParams sp; GenView gen; ParentWs ws; SlotView sl; int ms;
   struct Par { int r, gid, phc, m, pad; unsigned F_int, sgn; double zeta; const double *Ap, *pp, *bp; };
@@ -330,8 +336,8 @@ struct KMsmtUpdate2 {
     });
     // ---- P1: mu_l = a_l / (H a_l), rho_l = p_l |H a_l| (term:104-134), one (parent, row) per thread ----
     c.par([&](int tid) {
-      for (int it = tid; it < npb * (MT + 1); it += NT) {
-        const int pb = it / (MT + 1), l = it - pb * (MT + 1);
+      const int pb = tid >> 5, lane = tid & 31;
+      for (int l = lane; l <= MT && pb < npb; l += 32) {
         Par& P = par[pb];
         if (l > P.m) continue;
         double* mu_l = MU(pb) + l * d;
@@ -347,12 +353,13 @@ struct KMsmtUpdate2 {
           if (!(H_mu > 0)) c.atomic_or(&P.sgn, 1u << l);
         }
       }
-      for (int it = tid; it < npb * spp; it += NT) { Slot& S = slot[it]; S.valid = 0; S.t = 0; S.newm = 0; S.hofs = 0; S.csneg = 0; S.flags2 = 0; }
+      for (int s = lane; s < spp && pb < npb; s += 32) { Slot& S = slot[pb * spp + s]; S.valid = 0; S.t = 0; S.newm = 0; S.hofs = 0; S.csneg = 0; S.flags2 = 0; }
     });
     // ---- P2: child rows (term:158-211), one (parent, child, row) per thread ----
     c.par([&](int tid) {
-      for (int it = tid; it < npb * spp * MT; it += NT) {
-        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (RowIt w(lane, MT); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, l = w.l, ps = pb * spp + s;
         const Par& P = par[pb];
         const int m = P.m, t = (s == 0) ? m : s - 1;
         if (t > m || (s != 0 && t >= m) || !((P.F_int >> t) & 1u)) continue;        // no such child
@@ -372,8 +379,9 @@ struct KMsmtUpdate2 {
     });
     // ---- P3: moment contribution (est:307-338) + slot meta, one (parent, child) per thread ----
     c.par([&](int tid) {
-      for (int ps = tid; ps < npb * spp; ps += NT) {
-        const int pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (int s = lane; s < spp && pb < npb; s += 32) {
+        const int ps = pb * spp + s;
         const Par& P = par[pb]; Slot& S = slot[ps];
         const long long ls = (long long)(pb0 + pb) * spp + s, gslot = sl.slot_begin[ms] + ls;
         double* yout = sl.y + gslot * 2 * d;
@@ -407,8 +415,9 @@ struct KMsmtUpdate2 {
     if (sp.skip_post_mu) return;
     // ---- P4: L1 normalisation (normalize_hps, term:458-472), one (parent, child, row) per thread ----
     c.par([&](int tid) {
-      for (int it = tid; it < npb * spp * MT; it += NT) {
-        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (RowIt w(lane, MT); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, l = w.l, ps = pb * spp + s;
         if (!slot[ps].valid || l >= par[pb].m) continue;
         double* ca = CA(pb, s) + l * d;
         CQ(pb, s)[l] = CP(pb, s)[l];
@@ -421,8 +430,9 @@ struct KMsmtUpdate2 {
     });
     // ---- P5: (anti)parallel gates of every row pair of a new child (term:563-575), one (parent, child, row j) per thread ----
     c.par([&](int tid) {
-      for (int it = tid; it < npb * spp * MT; it += NT) {
-        const int ps = it / MT, j = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (RowIt w(lane, MT); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, j = w.l, ps = pb * spp + s;
         const int m = par[pb].m;
         if (s == 0 || !slot[ps].valid || j >= m - 1) continue;
         const double* A = CA(pb, s);
@@ -438,8 +448,9 @@ struct KMsmtUpdate2 {
     });
     // ---- P6: sequential merge of coaligned rows (mu_coalign, term:533-745), one (parent, child) per thread ----
     c.par([&](int tid) {
-      for (int ps = tid; ps < npb * spp; ps += NT) {
-        const int pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (int s = lane; s < spp && pb < npb; s += 32) {
+        const int ps = pb * spp + s;
         Slot& S = slot[ps];
         if (!S.valid) continue;
         const int m = par[pb].m;
@@ -458,22 +469,23 @@ struct KMsmtUpdate2 {
     });
     // ---- P7: store the slots (coalesced over each slot's rows) ----
     c.par([&](int tid) {
-      for (int it = tid; it < npb * spp * MT * d; it += NT) {
-        const int ps = it / (MT * d), e = it - ps * (MT * d), pb = ps / spp, s = ps - pb * spp;
+      const int pb = tid >> 5, lane = tid & 31;
+      for (RowIt w(lane, MT * d); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, e = w.l, ps = pb * spp + s;
         const Slot& S = slot[ps];
         if (!S.valid || e >= S.newm * d) continue;
         const long long ls = (long long)(pb0 + pb) * spp + s;
         sl.A[sl.A_off[ms] + ls * (long long)MT * d + e] = CA(pb, s)[e];
       }
-      for (int it = tid; it < npb * spp * MT; it += NT) {
-        const int ps = it / MT, l = it - ps * MT, pb = ps / spp, s = ps - pb * spp;
+      for (RowIt w(lane, MT); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, l = w.l, ps = pb * spp + s;
         const Slot& S = slot[ps];
         if (!S.valid) continue;
         const long long ls = (long long)(pb0 + pb) * spp + s;
         if (l < S.newm) { sl.p[sl.pq_off[ms] + ls * MT + l] = CP(pb, s)[l]; sl.q[sl.pq_off[ms] + ls * MT + l] = CQ(pb, s)[l]; }
       }
-      for (int it = tid; it < npb * spp * d; it += NT) {
-        const int ps = it / d, i = it - ps * d, pb = ps / spp, s = ps - pb * spp;
+      for (RowIt w(lane, d); w.s < spp && pb < npb; w.next()) {
+        const int s = w.s, i = w.l, ps = pb * spp + s;
         if (!slot[ps].valid) continue;
         sl.b[(sl.slot_begin[ms] + (long long)(pb0 + pb) * spp + s) * d + i] = CB(pb, s)[i];
       }
