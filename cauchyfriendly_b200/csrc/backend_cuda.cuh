@@ -61,6 +61,8 @@ struct CudaBackend {
     } catch (const std::exception& ex) { *why = ex.what(); return false; }
     return true;
   }
+  // the calling host thread may be new (window banks step their estimators from a thread pool): bind it to this device
+  void make_current() { cudaSetDevice(device); }
   void shutdown() {
     if (cub_tmp) cudaFree(cub_tmp);
     cub_tmp = nullptr; cub_tmp_bytes = 0;

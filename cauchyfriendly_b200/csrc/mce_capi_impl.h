@@ -53,6 +53,7 @@ int mce_step(mce_handle* h, double msmt, const double* Phi, const double* Gamma,
   EngineT* e = h->e;
   if (e->master_step > 0 && (e->master_step % e->p) == 0 && (!Phi || (e->pncc > 0 && (!Gamma || !beta)))) { g_mce_error = "mce_step: Phi/Gamma/beta required on a time-propagation step"; return MCE_ERR_BAD_ARG; }
   int rc;
+  e->be.make_current();
   try { rc = e->step(msmt, Phi, Gamma, beta, H, gamma, B, u); }
   catch (const std::exception& ex) { g_mce_error = std::string("mce_step: ") + ex.what(); return MCE_ERR_CUDA; }
   if (rc < 0) g_mce_error = "mce_step: " + e->error;
@@ -89,15 +90,18 @@ int mce_reinitialize_start_statistics(mce_handle* h, const double* A0, const dou
 }
 int mce_shift_b(mce_handle* h, const double* delta, double sign) {
   if (!h || !delta) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
   try { return h->e->shift_b(delta, sign); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
 int mce_deterministic_time_prop(mce_handle* h, const double* Phi, const double* B, const double* u) {
   if (!h || !Phi) return MCE_ERR_BAD_ARG;
   if ((B == nullptr) != (u == nullptr)) { g_mce_error = "mce_deterministic_time_prop: set both B and u or neither (est:1336-1344)"; return MCE_ERR_BAD_ARG; }
+  h->e->be.make_current();
   try { return h->e->det_time_prop(Phi, B, u); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
 int mce_export_shape(mce_handle* h, int m, int* n_terms, long long* n_cells_total, double* A, double* p, double* b, int* cells, uint32_t* keys, double* G) {
   if (!h || !n_terms || !n_cells_total) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
   try { return h->e->export_shape(m, n_terms, n_cells_total, A, p, b, cells, keys, G); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {

@@ -47,7 +47,7 @@ class SlidingWindowBank:
     step(msmts, controls) mirrors PySlidingWindowManager.step and returns (xhat, Phat, wavg_xhat, wavg_Phat)."""
 
     def __init__(self, num_windows, A0, p0, b0, Phi, B, Gamma, beta, H, gamma, *, estimator_cls=CauchyEstimator, est_kwargs=None,
-                 dist=None, seed=0, debug_print=False):
+                 dist=None, seed=0, debug_print=False, concurrent=False):
         self.W = int(num_windows)
         self.n = int(np.asarray(p0).size)
         self.Phi = np.asarray(Phi, np.float64).reshape(self.n, self.n)
@@ -63,6 +63,12 @@ class SlidingWindowBank:
         self.rank = dist.get_rank() if dist is not None else 0
         self.world = dist.get_world_size() if dist is not None else 1
         self.debug_print = debug_print
+        # concurrent=True steps this rank's windows from a thread pool: every estimator owns its CUDA streams and the C ABI
+        # releases the GIL, so the launch-latency-bound young windows overlap with the full one on the same GPU
+        self._pool = None
+        if concurrent:
+            from concurrent.futures import ThreadPoolExecutor
+            self._pool = ThreadPoolExecutor(max_workers=max(1, (int(num_windows) + self.world - 1) // self.world))
         kw = dict(est_kwargs or {})
         # every window is created with the same (seeded) root point / perturbation, on the rank that owns it
         self.ests = {}
@@ -136,10 +142,14 @@ class SlidingWindowBank:
         else:
             max_idx = int(np.argmax(self.win_counts))
             min_idx = int(np.argmin(self.win_counts))
+            mine = [w for w in range(self.W) if self.win_counts[w] > 0 and w in self.ests]
+            if self._pool is not None and len(mine) > 1:
+                list(self._pool.map(lambda w: self._step_window(w, msmts, controls), mine))
+            else:
+                for w in mine:
+                    self._step_window(w, msmts, controls)
             for w in range(self.W):
                 if self.win_counts[w] > 0:
-                    if w in self.ests:
-                        self._step_window(w, msmts, controls)
                     self.win_counts[w] += 1
         self._stats[:, 0] = self.win_counts
         self._exchange()
@@ -176,6 +186,9 @@ class SlidingWindowBank:
         return xhat, Phat, xavg, Pavg
 
     def shutdown(self):
+        if self._pool is not None:
+            self._pool.shutdown()
+            self._pool = None
         for e in self.ests.values():
             e.shutdown()
         self.ests = {}

@@ -63,6 +63,7 @@ struct EmuBackend {
     }
   }
   void sync() {}
+  void make_current() {}
   void side_begin() {}
   template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch(k, nblocks, nthreads, smem); }
   void side_join() {}
