@@ -153,6 +153,14 @@ class Engine {
     if (d < 2 || d > MAXD) { *why = "state dimension must be in [2, 8]"; return false; }
     if (max_shape > MAXM - 1) { *why = "max hyperplane count exceeds 31 (reference cap, est:231-235)"; return false; }
     if (pncc > MAXPN) { *why = "pncc > 4 not supported"; return false; }
+    // the group kernel keeps one table (keys + two complex values per cell) in shared memory
+    const int Hcap = cell_count_central_half(max_shape, d);
+    const size_t need = max_shape <= 16 ? KGTable2::smem_bytes(Hcap, (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1)
+                                        : KGTable::smem_bytes(next_pow2(Hcap < 4 ? 4 : Hcap));
+    if (need > 227 * 1024) {
+      *why = "a window this deep gives tables of up to " + std::to_string(Hcap) + " cells; the group kernel holds a table in shared memory (227 KB, about 5500 cells)";
+      return false;
+    }
     return true;
   }
 
