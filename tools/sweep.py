@@ -39,7 +39,8 @@ for n in range(n_lo, n_hi + 1):
     for _ in range(steps):
         x = Phi @ x + Gam * 0.1 * rng.standard_cauchy(); zs.append(H @ x + 0.2 * rng.standard_cauchy())
     _, sc = lti("syn%d_deep" % n, Phi, Gam, H, [0.1], [0.2], np.eye(n), np.full(n, .1), np.zeros(n), zs, steps, seed=100 + n)
-    s = Session(lib, sc)
+    phases = bool(os.environ.get("SWEEP_PHASES"))
+    s = Session(lib, sc, phase_timing=phases)
     for rep in range(2):                             # pass 0 sizes the buffers
         lib.mce_reset(s.h)
         child = 0; ms = 0.0; prev = 1; last = 0; rows = []
@@ -52,6 +53,8 @@ for n in range(n_lo, n_hi + 1):
             prev = st.survivors if st.survivors else prev
             ms += dt; last = k + 1
             rows.append((k + 1, st.parents, st.terms_after_muc, st.survivors, dt, st.split_groups))
+            if phases and rep == 1:
+                print("   phases: tp %.2f mu %.2f mom %.2f regroup %.2f ftr %.2f gtable %.2f compact %.2f" % (st.ms_tp, st.ms_mu, st.ms_moments, st.ms_regroup, st.ms_ftr, st.ms_gtable, st.ms_compact))
             if st.terms_after_muc * 3.5 > cap and k + 1 < len(sc.rec):      # the next step would exceed the cap
                 break
     s.close()
