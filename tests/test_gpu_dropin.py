@@ -56,3 +56,16 @@ def test_reference_example_runs_on_the_gpu_path(ref_name, our_name, tmp_path):
     assert len(m_ref) >= 10
     assert c_our == c_ref, "term counts differ:\n%s\n%s\n%s" % (c_ref, c_our, ours[-1500:])
     assert m_our == m_ref
+
+
+def test_reference_window_manager_runs_on_the_gpu_path(tmp_path):
+    """src/window_manager.cpp unchanged: SlidingWindowManager forks 8 window processes, each creating its own estimator
+    (and CUDA context) through the drop-in header; 201 measurements of the 3-state system must go through."""
+    exe = os.path.join(ROOT, "build", "dropin", "window_manager")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    out = _run(exe, str(tmp_path))
+    m = re.search(r"The Simulation of (\d+) measurements took (\S+) seconds; rate = (\S+) hz", out)
+    assert m, out[-2000:]
+    assert int(m.group(1)) == 201 and float(m.group(3)) > 0
+    assert "All children have exited" in out
