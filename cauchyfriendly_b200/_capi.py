@@ -27,10 +27,12 @@ class MceStepStats(ct.Structure):
                 ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_ftr_ms", ct.c_double), ("ev_mu_ms", ct.c_double)]
 
 
+EXCHANGE_FN = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_longlong)
+
 # every symbol include/mce_b200.h declares
 SYMBOLS = ["mce_default_options", "mce_create", "mce_destroy", "mce_step", "mce_get_moments", "mce_shape_range",
            "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_shift_b",
-           "mce_deterministic_time_prop", "mce_export_shape", "mce_get_step_stats", "mce_debug_capture", "mce_debug_muc_shape",
+           "mce_deterministic_time_prop", "mce_export_shape", "mce_get_step_stats", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback",
            "mce_last_error", "mce_version"]
 
 
@@ -54,6 +56,9 @@ def bind(lib):
     lib.mce_export_shape.argtypes = [ct.c_void_p, ct.c_int, ip, ct.POINTER(ct.c_longlong), dp, dp, dp, ip, ct.POINTER(ct.c_uint32), dp]
     lib.mce_get_step_stats.argtypes = [ct.c_void_p, ct.POINTER(MceStepStats)]
     lib.mce_debug_capture.argtypes = [ct.c_void_p, ct.c_int]
+    lib.mce_shard_unique_id.argtypes = [ct.c_int, ct.c_void_p]
+    lib.mce_shard_init.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]
+    lib.mce_shard_init_callback.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, EXCHANGE_FN, ct.c_void_p]
     lib.mce_debug_muc_shape.argtypes = [ct.c_void_p, ct.c_int, ip, dp, dp, dp, dp, dp, ip, ct.POINTER(ct.c_uint8), ct.POINTER(ct.c_int8), ip]
     lib.mce_last_error.restype = ct.c_char_p
     lib.mce_version.restype = ct.c_char_p

@@ -10,8 +10,11 @@
 #include <cub/device/device_scan.cuh>
 #include <stdexcept>
 #include <string>
+#include <string.h>
 
+#include <dlfcn.h>
 #include "mce_exec.h"
+#include "mce_shard.h"
 
 namespace mce {
 
@@ -61,9 +64,72 @@ struct CudaBackend {
     } catch (const std::exception& ex) { *why = ex.what(); return false; }
     return true;
   }
+
+  // ---- exchange layer (mce_shard.h): NCCL opened at run time, or a host callback ----
+  struct NcclId { char b[128]; };       // ncclUniqueId (passed by value to ncclCommInitRank)
+  struct Nccl {
+    void* lib = nullptr; void* comm = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr; int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+  } nccl;
+  ShardInfo shard;
+  bool nccl_load(std::string* why) {
+    if (nccl.lib) return true;
+    nccl.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!nccl.lib) { *why = std::string("cannot open libnccl.so.2: ") + dlerror(); return false; }
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(nccl.lib, n); if (!p) { ok = false; *why = std::string("libnccl.so.2 lacks ") + n; } return p; };
+    nccl.GetUniqueId = (decltype(nccl.GetUniqueId))sym("ncclGetUniqueId");
+    nccl.CommInitRank = (decltype(nccl.CommInitRank))sym("ncclCommInitRank");
+    nccl.AllGather = (decltype(nccl.AllGather))sym("ncclAllGather");
+    nccl.AllReduce = (decltype(nccl.AllReduce))sym("ncclAllReduce");
+    nccl.GroupStart = (decltype(nccl.GroupStart))sym("ncclGroupStart");
+    nccl.GroupEnd = (decltype(nccl.GroupEnd))sym("ncclGroupEnd");
+    nccl.CommDestroy = (decltype(nccl.CommDestroy))sym("ncclCommDestroy");
+    nccl.GetErrorString = (decltype(nccl.GetErrorString))sym("ncclGetErrorString");
+    return ok;
+  }
+  void nccl_check(int rc, const char* what) {
+    if (rc != 0) throw std::runtime_error(std::string(what) + ": " + (nccl.GetErrorString ? nccl.GetErrorString(rc) : "NCCL error"));
+  }
+  bool shard_unique_id(void* id128, std::string* why) {
+    if (!nccl_load(why)) return false;
+    const int rc = nccl.GetUniqueId(id128);
+    if (rc != 0) { *why = std::string("ncclGetUniqueId: ") + nccl.GetErrorString(rc); return false; }
+    return true;
+  }
+  bool shard_init_native(int rank, int world, const void* id128, std::string* why) {
+    if (!nccl_load(why)) return false;
+    make_current();
+    NcclId id; memcpy(id.b, id128, 128);
+    const int rc = nccl.CommInitRank(&nccl.comm, world, id, rank);
+    if (rc != 0) { *why = std::string("ncclCommInitRank: ") + nccl.GetErrorString(rc); return false; }
+    shard.rank = rank; shard.world = world; shard.fn = nullptr; shard.fn_ctx = nullptr;
+    return true;
+  }
+  void shard_init_callback(int rank, int world, mce_exchange_fn fn, void* ctx) { shard.rank = rank; shard.world = world; shard.fn = fn; shard.fn_ctx = ctx; }
+  // grouped exchanges: with NCCL the calls between begin/end become one launch on the engine's stream
+  void xchg_begin() { if (!shard.fn) nccl_check(nccl.GroupStart(), "ncclGroupStart"); else MCE_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+  void xchg_end() { if (!shard.fn) nccl_check(nccl.GroupEnd(), "ncclGroupEnd"); }
+  void xchg_allgather(void* base, size_t bytes_per_rank) {
+    if (bytes_per_rank == 0) return;
+    if (shard.fn) { if (shard.fn(shard.fn_ctx, MCE_XCHG_ALLGATHER, base, (long long)bytes_per_rank) != 0) throw std::runtime_error("exchange callback failed"); return; }
+    nccl_check(nccl.AllGather((const char*)base + (size_t)shard.rank * bytes_per_rank, base, bytes_per_rank, /*ncclInt8*/ 0, nccl.comm, stream), "ncclAllGather");
+  }
+  void xchg_allreduce_u32(void* base, size_t n) {
+    if (n == 0) return;
+    if (shard.fn) { if (shard.fn(shard.fn_ctx, MCE_XCHG_ALLREDUCE_SUM_U32, base, (long long)n) != 0) throw std::runtime_error("exchange callback failed"); return; }
+    nccl_check(nccl.AllReduce(base, base, n, /*ncclUint32*/ 3, /*ncclSum*/ 0, nccl.comm, stream), "ncclAllReduce");
+  }
+
   // the calling host thread may be new (window banks step their estimators from a thread pool): bind it to this device
   void make_current() { cudaSetDevice(device); }
   void shutdown() {
+    if (nccl.comm && nccl.CommDestroy) { nccl.CommDestroy(nccl.comm); nccl.comm = nullptr; }
     if (cub_tmp) cudaFree(cub_tmp);
     cub_tmp = nullptr; cub_tmp_bytes = 0;
     for (int i = 0; i < 12; i++) if (evs[i]) { cudaEventDestroy(evs[i]); evs[i] = nullptr; }

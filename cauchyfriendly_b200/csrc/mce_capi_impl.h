@@ -132,6 +132,35 @@ int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p
   }
   return 0;
 }
+int mce_shard_unique_id(int device, void* id128) {
+  if (!id128) return MCE_ERR_BAD_ARG;
+  MCE_BACKEND be; std::string why;
+  (void)device;
+  if (!be.shard_unique_id(id128, &why)) { g_mce_error = "mce_shard_unique_id: " + why; return MCE_ERR_CUDA; }
+  return 0;
+}
+static int shard_check(mce_handle* h, int rank, int world) {
+  if (!h || world < 1 || rank < 0 || rank >= world) { g_mce_error = "mce_shard_init: bad argument"; return MCE_ERR_BAD_ARG; }
+  if (h->e->max_shape > 16) { g_mce_error = "mce_shard_init: term-level sharding needs at most 16 hyperplanes per term"; return MCE_ERR_BAD_ARG; }
+  if (h->e->master_step != 0) { g_mce_error = "mce_shard_init: call before the first step"; return MCE_ERR_BAD_ARG; }
+  return 0;
+}
+int mce_shard_init(mce_handle* h, int rank, int world, const void* id128) {
+  const int rc = shard_check(h, rank, world);
+  if (rc) return rc;
+  if (!id128) return MCE_ERR_BAD_ARG;
+  std::string why;
+  if (!h->e->be.shard_init_native(rank, world, id128, &why)) { g_mce_error = "mce_shard_init: " + why; return MCE_ERR_CUDA; }
+  return 0;
+}
+int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn fn, void* ctx) {
+  const int rc = shard_check(h, rank, world);
+  if (rc) return rc;
+  if (!fn) return MCE_ERR_BAD_ARG;
+  h->e->be.shard_init_callback(rank, world, (mce::mce_exchange_fn)fn, ctx);
+  return 0;
+}
+
 const char* mce_last_error(void) { return g_mce_error.c_str(); }
 const char* mce_version(void) { return MCE_VERSION_STRING; }
 

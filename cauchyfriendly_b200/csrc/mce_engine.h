@@ -347,9 +347,12 @@ class Engine {
       ws.m_tp = (unsigned char*)wsm.ensure((size_t)n_alive + 16);
       be.launch(KTimeProp{sp, pg.v, ws}, (n_alive + 127) / 128, 128, 0);
       if (!skip_post_mu) {
+        const int W = be.shard.world, pch = shard_chunk(n_alive, W);        // term-level sharding: a chunk of parents per rank
+        int tp0 = 0, tp1 = n_alive;
+        if (W > 1) shard_range(n_alive, be.shard.rank, W, &tp0, &tp1);
         ws.tpB_stride = Hcap;
-        ws.tpB = (unsigned*)wsTpB.ensure(sizeof(unsigned) * (size_t)n_alive * Hcap);
-        ws.tpB_cells = (int*)wsTpBc.ensure(sizeof(int) * (n_alive + 4));
+        ws.tpB = (unsigned*)wsTpB.ensure(sizeof(unsigned) * (size_t)pch * W * Hcap);
+        ws.tpB_cells = (int*)wsTpBc.ensure(sizeof(int) * ((size_t)pch * W + 4));
         int max_mtp = 0;
         for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) max_mtp = m + sp.npn;
         if (max_mtp > max_shape) max_mtp = max_shape;
@@ -358,9 +361,15 @@ class Engine {
         const int nth = 128;
         if (max_shape <= 16) {
           const int NWt = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
-          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag}, n_alive, nth, KTpDce2::smem_bytes(NWt, nth, d));
+          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2::smem_bytes(NWt, nth, d));
         } else {
-          be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag}, n_alive, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
+          be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag, tp0}, tp1 - tp0, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
+        }
+        if (W > 1) {           // every rank receives the B-tables of the other ranks' parents
+          be.xchg_begin();
+          be.xchg_allgather(ws.tpB, sizeof(unsigned) * (size_t)pch * Hcap);
+          be.xchg_allgather(ws.tpB_cells, sizeof(int) * (size_t)pch);
+          be.xchg_end();
         }
       }
     }
@@ -559,7 +568,7 @@ class Engine {
         const int Hm = cell_count_central_half(m, d);
         for (int ph = 0; ph < 2; ph++) {
           const int ix = ph * NSHAPE + m;
-          be.launch(KBigGroups{gstart, cr_d + 2 * m, ph, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix}, nb, 128, 0);
+          be.launch(KBigGroups{gstart, cr_d + 2 * m, ph, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix, be.shard.rank, be.shard.world}, nb, 128, 0);
         }
       }
     }
@@ -582,8 +591,18 @@ class Engine {
       n_groups[m] = cr[2 * m];
       n_phase1[m] = cr[2 * m + 1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
     }
-    fill_gen_layout(ng, n_groups);
+    // Term-level sharding (mce_shard.h): every (phase, shape) block of group slots is padded to a multiple of the world size,
+    // so that the ranks' equal chunks of every output array can be all-gathered in place; padding slots stay dead.
+    const int W = be.shard.world, R = be.shard.rank;
+    std::vector<int> n_layout(n_groups), shift1(NSHAPE, 0);
+    if (W > 1)
+      for (int m : shapes) {
+        const int pad0 = round_up(n_phase1[m], W), pad1 = round_up(n_groups[m] - n_phase1[m], W);
+        n_layout[m] = pad0 + pad1; shift1[m] = pad0 - n_phase1[m];
+      }
+    fill_gen_layout(ng, n_layout);
     unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
+    if (W > 1) be.memset(aflag, 0, (size_t)ng.v.n_groups);
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
     const size_t gsm = KGTable::smem_bytes(HC2);
     long long total_groups = 0;
@@ -607,12 +626,15 @@ class Engine {
       }
     }
     be.ev_record(2);
-    for (int phase = 0; phase < 2; phase++)
+    for (int phase = 0; phase < 2; phase++) {
       for (int m = 1; m < NSHAPE; m++) {
         if (n_groups[m] == 0) continue;
         const int g0 = phase == 0 ? 0 : n_phase1[m], g1 = phase == 0 ? n_phase1[m] : n_groups[m];
         if (g1 <= g0) continue;
         total_groups += g1 - g0;
+        int lo = g0, hi = g1;                                   // this rank's groups of the block
+        if (W > 1) { shard_range(g1 - g0, R, W, &lo, &hi); lo += g0; hi += g0; }
+        const int gshift = phase == 0 ? 0 : shift1[m];
         const int Hm = cell_count_central_half(m, d);
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
         if (max_shape <= 16) {
@@ -626,12 +648,12 @@ class Engine {
           }
           const int* ord = order_all + tv.t_begin[m]; const int* gst = gstart_all + gstart_off[m];
           const size_t smb = KGTable2::smem_bytes(Hcap, NW);
-          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba};
-          be.launch(k, g1 - g0, nth, smb);
+          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
+          be.launch(k, hi - lo, nth, smb);
           if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
-            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbg, nth, smb);
-            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbp, nth, smb);
-            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pg.v, ng.v, ws, tv, m, g0, ord, gst, Hcap, NW, aflag, diag, big_T, ba}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
+            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
           }
         } else {
           KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
@@ -639,6 +661,27 @@ class Engine {
         }
         stats.gtable_launches++;
       }
+      if (W > 1) {             // all-gather the new terms and tables of this phase; after phase 0 also the re-orientation masks
+        be.xchg_begin();
+        for (int m : shapes) {
+          const int g0 = phase == 0 ? 0 : n_phase1[m], g1 = phase == 0 ? n_phase1[m] : n_groups[m];
+          if (g1 <= g0) continue;
+          const size_t ch = (size_t)shard_chunk(g1 - g0, W);
+          const int gidA = ng.v.gid_begin[m] + (phase == 0 ? 0 : round_up(n_phase1[m], W));
+          const size_t stride = (size_t)ng.v.tab_stride[m];
+          be.xchg_allgather(ng.v.g_m + gidA, ch);
+          be.xchg_allgather(ng.v.cells + gidA, ch * sizeof(int));
+          be.xchg_allgather(aflag + gidA, ch);
+          be.xchg_allgather(gen_A(ng.v, gidA, m, d), ch * m * d * sizeof(double));
+          be.xchg_allgather(gen_p(ng.v, gidA, m), ch * m * sizeof(double));
+          be.xchg_allgather(gen_b(ng.v, gidA, d), ch * d * sizeof(double));
+          be.xchg_allgather(gen_keys(ng.v, gidA, m), ch * stride * sizeof(unsigned));
+          be.xchg_allgather(gen_G(ng.v, gidA, m), ch * stride * sizeof(cplx));
+        }
+        if (phase == 0) be.xchg_allreduce_u32(ws.bxor, (size_t)n_alive);
+        be.xchg_end();
+      }
+    }
     be.ev_record(3);
     stats.ev_gtable_ms = be.ev_elapsed(2, 3); stats.ev_ftr_ms = be.ev_elapsed(7, 8);
     stats.groups = total_groups;

@@ -162,11 +162,12 @@ MCE_HD bool solve_vertex_s(double* Ac, int st, const double* bc, double* vertex,
 
 struct KTpDce {
   StepParams sp; GenView gen; ParentWs ws; int vis_cap /*pow2*/, acc_cap /*pow2*/; int* diag;
+  int r0 = 0;
   static MCE_HD size_t smem_bytes(int vis_cap, int acc_cap, int nthreads) {
     return sizeof(double) * MAXM * MAXD + sizeof(unsigned) * ((size_t)vis_cap + 2 * (size_t)acc_cap + 2 * (size_t)nthreads + 8);
   }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int r = c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
+    const int r = r0 + c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
     const unsigned* pkeys = gen_keys(gen, gid, phc);
     unsigned* out = ws.tpB + (long long)r * ws.tpB_stride;
     if (m == phc) {                       // Gamma fully coaligned: B is unchanged (est:680-685)

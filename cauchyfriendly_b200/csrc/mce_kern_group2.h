@@ -24,11 +24,12 @@ namespace mce {
 struct KTpDce2 {
   static constexpr int kMaxThreads = 128, kMinBlocks = 6;
   StepParams sp; GenView gen; ParentWs ws; int NW /* 2^max_shape / 32 */; int* diag;
+  int r0 = 0;                           // first parent of this launch (term-level sharding: a rank takes a range of parents)
   static MCE_HD size_t smem_bytes(int NW, int nthreads, int d) {
     return sizeof(double) * (MAXM * MAXD + (size_t)d * d * nthreads) + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
   }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int r = c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
+    const int r = r0 + c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
     const unsigned* pkeys = gen_keys(gen, gid, phc);
     unsigned* out = ws.tpB + (long long)r * ws.tpB_stride;
     if (m == phc) {                       // Gamma fully coaligned: B is unchanged (est:680-685)
@@ -261,6 +262,7 @@ struct KGTable2T {
   unsigned char* alive_flag; int* diag;
   int big_T;                    // G2_NORMAL: groups with more members are left to the split launches
   BigArgs big;
+  int gid_shift = 0;            // slot of group gi in the new generation = gid_begin[m] + gi + gid_shift (sharded layouts pad each phase)
   static MCE_HD size_t smem_bytes(int HC, int NW) {
     return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + 1024) * sizeof(unsigned short) + 64;
   }
@@ -590,7 +592,7 @@ struct KGTable2T {
     const int start = grp_start[gi];
     w.ncomb = grp_start[gi + 1] - start;
     w.members = order + start;
-    w.gid_out = next.gid_begin[m] + gi;
+    w.gid_out = next.gid_begin[m] + gi + gid_shift;
     w.rev_m = (1u << m) - 1u; w.top_m = 1u << (m - 1);
     w.nwM = m >= 5 ? (1 << (m - 5)) : 1;
     w.cbase = 0;
@@ -652,9 +654,11 @@ using KGTable2 = KGTable2T<G2_NORMAL>;
 struct KBigGroups {
   const int* grp_start; const int* roots /* device: [0] groups, [1] groups rooted at an old term */; int phase, T, Hm;
   BigGroup* groups; BigPart* parts; int* cnt /*[2]: groups, parts*/; unsigned long long* cnt64 /*[3]: rows, flags, keys*/;
+  int rank = 0, world = 1;      // term-level sharding: only the groups of this rank's chunk of the phase are listed
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
-      const int ga = phase == 0 ? 0 : roots[1], gb = phase == 0 ? roots[1] : roots[0];
+      int ga = phase == 0 ? 0 : roots[1], gb = phase == 0 ? roots[1] : roots[0];
+      if (world > 1) { const int ch = (gb - ga + world - 1) / world, lo = ga + rank * ch, hi = lo + ch; ga = lo < gb ? lo : gb; gb = hi < gb ? hi : gb; }
       const int gi = ga + c.block() * c.nthreads() + tid;
       if (gi >= gb) return;
       const int size = grp_start[gi + 1] - grp_start[gi];

@@ -1,0 +1,58 @@
+"""Term-level sharding of one estimator over torch.distributed ranks (one process per GPU) -- host glue for the
+mce_shard_* entry points of include/mce_b200.h (design: csrc/mce_shard.h).
+
+Every rank creates the estimator with identical arguments, calls `init_term_sharding` once before the first step, and then
+makes identical step calls; all ranks end up with bit-identical state and moments.
+
+transport="nccl": the library opens libnccl.so.2 itself and issues grouped all-gathers on its own CUDA stream; torch.distributed
+is only used to ship the 128-byte NCCL id from rank 0.  transport="callback": the library hands every exchange to Python,
+which runs it over `dist` (used by the CPU tests with the gloo backend and host memory)."""
+import ctypes as ct
+
+import numpy as np
+
+from . import _capi
+
+_KEEP = []          # callback objects must outlive the handles that use them
+EXCHANGES = [0, 0]   # callback transport: number of exchanges, bytes received per rank (diagnostics)
+
+
+def init_term_sharding(handle, dist, lib=None, transport="nccl", device=-1):
+    lib = lib or _capi.load()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return
+    if transport == "nccl":
+        buf = ct.create_string_buffer(128)
+        if rank == 0 and lib.mce_shard_unique_id(device, buf) != 0:
+            raise RuntimeError(lib.mce_last_error().decode())
+        box = [bytes(buf.raw)]
+        dist.broadcast_object_list(box, src=0)
+        ident = ct.create_string_buffer(box[0], 128)
+        if lib.mce_shard_init(handle, rank, world, ident) != 0:
+            raise RuntimeError(lib.mce_last_error().decode())
+        return
+    import torch
+
+    def exchange(_ctx, op, base, n):
+        try:
+            EXCHANGES[0] += 1
+            EXCHANGES[1] += n * (world - 1) if op == 0 else 4 * n
+            if op == 0:          # in-place all-gather of `world` chunks of n bytes
+                whole = torch.from_numpy(np.ctypeslib.as_array((ct.c_ubyte * (n * world)).from_address(base)))
+                chunks = [torch.empty(n, dtype=torch.uint8) for _ in range(world)]
+                dist.all_gather(chunks, whole[rank * n:(rank + 1) * n].clone())
+                for r in range(world):
+                    whole[r * n:(r + 1) * n] = chunks[r]
+            else:                # in-place sum of n uint32 (two's complement: the int32 sum has the same bits)
+                t = torch.from_numpy(np.ctypeslib.as_array((ct.c_int32 * n).from_address(base)))
+                dist.all_reduce(t)
+            return 0
+        except Exception as e:      # noqa: BLE001 -- must not unwind through the C caller
+            print("exchange callback failed:", e, flush=True)
+            return 1
+
+    fn = _capi.EXCHANGE_FN(exchange)
+    _KEEP.append(fn)
+    if lib.mce_shard_init_callback(handle, rank, world, fn, None) != 0:
+        raise RuntimeError(lib.mce_last_error().decode())

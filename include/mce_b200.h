@@ -115,6 +115,19 @@ typedef struct mce_step_stats {
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 
+/* ---- Term-level sharding of ONE estimator over several ranks (one process per GPU; SURVEY.md 8e, csrc/mce_shard.h) ----
+ * Every rank creates the estimator with identical arguments and makes identical calls; the DCE-TP and G-table kernels are
+ * split over the ranks and their outputs all-gathered, so all ranks hold the same (bit-identical) state and moments.
+ * Native transport: NCCL (libnccl.so.2 opened at run time).  Rank 0 calls mce_shard_unique_id, ships the 128 bytes to the
+ * other ranks by any means (e.g. torch.distributed.broadcast), then every rank calls mce_shard_init.
+ * Callback transport: the library calls `fn` for every exchange (op 0: in-place all-gather of world chunks of n bytes at
+ * base, chunk `rank` valid on entry; op 1: in-place sum of n uint32 over the ranks); the pointers are device pointers on
+ * the CUDA build.  Requires at most 16 hyperplanes per term. */
+typedef int (*mce_exchange_fn)(void* ctx, int op, void* base, long long n);
+int mce_shard_unique_id(int device, void* id128);
+int mce_shard_init(mce_handle* h, int rank, int world, const void* id128);
+int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn fn, void* ctx);
+
 /* Test hook: keep a host copy of the post-MUC term list and FTR flag arrays of the last step. */
 int mce_debug_capture(mce_handle* h, int enable);
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,

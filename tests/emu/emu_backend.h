@@ -12,8 +12,11 @@
 
 #include <algorithm>
 #include <numeric>
+#include <stdexcept>
 #include <string>
 #include <vector>
+
+#include "../../cauchyfriendly_b200/csrc/mce_shard.h"
 
 namespace mce {
 
@@ -63,6 +66,15 @@ struct EmuBackend {
     }
   }
   void sync() {}
+  // exchange layer: callback transport only (tests drive it over torch.distributed / gloo)
+  ShardInfo shard;
+  bool shard_unique_id(void*, std::string* why) { *why = "the emulation backend has no native transport"; return false; }
+  bool shard_init_native(int, int, const void*, std::string* why) { *why = "the emulation backend has no native transport"; return false; }
+  void shard_init_callback(int rank, int world, mce_exchange_fn fn, void* ctx) { shard.rank = rank; shard.world = world; shard.fn = fn; shard.fn_ctx = ctx; }
+  void xchg_begin() {}
+  void xchg_end() {}
+  void xchg_allgather(void* base, size_t bytes_per_rank) { if (bytes_per_rank && shard.fn(shard.fn_ctx, MCE_XCHG_ALLGATHER, base, (long long)bytes_per_rank) != 0) throw std::runtime_error("exchange callback failed"); }
+  void xchg_allreduce_u32(void* base, size_t n) { if (n && shard.fn(shard.fn_ctx, MCE_XCHG_ALLREDUCE_SUM_U32, base, (long long)n) != 0) throw std::runtime_error("exchange callback failed"); }
   void make_current() {}
   void side_begin() {}
   template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch(k, nblocks, nthreads, smem); }

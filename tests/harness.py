@@ -124,9 +124,12 @@ def _ssum(a):
     return float(np.add.accumulate(a)[-1]) if a.size else 0.0
 
 
-def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0):
+def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0,
+                 on_create=None):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
     s = Session(lib, sc, print_basic_info=print_basic_info, split=split)
+    if on_create is not None:
+        on_create(s)
     out = {}
     d = sc.d
     MS = s.shape_range - 1
