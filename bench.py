@@ -150,6 +150,10 @@ def gpu_arm(args):
     lib = load_product()
     sc = read_scenario(SCEN)
     s = Session(lib, sc, device=local_rank)
+    term_sharded = dist is not None and args.shard == "terms"
+    if term_sharded:
+        from cauchyfriendly_b200.shard import init_term_sharding
+        init_term_sharding(s.h, dist, lib=lib, transport="nccl", device=local_rank)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def one_pass(collect):
@@ -207,9 +211,10 @@ def gpu_arm(args):
         t = torch.tensor([ev_s, wall_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ev_s, wall_s = float(t[0]), float(t[1])
-        c = torch.tensor([child], dtype=torch.int64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        child = int(c[0])
+        if not term_sharded:                  # term sharding: every rank works on the same window
+            c = torch.tensor([child], dtype=torch.int64, device="cuda")
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            child = int(c[0])
     if rank == 0:
         peaks, which = _peaks()
         a0 = acc[-1]
@@ -224,12 +229,12 @@ def gpu_arm(args):
             except Exception:
                 traffic = None
         line = {"metric": METRIC, "value": child / ev_s, "unit": "child terms/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-                "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "strong" if term_sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "child_terms_per_step": child // (args.steps * world), "mus_per_step": len(sc.rec),
+                "config": {"workload": WORKLOAD, "child_terms_per_step": child // (args.steps * (1 if term_sharded else world)), "mus_per_step": len(sc.rec),
                            "ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
                            "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
-                           "parallelism": "window-per-gpu x%d" % world, "l2": "flushed between timed iterations (256 MiB fill)",
+                           "parallelism": ("one window, terms sharded over %d gpus (NCCL all-gather of DCE-TP and G-table outputs)" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
                            "moments": "reference serial order (bit-exact)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
                 "e2e": {"value": child / wall_s, "unit": "child terms/s", "h2d_bytes_per_step": a0["h2d"], "d2h_bytes_per_step": a0["d2h"]},
                 "gpu_launches": int(sum(a["launches"] for a in acc)),
@@ -258,6 +263,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="windows", choices=["windows", "terms"],
+                    help="N > 1: one window per GPU (default, weak scaling) or ONE window with its terms sharded over the GPUs (strong scaling)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)

@@ -125,9 +125,9 @@ def _ssum(a):
 
 
 def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0,
-                 on_create=None):
+                 on_create=None, device=-1):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc, print_basic_info=print_basic_info, split=split)
+    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device)
     if on_create is not None:
         on_create(s)
     out = {}
