@@ -43,6 +43,8 @@ mce_handle* mce_create(int d, int cmcc, int pncc, int p, int steps, const double
 
 void mce_destroy(mce_handle* h) {
   if (!h) return;
+  h->e->be.make_current();
+  try { h->e->release_all(); } catch (...) {}
   h->e->be.shutdown();
   delete h->e; delete h;
 }
@@ -104,6 +106,29 @@ int mce_export_shape(mce_handle* h, int m, int* n_terms, long long* n_cells_tota
   h->e->be.make_current();
   try { return h->e->export_shape(m, n_terms, n_cells_total, A, p, b, cells, keys, G); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
+int mce_cpdf_grid_count(double grid_low, double grid_high, double grid_res) {
+  if (!(grid_high > grid_low) || !(grid_res > 0)) return MCE_ERR_BAD_ARG;                     // asserts of cpdf_ndim.hpp:2057-2058
+  return (int)((grid_high - grid_low + grid_res - 1e-15) / grid_res) + 1;                   // cpdf_ndim.hpp:2060
+}
+int mce_marginal_1d_points(mce_handle* h, int marg_idx, const double* bar_nu, int n, const double* xs, double* ys) {
+  if (!h || !bar_nu || !xs || !ys || n < 1) { g_mce_error = "mce_marginal_1d_points: bad argument"; return MCE_ERR_BAD_ARG; }
+  h->e->be.make_current();
+  int rc;
+  try { rc = h->e->marginal_1d_points(marg_idx, bar_nu, n, xs, ys); } catch (const std::exception& ex) { g_mce_error = std::string("mce_marginal_1d_points: ") + ex.what(); return MCE_ERR_CUDA; }
+  if (rc < 0) { g_mce_error = "mce_marginal_1d_points: " + h->e->error; return MCE_ERR_BAD_ARG; }
+  return rc;
+}
+int mce_marginal_1d_grid(mce_handle* h, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res, double* xy, int n_cap) {
+  const int n = mce_cpdf_grid_count(grid_low, grid_high, grid_res);
+  if (!h || !xy || n < 1 || n > n_cap) { g_mce_error = "mce_marginal_1d_grid: bad grid or capacity"; return MCE_ERR_BAD_ARG; }
+  std::vector<double> xs(n), ys(n);
+  for (int i = 0; i < n; i++) { double g = grid_low + i * grid_res; if (g > grid_high) g = grid_high; xs[i] = g; }   // cpdf_ndim.hpp:2063-2070
+  const int rc = mce_marginal_1d_points(h, marg_idx, bar_nu, n, xs.data(), ys.data());
+  if (rc <= 0) return rc;
+  for (int i = 0; i < n; i++) { xy[2 * i] = xs[i]; xy[2 * i + 1] = ys[i]; }
+  return n;
+}
+double mce_cpdf_last_ms(mce_handle* h) { return h ? h->e->cpdf_ms : 0.0; }
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
   if (!h || !out) return MCE_ERR_BAD_ARG;
   const mce::StepStats& s = h->e->stats;

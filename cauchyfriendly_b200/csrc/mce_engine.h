@@ -16,6 +16,7 @@
 #include "mce_kern_group.h"
 #include "mce_kern_group2.h"
 #include "mce_kern_prop.h"
+#include "mce_kern_cpdf.h"
 
 namespace mce {
 
@@ -109,6 +110,8 @@ class Engine {
   } gen[2];
   int cur = 0;
   DevBuf<BE> wsA, wsp, wsb, wsm, wsSgn, wsXor, wsTpB, wsTpBc;
+  DevBuf<BE> cpVal0, cpCache, cpXs, cpOut;   // point-wise marginal cpdf (mce_kern_cpdf.h)
+  double cpdf_ms = 0;                          // device time of the last marginal_1d_points call (CUDA events)
   DevBuf<BE> slA, slp, slq, slb, slmeta, slcmap, slg, sly;
   DevBuf<BE> tvA, tvp, tvq, tvb, tvmeta, tvcmap, slotOfTerm;
   DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
@@ -143,11 +146,13 @@ class Engine {
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
                          &scratchI0, &scratchI1, &scratchI2, &scratchI3, &scratchK0, &scratchK1, &ftrF, &ftrWide, &grpOrder, &grpStart,
-                         &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys};
-    for (auto* b : all) b->be = &be;
+                         &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys, &cpVal0, &cpCache, &cpXs, &cpOut};
+    for (auto* b : all) { b->be = &be; all_bufs.push_back(b); }
     gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0);
   }
   ~Engine() {}
+  std::vector<DevBuf<BE>*> all_bufs;
+  void release_all() { for (auto* b : all_bufs) b->release(); }   // device memory of this estimator (mce_destroy)
 
   static bool supported(int d, int max_shape, int pncc, std::string* why) {
     if (d < 2 || d > MAXD) { *why = "state dimension must be in [2, 8]"; return false; }
@@ -815,6 +820,39 @@ class Engine {
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = 1;
     gen[0].v.n_alive = 0; gen[1].v.n_alive = 0;
     cur = 0;          // same buffer parity on every pass of a window: the grow-only buffers settle after the first pass
+  }
+
+
+  // Point-wise 1-D marginal cpdf at the points xs[0..n) (cpdf_ndim.hpp:1233-1354 as driven by the grid dispatcher,
+  // cpdf_ndim.hpp:2074-2139: the first point is evaluated uncached, the others from the per-term cache).  Returns n, 0 when
+  // the estimator holds no tables (the window's last step, SKIP_LAST_STEP: cpdf_ndim.hpp:2079-2083), < 0 on misuse.
+  int marginal_1d_points(int marg_idx, const double* bar_nu, int n, const double* xs, double* ys) {
+    if (master_step < 1) { error = "marginal cpdf: the estimator has not been stepped (cpdf_ndim.hpp:1239)"; return -2; }
+    if (marg_idx < 0 || marg_idx >= d || n < 1) { error = "marginal cpdf: bad state index or point count"; return -2; }
+    if (master_step == num_estimation_steps || skip_post_mu) return 0;
+    GenStore& g = gen[cur];
+    const int nt = g.v.n_alive;
+    if (nt <= 0) return 0;
+    double* val0 = (double*)cpVal0.ensure(sizeof(double) * (size_t)nt);
+    Cpdf1dTerm* cache = (Cpdf1dTerm*)cpCache.ensure(sizeof(Cpdf1dTerm) * (size_t)nt);
+    double* dxs = (double*)cpXs.ensure(sizeof(double) * (size_t)n);
+    double* dout = (double*)cpOut.ensure(sizeof(double) * (size_t)n);
+    be.h2d(dxs, xs, sizeof(double) * (size_t)n);
+    be.ev_record(10);
+    KCpdf1dTerms kt; memset(&kt, 0, sizeof(kt));
+    kt.gen = g.v; kt.d = d; kt.marg_idx = marg_idx; kt.x0 = xs[0]; kt.val0 = val0; kt.cache = cache;
+    for (int i = 0; i < d; i++) kt.bar_nu[i] = bar_nu[i];
+    be.launch(kt, (nt + 127) / 128, 128, 0);
+    const int NTH = 32;      // one warp per CTA: a few thousand grid points still reach every SM
+    KCpdf1dGrid kg{nt, n, dxs, val0, cache, dout};
+    be.launch(kg, (n + NTH - 1) / NTH, NTH, KCpdf1dGrid::smem_bytes());
+    be.ev_record(11);
+    be.d2h(ys, dout, sizeof(double) * (size_t)n);
+    cpdf_ms = be.ev_elapsed(10, 11);
+    const double norm_factor = fz.re, RECIPRICAL_TWO_PI = 1.0 / (2.0 * M_PI);   // cauchy_constants.hpp:25
+    ys[0] = ys[0] * RECIPRICAL_TWO_PI / norm_factor;                           // cpdf_ndim.hpp:1351-1352
+    for (int k = 1; k < n; k++) ys[k] = ys[k] / norm_factor;                   // cpdf_ndim.hpp:1349-1350
+    return n;
   }
 
   // Host copy of the parents of shape m (canonical order).

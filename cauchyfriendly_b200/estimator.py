@@ -3,6 +3,7 @@ C ABI of libmce_b200.so.  Same member names, argument meaning and error behaviou
 against the reference (src/*.cpp, scripts/swig/cauchy/cauchy_estimator.py:515 PyCauchyEstimator) ports line by line.
 All term-list work happens on the GPU; this file only marshals arguments."""
 import ctypes as ct
+import os
 
 import numpy as np
 
@@ -160,6 +161,64 @@ class CauchyEstimator:
                                        cells.ctypes.data_as(ct.POINTER(ct.c_int)), keys.ctypes.data_as(ct.POINTER(ct.c_uint32)),
                                        G.view(np.float64).ctypes.data_as(ct.POINTER(ct.c_double)))
         return dict(A=A, p=p, b=b, cells=cells, keys=keys, G=G)
+
+    # ---- point-wise marginal cpdf (cauchy_estimator.py:1003-1031 / pycauchy.hpp:890-931), evaluated on the device ----
+    def _bar_nu(self):
+        # the reference draws this direction with rand() when the cpdf object is created (cpdf_ndim.hpp:385-389: 2 U(0,1])
+        if getattr(self, "bar_nu", None) is None:
+            self.bar_nu = 2.0 * (np.random.RandomState(12345).randint(0, 2**31 - 1, self.d) + 1.0) / 2.0**31
+        return _f64(self.bar_nu, self.d)
+
+    def get_marginal_1D_pointwise_cpdf(self, marg_idx, gridx_low, gridx_high, gridx_resolution, log_dir=None):
+        """X, Y of the marginal cpdf of state `marg_idx` on the grid [low, high] with step `resolution` (same grid, same
+        values and -- when `log_dir` is given -- the same files as the reference: cpdf_ndim.hpp:2055-2072, 2141-2202)."""
+        if self.master_step < 1:
+            print("Cannot evaluate Cauchy Estimator 1D Marginal CPDF before it has been stepped!")
+            return None, None
+        lo, hi, res, idx = float(gridx_low), float(gridx_high), float(gridx_resolution), int(marg_idx)
+        assert hi > lo and res > 0 and -1 < idx < self.d
+        n = self._lib.mce_cpdf_grid_count(lo, hi, res)
+        xy = np.zeros((n, 2))
+        bar_nu = self._bar_nu()
+        rc = self._lib.mce_marginal_1d_grid(self._h, idx, _dp(bar_nu), lo, hi, res, _dp(xy), n)
+        if rc < 0:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+        if rc == 0:
+            print("[WARN CauchyCPDFGridDispatcher1D:] Cannot evaluate cauchy estimator cpdf for the last step since SKIP_LAST_STEP == true!")
+            return np.zeros(0), np.zeros(0)
+        if log_dir:
+            self._log_1d_grid(str(log_dir).rstrip("/"), idx, xy)
+        return xy[:, 0].copy(), xy[:, 1].copy()
+
+    def get_1D_pointwise_cpdf(self, gridx_low, gridx_high, gridx_resolution, log_dir=None):   # cauchy_estimator.py:1033
+        if self.d != 1:
+            print("Cannot evaluate Cauchy Estimator 1D CPDF for a {}-state system!".format(self.d))
+            return None, None
+        return self.get_marginal_1D_pointwise_cpdf(0, gridx_low, gridx_high, gridx_resolution, log_dir)
+
+    def marginal_1d_points(self, marg_idx, xs):
+        """f(xs[k]) for arbitrary points; the first point is evaluated uncached like the grid dispatcher's first point."""
+        xs = np.ascontiguousarray(xs, np.float64)
+        ys = np.zeros_like(xs)
+        bar_nu = self._bar_nu()
+        rc = self._lib.mce_marginal_1d_points(self._h, int(marg_idx), _dp(bar_nu), len(xs), _dp(xs), _dp(ys))
+        if rc < 0:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+        return ys if rc > 0 else np.zeros(0)
+
+    def cpdf_last_ms(self):
+        return self._lib.mce_cpdf_last_ms(self._h)
+
+    def _log_1d_grid(self, log_dir, marg_idx, xy):
+        # CauchyCPDFGridDispatcher1D::log_point_grid (cpdf_ndim.hpp:2141-2202): binary (x, y) pairs appended per call to
+        # cpdf_<idx>_<count>.bin and one "<num_points>" row per call in grid_elems_<idx>.txt
+        os.makedirs(log_dir, exist_ok=True)
+        counts = self.__dict__.setdefault("_cpdf_log_counts", {})
+        k = counts.get((log_dir, marg_idx), 0)
+        with open(os.path.join(log_dir, "grid_elems_%d.txt" % marg_idx), "w" if k == 0 else "a") as f:
+            f.write("%d\n" % len(xy))
+        xy.astype(np.float64).tofile(os.path.join(log_dir, "cpdf_%d_%d.bin" % (marg_idx, k + 1)))   # tag_count starts at 1
+        counts[(log_dir, marg_idx)] = k + 1
 
     def print_conditional_mean_variance(self):   # est:513-522
         print("fz: %.16f + %.16fj" % (self.fz.real, self.fz.imag))

@@ -95,6 +95,22 @@ int mce_deterministic_time_prop(mce_handle* h, const double* Phi, const double* 
 int mce_export_shape(mce_handle* h, int m, int* n_terms, long long* n_cells_total, double* A /*[n][m*d]*/, double* p /*[n][m]*/,
                      double* b /*[n][d]*/, int* cells /*[n]*/, uint32_t* keys /*[sum cells]*/, double* G /*[sum cells][2]*/);
 
+/* Point-wise 1-D marginal conditional pdf, evaluated on the device from the resident term list (no term export).
+ * Replaces PointWiseNDimCauchyCPDF::evaluate_1D_marginal_cpdf (cpdf_ndim.hpp:1233-1354) as it is driven by
+ * CauchyCPDFGridDispatcher1D (cpdf_ndim.hpp:2017-2139; pycauchy_get_marginal_1D_pointwise_cpdf, pycauchy.hpp:890-931):
+ * the first point is evaluated term by term, the others from the per-term cache, every sum in the reference's term order.
+ * `bar_nu` [d] is the direction the reference draws with rand() for hyperplanes orthogonal to the marginal axis
+ * (cpdf_ndim.hpp:385-389).
+ *   mce_cpdf_grid_count     number of grid points of reset_grid(low, high, res)            (cpdf_ndim.hpp:2055-2072)
+ *   mce_marginal_1d_points  ys[k] = f(xs[k]); returns n, 0 when no tables exist (last step of the window), < 0 on error
+ *   mce_marginal_1d_grid    fills xy[n][2] = (x, f(x)) like CauchyPoint2D points[]; returns n (<= n_cap) or as above
+ *   mce_cpdf_last_ms        device time (CUDA events) of the last evaluation */
+int mce_cpdf_grid_count(double grid_low, double grid_high, double grid_res);
+int mce_marginal_1d_points(mce_handle* h, int marg_idx, const double* bar_nu, int n, const double* xs, double* ys);
+int mce_marginal_1d_grid(mce_handle* h, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res,
+                         double* xy, int n_cap);
+double mce_cpdf_last_ms(mce_handle* h);
+
 /* Statistics of the last step: device milliseconds per phase and algorithmic byte counts (bench.py roofline). */
 typedef struct mce_step_stats {
   double ms_total, ms_tp, ms_mu, ms_moments, ms_regroup, ms_ftr, ms_gtable, ms_compact;

@@ -1081,6 +1081,67 @@ void mceo_shift_b(mceo* e, const double* delta) {         /* est:1365-1383 */
       for (int j = 0; j < e->d; j++) e->terms_dp[m][i].b[j] -= delta[j];
 }
 
+
+/* ---- point-wise 1-D marginal cpdf on a grid -------------------------------------------
+ * Restates PointWiseNDimCauchyCPDF::evaluate_1D_marginal_cpdf (cpdf_ndim.hpp:1233-1354) as it is driven by
+ * CauchyCPDFGridDispatcher1D::evaluate_point_grid (cpdf_ndim.hpp:2074-2139): the first grid point is evaluated term by
+ * term with two G-table lookups and two complex divisions while the per-term cache {a, b, w, s} (cpdf_ndim.hpp:216-222)
+ * is filled; every further point is the cached sum  sum_t (a x + b) / (w^2 + (x - s)^2)  in term order.  The grid itself
+ * is reset_grid (cpdf_ndim.hpp:2055-2072).  Returns the number of grid points, 0 when the estimator holds no tables
+ * (window's last step, SKIP_LAST_STEP) -- xs / ys may be NULL to query the count. */
+int mceo_marginal_1d_grid(const mceo* e, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res,
+                          double* xs, double* ys) {
+  if (e->master_step < 1 || marg_idx < 0 || marg_idx >= e->d || !(grid_high > grid_low) || !(grid_res > 0)) return -1;
+  if (e->master_step == e->num_estimation_steps) return 0;                      /* cpdf_ndim.hpp:2079-2083 */
+  const int n_pts = (int)((grid_high - grid_low + grid_res - 1e-15) / grid_res) + 1;
+  if (!xs || !ys) return n_pts;
+  for (int i = 0; i < n_pts; i++) { double g = grid_low + i * grid_res; if (g > grid_high) g = grid_high; xs[i] = g; }
+  const int d = e->d;
+  const double norm_factor = creal(e->fz);
+  double* cache = (double*)malloc(sizeof(double) * 4 * (size_t)(e->Nt > 0 ? e->Nt : 1));
+  int count = 0;
+  { /* first point: uncached evaluation + cache set-up (cpdf_ndim.hpp:1283-1340) */
+    const double x1 = xs[0];
+    double fx = 0;
+    for (int m = 1; m < e->shape_range; m++) {
+      const int two_to_m_minus1 = 1 << (m - 1), rev_m_mask = (1 << m) - 1;
+      for (int i = 0; i < e->terms_per_shape[m]; i++) {
+        const mceo_term* t = e->terms_dp[m] + i;
+        const double b_c = t->b[marg_idx] - x1;
+        double p_cc = 0; int lhs = 0, rhs = 0;
+        for (int j = 0; j < m; j++) {
+          const double A_cj = t->A[j * d + marg_idx], f = fabs(A_cj);
+          p_cc += t->p[j] * f;
+          if (f > 1e-15) { if (A_cj > 0) lhs |= 1 << j; else rhs |= 1 << j; }
+          else { if (dot_prod(t->A + j * d, bar_nu, d) > 0) lhs |= 1 << j; else rhs |= 1 << j; }
+        }
+        const double complex gl = g_num_binsearch(lhs, two_to_m_minus1, rev_m_mask, t->gtable_p, t->cells_gtable_p);
+        const double complex gr = g_num_binsearch(rhs, two_to_m_minus1, rev_m_mask, t->gtable_p, t->cells_gtable_p);
+        const double complex gv = gl / CMPLX(p_cc, b_c) - gr / CMPLX(-p_cc, b_c);
+        fx += creal(gv);
+        double* c = cache + 4 * (size_t)count++;
+        const double s = t->b[marg_idx], w = p_cc, c_kk = creal(gr), d_kk = cimag(gr);
+        c[0] = d_kk / M_PI; c[1] = (c_kk * w - d_kk * s) / M_PI; c[2] = w; c[3] = s;
+      }
+    }
+    ys[0] = creal((double complex)(fx * (1.0 / (2.0 * M_PI)) / norm_factor));
+  }
+  for (int k = 1; k < n_pts; k++) {   /* cached points (cpdf_ndim.hpp:1266-1281) */
+    const double x1 = xs[k];
+    double fx = 0;
+    for (int i = 0; i < count; i++) {
+      const double* c = cache + 4 * (size_t)i;
+      const double w2 = c[2] * c[2];
+      double x1ms = x1 - c[3];
+      x1ms *= x1ms;
+      fx += (c[0] * x1 + c[1]) / (w2 + x1ms);
+    }
+    ys[k] = fx / norm_factor;
+  }
+  free(cache);
+  return n_pts;
+}
+
 void mceo_reset(mceo* e) {                                 /* est:1247-1300 */
   arena_reset(&e->gen[0]); arena_reset(&e->gen[1]); arena_reset(&e->step_arena); e->cur_gen = 0;
   for (int i = 0; i < e->shape_range; i++) { free(e->terms_dp[i]); e->terms_dp[i] = (mceo_term*)malloc(sizeof(mceo_term) * (i == e->d ? e->d + 1 : 1)); }

@@ -57,6 +57,9 @@ mceo* mceo_create(int d, int cmcc, int pncc, int p, int steps, const double* A0,
 int  mceo_step(mceo* e, double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H,
                double gamma, const double* B, const double* u);
 void mceo_shift_b(mceo* e, const double* delta);   /* b <- b - delta on every term (est:1365-1383) */
+/* point-wise 1-D marginal cpdf on a grid (cpdf_ndim.hpp:1233-1354, 2055-2139); returns the number of grid points */
+int  mceo_marginal_1d_grid(const mceo* e, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res,
+                           double* xs, double* ys);
 void mceo_reset(mceo* e);
 void mceo_destroy(mceo* e);
 

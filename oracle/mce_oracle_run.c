@@ -97,6 +97,7 @@ static void dump_ftr(mceo* e, dump_ctx* c) {
 
 int main(int argc, char** argv) {
   const char* scen = NULL; const char* out = NULL; int full_upto = 0, max_steps = 1 << 30, verbose = 0, time_only = 0, print_info = 0;
+  double cg[3] = {0, 0, 0}; const char* csteps = NULL;   /* --cpdf1d lo hi res step[,step..]: same arrays as oracle/ref_cpdf.cpp */
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--full-upto")) full_upto = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--max-steps")) max_steps = atoi(argv[++i]);
@@ -104,6 +105,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--time-only")) time_only = 1;
     else if (!strcmp(argv[i], "--print-basic-info")) print_info = 1;
     else if (!strcmp(argv[i], "--no-F")) {}
+    else if (!strcmp(argv[i], "--cpdf1d")) { cg[0] = atof(argv[i + 1]); cg[1] = atof(argv[i + 2]); cg[2] = atof(argv[i + 3]); csteps = argv[i + 4]; i += 4; }
     else if (!scen) scen = argv[i];
     else out = argv[i];
   }
@@ -142,6 +144,23 @@ int main(int argc, char** argv) {
     if (verbose || time_only) printf("step %d: after MUC %d, after FTR %d, %.3f ms err=%d\n", k + 1, e->Nt_muc, e->Nt, ms, err);
     if (r->shift_kind == MCE_SHIFT_OWN_MEAN) { double dl[MCE_MAX_D]; for (int i = 0; i < d; i++) dl[i] = creal(e->mean[i]); mceo_shift_b(e, dl); }
     else if (r->shift_kind == MCE_SHIFT_EXPLICIT) mceo_shift_b(e, r->delta);
+    if (csteps && ctx.f) {
+      int want = 0; { char buf[256]; strncpy(buf, csteps, 255); buf[255] = 0; for (char* t = strtok(buf, ","); t; t = strtok(NULL, ",")) want |= atoi(t) == k + 1; }
+      if (want) {
+        double bar_nu[MCE_MAX_D];
+        for (int i = 0; i < d; i++) bar_nu[i] = 0.25 + 1.5 * sc.root_point[i] - (int)(1.5 * sc.root_point[i]);
+        const int np = mceo_marginal_1d_grid(e, 0, bar_nu, cg[0], cg[1], cg[2], NULL, NULL);
+        if (np > 0) {
+          double* xs = malloc(sizeof(double) * np); double* ys = malloc(sizeof(double) * np); double* xy = malloc(sizeof(double) * 2 * np);
+          for (int idx = 0; idx < d; idx++) {
+            mceo_marginal_1d_grid(e, idx, bar_nu, cg[0], cg[1], cg[2], xs, ys);
+            for (int i = 0; i < np; i++) { xy[2 * i] = xs[i]; xy[2 * i + 1] = ys[i]; }
+            sprintf(nm, "s%d/cpdf1d/i%d", k + 1, idx); mced_put2(ctx.f, nm, MCED_F64, np, 2, xy);
+          }
+          free(xs); free(ys); free(xy);
+        }
+      }
+    }
   }
   if (ctx.f) fclose(ctx.f);
   return 0;

@@ -206,3 +206,52 @@ def oracle_dump(scenario_path, out_path, full_upto=0, max_steps=None, use_ref=Fa
         cmd += ["--print-basic-info"]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
     return read_dump(out_path)
+
+
+def cpdf_steps(gold):
+    """Steps for which a golden / oracle cpdf dump holds `s<k>/cpdf1d/i<idx>` arrays."""
+    return sorted({int(n.split("/")[0][1:]) for n in gold if "/cpdf1d/i" in n})
+
+
+def run_cpdf1d(lib, sc, gold, max_step=None):
+    """Replays the scenario and evaluates the point-wise 1-D marginal cpdf of every state after each step the golden dump
+    covers (after the recorded shift, like oracle/ref_cpdf.cpp), on the golden dump's grid with its bar_nu.
+    Returns {name: [n][2]} in the dump layout, through mce_marginal_1d_grid of the C ABI."""
+    lo, hi, res = [float(v) for v in gold["cpdf1d/grid"]]
+    bar_nu = np.ascontiguousarray(gold["cpdf1d/bar_nu"], np.float64)
+    want = [k for k in cpdf_steps(gold) if max_step is None or k <= max_step]
+    s = Session(lib, sc)
+    out = {}
+    try:
+        for k in range(max(want)):
+            r = sc.rec[k]
+            s.step(r)
+            mo = s.moments()
+            if r.shift_kind == SHIFT_EXPLICIT:
+                s.shift_b(r.delta, -1.0)
+            elif r.shift_kind == SHIFT_OWN_MEAN:
+                s.shift_b(np.array(mo.mean[: 2 * sc.d])[0::2], -1.0)
+            if (k + 1) not in want:
+                continue
+            n = lib.mce_cpdf_grid_count(lo, hi, res)
+            for idx in range(sc.d):
+                xy = np.zeros((n, 2))
+                rc = lib.mce_marginal_1d_grid(s.h, idx, _dp(bar_nu), lo, hi, res, _dp(xy), n)
+                if rc != n:
+                    raise RuntimeError("mce_marginal_1d_grid returned %d: %s" % (rc, lib.mce_last_error().decode()))
+                out["s%d/cpdf1d/i%d" % (k + 1, idx)] = xy
+    finally:
+        s.close()
+    return out
+
+
+def oracle_cpdf1d(scenario_path, out_path, lo, hi, res, steps, use_ref=False):
+    """1-D marginal cpdf grids from the C oracle (or the compiled reference, oracle/_ref/ref_cpdf_cpu1)."""
+    st = ",".join(str(k) for k in steps)
+    if use_ref:
+        cmd = [os.path.join(ROOT, "oracle", "_ref", "ref_cpdf_cpu1"), scenario_path, out_path, repr(lo), repr(hi), repr(res), st]
+    else:
+        cmd = [os.path.join(ROOT, "oracle", "_build", "mce_oracle_run"), scenario_path, out_path, "--max-steps", str(max(steps)),
+               "--cpdf1d", repr(lo), repr(hi), repr(res), st]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return {n: v for n, v in read_dump(out_path).items() if "cpdf1d" in n}

@@ -1,0 +1,72 @@
+"""GPU parity of the point-wise 1-D marginal cpdf (mce_kern_cpdf.h) through the C ABI: bit-identical to the grids of the
+UNMODIFIED reference (tests/golden/*.cpdf.mced, produced by oracle/ref_cpdf.cpp) after small and large steps of five
+scenarios, including 102 897 terms x 7 states of the 7-state LEO GPS window, and to the plain-C oracle run live on a
+different grid."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from harness import ROOT, cpdf_steps, load_product, oracle_cpdf1d, run_cpdf1d
+from mceio import read_dump, read_scenario
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _same(a, b, n):
+    assert a.shape == b.shape, n
+    assert np.array_equal(a.view(np.uint64), np.ascontiguousarray(b).view(np.uint64)), "%s: max abs diff %.3e" % (n, np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7"])
+def test_cpdf1d_matches_reference_golden(name):
+    gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
+    got = run_cpdf1d(load_product(), read_scenario(os.path.join(GOLD, name + ".mces")), gold)
+    names = [n for n in gold if "/cpdf1d/i" in n]
+    assert len(names) == len(cpdf_steps(gold)) * int(gold["header"][0])
+    for n in names:
+        _same(gold[n], got[n], n)
+        y = gold[n][:, 1]
+        assert np.all(np.isfinite(y))
+
+
+def test_cpdf1d_matches_oracle_on_another_grid(tmp_path):
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    scen = os.path.join(GOLD, "lti3.mces")
+    lo, hi, res, steps = -1.3, 0.9, 0.003, [4, 9]
+    ref = oracle_cpdf1d(scen, str(tmp_path / "o.mced"), lo, hi, res, steps)
+    gold = dict(ref)
+    sc = read_scenario(scen)
+    gold["cpdf1d/grid"] = np.array([lo, hi, res])
+    gold["cpdf1d/bar_nu"] = np.array([0.25 + 1.5 * v - int(1.5 * v) for v in sc.root_point[: sc.d]])
+    got = run_cpdf1d(load_product(), sc, gold)
+    for n in [k for k in ref if "/cpdf1d/i" in k]:
+        _same(ref[n], got[n], n)
+    # the marginal integrates to ~1 over a window that holds the mass (sanity of the normalisation)
+    y = got["s9/cpdf1d/i0"]
+    assert 0.5 < y[:, 1].sum() * res <= 1.0 + 1e-9
+
+
+def test_python_mirror_matches_capi(tmp_path):
+    """cauchyfriendly_b200.CauchyEstimator.get_marginal_1D_pointwise_cpdf (cauchy_estimator.py:1003) returns the same grid
+    and writes the reference's log files (cpdf_ndim.hpp:2141-2202)."""
+    from cauchyfriendly_b200 import CauchyEstimator
+    sc = read_scenario(os.path.join(GOLD, "lti3.mces"))
+    gold = read_dump(os.path.join(GOLD, "lti3.cpdf.mced"))
+    lo, hi, res = [float(v) for v in gold["cpdf1d/grid"]]
+    est = CauchyEstimator(sc.A0, sc.p0, sc.b0, sc.steps, sc.d, sc.cmcc, sc.pncc, sc.p, root_point=sc.root_point, b_pert=sc.b_pert,
+                          tr_search_idxs_ordering=sc.tr_order)
+    est.bar_nu = gold["cpdf1d/bar_nu"]
+    assert est.get_marginal_1D_pointwise_cpdf(0, lo, hi, res) == (None, None)
+    for k in range(5):
+        r = sc.rec[k]
+        est.step(r.msmt, r.Phi, r.Gamma, r.beta, r.H, r.gamma)
+    X, Y = est.get_marginal_1D_pointwise_cpdf(1, lo, hi, res, log_dir=str(tmp_path / "log"))
+    _same(gold["s5/cpdf1d/i1"], np.stack([X, Y], 1), "python mirror")
+    raw = np.fromfile(str(tmp_path / "log" / "cpdf_1_1.bin")).reshape(-1, 2)
+    _same(gold["s5/cpdf1d/i1"], raw, "log file")
+    assert open(str(tmp_path / "log" / "grid_elems_1.txt")).read().split() == [str(len(X))]
+    assert est.cpdf_last_ms() > 0
+    est.shutdown()
