@@ -142,6 +142,11 @@ int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
   out->ftr_rounds_max = s.ftr_rounds_max; out->diag_unmodelled_alias = s.diag_alias; out->diag_hash_overflow = s.diag_hash;
   return 0;
 }
+int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, unsigned long long* out) {
+  if (!h || !out || n < 1) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
+  try { return h->e->div_selftest(n, seed, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
 int mce_debug_capture(mce_handle* h, int enable) { if (!h) return MCE_ERR_BAD_ARG; h->e->capture = enable != 0; return 0; }
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd, int* meta, uint8_t* cmap, int8_t* csmap, int* F) {
   if (!h || !n_terms) return MCE_ERR_BAD_ARG;

@@ -855,6 +855,16 @@ class Engine {
     return n;
   }
 
+
+  // device self-test of div_nobranch (mce_math.h): out[0] = flagged-ok pairs that differ from a / b, out[1] = ok pairs
+  int div_selftest(long long n, unsigned long long seed, unsigned long long* out) {
+    unsigned long long* cnt = (unsigned long long*)cpOut.ensure(sizeof(unsigned long long) * 2);
+    be.memset(cnt, 0, sizeof(unsigned long long) * 2);
+    be.launch(KDivSelfTest{seed, n, cnt}, 148 * 8, 128, 0);
+    be.d2h(out, cnt, sizeof(unsigned long long) * 2);
+    return 0;
+  }
+
   // Host copy of the parents of shape m (canonical order).
   int export_shape(int m, int* n_terms, long long* n_cells_total, double* A, double* pp, double* b, int* cells, uint32_t* keys, double* G) {
     GenStore& g = gen[cur];

@@ -77,6 +77,7 @@ MCE_HD double cpdf1d_term(const Cpdf1dTerm& t, double x1) {
 }
 
 struct KCpdf1dGrid {
+  static constexpr int kMaxThreads = 64, kMinBlocks = 1;     // one or two warps per CTA: registers are not the limit here
   int n_terms, n_pts; const double* xs; const double* val0; const Cpdf1dTerm* cache; double* out;   // out[k] = unnormalised sum of point k
   static MCE_HD size_t smem_bytes() { return sizeof(Cpdf1dTerm) * CPDF_TILE + sizeof(double) * CPDF_TILE; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
@@ -100,11 +101,21 @@ struct KCpdf1dGrid {
           const double x1 = xs[k];
           int i = 0;
           for (; i + CPDF_UNROLL <= nt; i += CPDF_UNROLL) {
-            double q[CPDF_UNROLL];
+            double q[CPDF_UNROLL]; bool all_ok = true;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-            for (int u = 0; u < CPDF_UNROLL; u++) q[u] = cpdf1d_term(st[i + u], x1);
+            for (int u = 0; u < CPDF_UNROLL; u++) {
+              const Cpdf1dTerm t = st[i + u];
+              double x1ms = x1 - t.s;
+              x1ms *= x1ms;
+              bool ok;
+              q[u] = div_nobranch(t.a * x1 + t.b, t.w2 + x1ms, &ok);      // == cpdf1d_term when ok
+              all_ok = all_ok && ok;
+            }
+            if (!all_ok) {                      // rare (zero / tiny numerators): redo the batch with the plain division
+              for (int u = 0; u < CPDF_UNROLL; u++) q[u] = cpdf1d_term(st[i + u], x1);
+            }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -115,6 +126,39 @@ struct KCpdf1dGrid {
         out[k] = fx;
       });
     }
+  }
+};
+
+
+// Device self-test of div_nobranch (mce_math.h): pseudo-random operand pairs over the whole exponent range plus mantissa
+// edge patterns; counts the pairs whose flag is set but whose value differs from `a / b`, and the pairs that were flagged.
+struct KDivSelfTest {
+  unsigned long long seed; long long n; unsigned long long* counters;   // [0] mismatches, [1] ok pairs
+  static MCE_HD unsigned long long mix(unsigned long long k) {
+    unsigned long long x = (k + 1) * 0x9E3779B97F4A7C15ULL; x ^= x >> 29; x *= 0xBF58476D1CE4E5B9ULL; x ^= x >> 32; x *= 0x94D049BB133111EBULL; x ^= x >> 29; return x;
+  }
+  static MCE_HD double make(unsigned long long bits, int mode) {
+    // mode 0: any exponent; 1: exponents near 1; 2: mantissa of all ones / single bits
+    unsigned long long man = bits & 0xFFFFFFFFFFFFFULL, sign = (bits >> 63) << 63; long long ex = (long long)((bits >> 52) & 0x7FF);
+    if (mode == 1) ex = 1023 + (ex % 41) - 20;
+    if (mode == 2) { const int k = (int)(man % 53); man = (bits & (1ULL << 60)) ? (0xFFFFFFFFFFFFFULL >> k) : ((1ULL << k) >> 1); ex = 1023 + (ex % 201) - 100; }
+    union { unsigned long long u; double d; } v; v.u = sign | ((unsigned long long)ex << 52) | man; return v.d;
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    c.par([&](int tid) {
+      unsigned long long bad = 0, okc = 0;
+      const long long stride = (long long)c.nthreads() * c.nblocks();
+      for (long long i = (long long)c.block() * c.nthreads() + tid; i < n; i += stride) {
+        const unsigned long long ra = mix(seed + 2 * (unsigned long long)i), rb = mix(seed + 2 * (unsigned long long)i + 1);
+        const int mode = (int)(i % 3);
+        const double a = make(ra, mode), b = make(rb, mode);
+        bool ok; const double q = div_nobranch(a, b, &ok), ref = a / b;
+        union { double d; unsigned long long u; } x, y; x.d = q; y.d = ref;
+        if (ok) { okc++; if (x.u != y.u) bad++; }
+      }
+      if (bad) c.atomic_add_u64(counters, bad);
+      if (okc) c.atomic_add_u64(counters + 1, okc);
+    });
   }
 };
 

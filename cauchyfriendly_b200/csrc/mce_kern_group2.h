@@ -251,6 +251,9 @@ MCE_HD bool is_skip_addend(const cplx& x) {
   return v.u == 0x7ff8dead0000beefULL;
 }
 
+// libgcc's full complex division, twice, out of line (the rare path of eval_cell)
+static MCE_HDN MCE_NOINLINE void g2_cdiv_pair_full(cplx u1, cplx v1, cplx u2, cplx v2, cplx* r1, cplx* r2) { *r1 = cdiv(u1, v1); *r2 = cdiv(u2, v2); }
+
 template <int MODE>
 struct KGTable2T {
   static constexpr int kMaxThreads = 128, kMinBlocks = 8;   // 64 registers: 8 CTAs (32 warps) per SM
@@ -351,7 +354,10 @@ struct KGTable2T {
     const cplx* pG = gen_G(prev, e->gidp, phc);
     const cplx gp = lookup(e, pG, bmP, pfP, lp ^ (int)e->enc_lhp);
     const cplx gm = lookup(e, pG, bmP, pfP, lm ^ (int)e->enc_lhp);
-    cplx g = csub(cdiv(gp, make_cplx(ygi + e->d, e->c)), cdiv(gm, make_cplx(ygi - e->d, e->c)));
+    const cplx vp = make_cplx(ygi + e->d, e->c), vm = make_cplx(ygi - e->d, e->c);
+    cplx rp, rm;
+    if (!cdiv2_fast(gp, vp, gm, vm, &rp, &rm)) g2_cdiv_pair_full(gp, vp, gm, vm, &rp, &rm);   // rare: guards, absent cells (0 numerators)
+    cplx g = csub(rp, rm);
     g = cscale(g, sp.gscale);
     if (!*(volatile int*)flag) {           // |G| only matters until one cell is found non-negligible (flat:242-247)
       // max(|re|,|im|) <= |G| <= |re|+|im| and rounding is monotone, so the two cheap bounds decide almost every cell

@@ -145,6 +145,9 @@ int mce_shard_init(mce_handle* h, int rank, int world, const void* id128);
 int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn fn, void* ctx);
 
 /* Test hook: keep a host copy of the post-MUC term list and FTR flag arrays of the last step. */
+/* Device self-test of the branch-free IEEE division used by the cpdf grid kernel (csrc/mce_math.h: div_nobranch) on n
+ * pseudo-random operand pairs: out[0] = pairs flagged valid whose value differs from a / b (must be 0), out[1] = valid pairs. */
+int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, unsigned long long* out /*[2]*/);
 int mce_debug_capture(mce_handle* h, int enable);
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,
                         int* meta /*[n][8]*/, uint8_t* cmap /*[n][32]*/, int8_t* csmap /*[n][32]*/, int* F /*[n]*/);

@@ -70,3 +70,22 @@ def test_python_mirror_matches_capi(tmp_path):
     assert open(str(tmp_path / "log" / "grid_elems_1.txt")).read().split() == [str(len(X))]
     assert est.cpdf_last_ms() > 0
     est.shutdown()
+
+
+def test_branch_free_division_equals_ieee_division():
+    """div_nobranch (mce_math.h) replays nvcc's division sequence without its branch; whenever it flags its result valid the
+    value must be the IEEE quotient.  3 x 10^9 operand pairs: all exponents, exponents near 1, mantissa edge patterns."""
+    import ctypes as ct
+    from harness import Session
+    lib = load_product()
+    s = Session(lib, read_scenario(os.path.join(GOLD, "lti3.mces")))
+    try:
+        tot_ok = 0
+        for seed in (1, 2, 3):
+            out = (ct.c_ulonglong * 2)()
+            assert lib.mce_debug_div_selftest(s.h, 1000 * 1000 * 1000, seed * 7919, out) == 0
+            assert out[0] == 0, "%d of %d flagged-valid quotients differ from a / b" % (out[0], out[1])
+            tot_ok += out[1]
+        assert tot_ok > 2 * 10**9          # the flag is set for the bulk of the pairs (the test is not vacuous)
+    finally:
+        s.close()
