@@ -334,7 +334,10 @@ struct KGTable2T {
     // ygi = sum over non-H-orthogonal rows of q_k s_k, in row order (flat:137-154).  sm->q holds +0.0 for the H-orthogonal
     // rows (adding +0.0 never changes a running sum that started at +0.0), so the loop is branch-free; s_k flips the sign bit.
     double ygi = 0;
-    MCE_NOUNROLL for (int k = 0; k < m; k++) ygi += flip_sign(q[k], (key >> k) & 1u);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 16; k++) { if (k >= m) break; ygi += flip_sign(q[k], (key >> k) & 1u); }   // this kernel serves max_shape <= 16
     int lp, lm;
     const int phc_mask = (1 << phc) - 1;
     if (!e->is_child) { lp = (int)(key & (unsigned)phc_mask); lm = lp; }

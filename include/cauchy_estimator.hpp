@@ -92,6 +92,7 @@ struct CauchyEstimator
         mce_options opts; mce_default_options(&opts);
         for(int i = 0; i < 12; i++) opts.tr_search_order[i] = TR_SEARCH_IDXS_ORDERING[i];
         opts.print_basic_info = _print_basic_info ? 1 : 0;   // quirk A.9(iii): with prints on, moments are recomputed after FTR
+        set_function_pointers();
         handle = mce_create(d, cmcc, pncc, p, _steps, A0_init, p0_init, b0_init, root_point, b_pert, &opts);
         free(b_pert);
         if(handle == NULL)
@@ -151,7 +152,17 @@ struct CauchyEstimator
     }
 
     void set_win_num(int _win_num) { win_num = _win_num; }
-    void set_function_pointers() {}      // est:192: the device build has one storage mode (sorted keys, half storage)
+    // est:192-222.  The device path has one storage mode (sorted keys, half storage); the reference's side consumers
+    // (cpdf_ndim.hpp, cauchy_prediction.hpp) still call the global function pointers of cauchy_types.hpp:69-78 when they
+    // read the host mirror, whose tables are sorted KeyCValue arrays -- i.e. the BINSEARCH accessors.
+    void set_function_pointers()
+    {
+        lookup_g_numerator = (LOOKUP_G_NUMERATOR_TYPE) g_num_binsearch;
+        gtable_insert = (GTABLE_INSERT_TYPE) g_insert_binsearch;
+        gtable_add = (GTABLE_ADD_TYPE) gs_add_binsearch;
+        gtable_p_find = (GTABLE_P_FIND_TYPE) gp_find_binsearch;
+        gtable_p_get_keys = (GTABLE_P_GET_KEYS_TYPE) gtable_p_get_keys_binsearch;
+    }
 
     void pull_state()
     {
@@ -206,6 +217,7 @@ struct CauchyEstimator
             printf(RED "[Window %d:] ERROR MASTER STEP. master_step == num_estimation_steps (max measurements=%d)!\nCannot continue stepping until this estimator has been reset!" NC "\n", win_num, master_step);
             exit(1);
         }
+        set_function_pointers();        // est:1213
         CPUTimer tmr; tmr.tic();
         mce_set_master_step(handle, master_step);      // callers may have written the field (cauchy_windows.hpp:538,659)
         int rc = mce_step(handle, msmt, Phi, Gamma, beta, H, gamma, B, u);

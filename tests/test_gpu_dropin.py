@@ -69,3 +69,16 @@ def test_reference_window_manager_runs_on_the_gpu_path(tmp_path):
     assert m, out[-2000:]
     assert int(m.group(1)) == 201 and float(m.group(3)) > 0
     assert "All children have exited" in out
+
+
+def test_device_cpdf_dispatcher_equals_the_reference_cpu_cpdf(tmp_path):
+    """tests/dropin/cpdf1d_dropin.cpp: the reference's own CauchyCPDFGridDispatcher1D (cpdf_ndim.hpp, compiled unchanged) reads
+    the host mirror of the device term list and must produce the same 401-point grids, bit for bit, as the device
+    dispatcher of include/cpdf_b200.hpp, for every state after each of 7 steps of the 3-state example."""
+    exe = os.path.join(ROOT, "build", "dropin", "cpdf1d_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    out = _run(exe, str(tmp_path))
+    assert "cpdf1d drop-in OK" in out, out[-2000:]
+    m = re.search(r"compared (\d+) grid values, (\d+) differ", out)
+    assert m and int(m.group(1)) == 7 * 3 * 401 and int(m.group(2)) == 0

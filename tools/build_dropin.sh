@@ -17,3 +17,9 @@ for t in cauchy_estimator leo_satellite_7state_gps window_manager; do
       -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
   echo "built build/dropin/$t"
 done
+# the device cpdf dispatcher checked against the reference's own CPU cpdf code over the host mirror (tests/dropin/cpdf1d_dropin.cpp)
+mkdir -p "$OV/tests"
+ln -sf "$ROOT/tests/dropin/cpdf1d_dropin.cpp" "$OV/tests/cpdf1d_dropin.cpp"
+g++ -O3 -w -ffp-contract=off -I"$OV/include" -I"$ROOT/include" "$OV/tests/cpdf1d_dropin.cpp" -o "$ROOT/build/dropin/cpdf1d_dropin" \
+    -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
+echo "built build/dropin/cpdf1d_dropin"
