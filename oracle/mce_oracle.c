@@ -1142,6 +1142,147 @@ int mceo_marginal_1d_grid(const mceo* e, int marg_idx, const double* bar_nu, dou
   return n_pts;
 }
 
+/* ---- point-wise 2-D marginal cpdf on a grid -------------------------------------------
+ * Restates PointWiseNDimCauchyCPDF::evaluate_2D_marginal_cpdf (cpdf_ndim.hpp:1356-1455) with its helpers
+ * marg2d_extract_2D_HPA (:31-40), marg2d_remove_zeros_and_coalign (:42-139), marg2d_get_cell_wall_angles (:142-170),
+ * marg2d_get_SVs (:176-201), marg2d_eval_term_for_cpdf (:1474-1658) and marg2d_cached_eval_term_for_cpdf (:1660-1747),
+ * as driven by CauchyCPDFGridDispatcher2D (reset_grid :1816-1848, evaluate_point_grid :1850-1919).  The per-term cache
+ * (angles' sines / cosines, gamma reals, G values) is built once; every grid point is the cached sum in term order (the
+ * uncached evaluation of the first point performs the same operations on the same values).  Uses libm atan2/sin/cos like
+ * the reference.  out = [ny*nx][3] (x, y, z), y-major like the dispatcher.  Returns the number of points. */
+#define MCEO_ZERO_HP 32
+#define MCEO_COALIGN_MU_EPS 1e-8
+#define MCEO_MU_EPS 1e-10
+#define MCEO_INTEGRAL_GAMMA_EPS 1e-8
+static int cmp_dless(const void* a, const void* b) { double x = *(const double*)a, y = *(const double*)b; return x > y ? 1 : (x < y ? -1 : 0); }
+typedef struct { int m; double b[2]; double *sin_t, *cos_t, *g1, *g2; double complex* gv; } mceo_c2d;
+
+static double c2d_eval(const mceo_c2d* c, double x1, double x2) {       /* cpdf_ndim.hpp:1660-1747 */
+  const double gam1_imag = c->b[0] - x1, gam2_imag = c->b[1] - x2;
+  const int check_gamma1 = fabs(gam1_imag) < MCEO_INTEGRAL_GAMMA_EPS;
+  double term_integral = 0;
+  for (int i = 0; i < c->m; i++) {
+    const double sin_t1 = c->sin_t[i], cos_t1 = c->cos_t[i], sin_t2 = c->sin_t[i + 1], cos_t2 = c->cos_t[i + 1];
+    double complex gamma1 = CMPLX(c->g1[i], gam1_imag), gamma2 = CMPLX(c->g2[i], gam2_imag), lo, hi, cell;
+    int fast = 1;
+    if (check_gamma1 && fabs(c->g1[i]) < MCEO_INTEGRAL_GAMMA_EPS) {
+      fast = 0;
+      if (fabs(c->g2[i]) < MCEO_INTEGRAL_GAMMA_EPS && fabs(gam2_imag) < MCEO_INTEGRAL_GAMMA_EPS) { fprintf(stderr, "marg2d: singular gamma\n"); exit(1); }
+    }
+    if (fast) {
+      gamma2 *= gamma1; gamma1 *= gamma1;
+      lo = sin_t1 / (gamma1 * cos_t1 + gamma2 * sin_t1);
+      hi = sin_t2 / (gamma1 * cos_t2 + gamma2 * sin_t2);
+      cell = hi - lo;
+      cell *= c->gv[i];
+      term_integral += creal(cell);
+    } else {
+      lo = (gamma1 * sin_t1 - gamma2 * cos_t1) / (gamma1 * cos_t1 + gamma2 * sin_t1);
+      hi = (gamma1 * sin_t2 - gamma2 * cos_t2) / (gamma1 * cos_t2 + gamma2 * sin_t2);
+      cell = hi - lo;
+      gamma1 *= gamma1; gamma2 *= gamma2;
+      cell *= c->gv[i] / (gamma1 + gamma2);
+      term_integral += creal(cell);
+    }
+  }
+  return term_integral;
+}
+
+int mceo_marginal_2d_grid(const mceo* e, int idx1, int idx2, const double* bar_nu, const double* gx /*lo,hi,res*/, const double* gy,
+                          double* out) {
+  if (e->master_step < 1 || idx1 < 0 || idx1 >= idx2 || idx2 >= e->d || !(gx[1] > gx[0]) || !(gy[1] > gy[0]) || !(gx[2] > 0) || !(gy[2] > 0)) return -1;
+  if (e->master_step == e->num_estimation_steps) return 0;
+  const int nx = (int)((gx[1] - gx[0] + gx[2] - 1e-15) / gx[2]) + 1, ny = (int)((gy[1] - gy[0] + gy[2] - 1e-15) / gy[2]) + 1;
+  if (!out) return nx * ny;
+  const int d = e->d, MS = e->shape_range;
+  mceo_c2d* cache = (mceo_c2d*)malloc(sizeof(mceo_c2d) * (size_t)(e->Nt > 0 ? e->Nt : 1));
+  int count = 0;
+  double* wA = malloc(sizeof(double) * 2 * MS); double* wA2 = malloc(sizeof(double) * 2 * MS); double* wp = malloc(sizeof(double) * MS);
+  double* wp2 = malloc(sizeof(double) * MS); int* c_map = malloc(sizeof(int) * MS); int* cs_map = malloc(sizeof(int) * MS);
+  int* F = malloc(sizeof(int) * MS); int* F_idxs = malloc(sizeof(int) * MS);
+  double* thetas = malloc(sizeof(double) * 2 * MS); double* SVs = malloc(sizeof(double) * MS * MS); double* As = malloc(sizeof(double) * 2 * MS);
+  for (int m = 1; m < e->shape_range; m++) {
+    for (int ti = 0; ti < e->terms_per_shape[m]; ti++) {
+      const mceo_term* t = e->terms_dp[m] + ti;
+      double b2[2];
+      memcpy(wp, t->p, sizeof(double) * m);
+      for (int i = 0; i < m; i++) { wA[2 * i] = t->A[i * d + idx1]; wA[2 * i + 1] = t->A[i * d + idx2]; }     /* :31-40 */
+      b2[0] = t->b[idx1]; b2[1] = t->b[idx2];
+      /* marg2d_remove_zeros_and_coalign, :42-139 */
+      for (int i = 0; i < m; i++) F[i] = 1;
+      for (int i = 0; i < m; i++) {
+        double* ai = wA + 2 * i; const double f0 = fabs(ai[0]), f1 = fabs(ai[1]);
+        if (f0 < MCEO_MU_EPS && f1 < MCEO_MU_EPS) { c_map[i] = MCEO_ZERO_HP; cs_map[i] = MCEO_ZERO_HP; F_idxs[i] = MCEO_ZERO_HP; F[i] = 0; continue; }
+        const double sum_a = f0 + f1; ai[0] /= sum_a; ai[1] /= sum_a; wp[i] *= sum_a;
+      }
+      int mn = 0;
+      for (int i = 0; i < m; i++) {
+        if (!F[i]) continue;
+        c_map[i] = mn; cs_map[i] = 1; F_idxs[i] = i; wp2[mn] = wp[i];
+        const double* ai = wA + 2 * i;
+        for (int j = i + 1; j < m; j++) {
+          if (!F[j]) continue;
+          const double* aj = wA + 2 * j;
+          if (fabs(ai[0] - aj[0]) < MCEO_COALIGN_MU_EPS && fabs(ai[1] - aj[1]) < MCEO_COALIGN_MU_EPS) { c_map[j] = mn; cs_map[j] = 1; F[j] = 0; F_idxs[j] = i; wp2[mn] += wp[j]; continue; }
+          if (fabs(ai[0] + aj[0]) < MCEO_COALIGN_MU_EPS && fabs(ai[1] + aj[1]) < MCEO_COALIGN_MU_EPS) { c_map[j] = mn; cs_map[j] = -1; F[j] = 0; F_idxs[j] = i; wp2[mn] += wp[j]; continue; }
+        }
+        mn++;
+      }
+      if (mn < m) { mn = 0; for (int i = 0; i < m; i++) if (F_idxs[i] == i) { wA2[2 * mn] = wA[2 * i]; wA2[2 * mn + 1] = wA[2 * i + 1]; mn++; } }
+      else memcpy(wA2, wA, sizeof(double) * 2 * m);
+      const int use_maps = mn != m;
+      /* marg2d_get_cell_wall_angles, :142-170 */
+      for (int i = 0, k = 0; i < mn; i++) {
+        const double* a = wA2 + 2 * i; double pt[2];
+        if (fabs(a[0]) < fabs(a[1])) { pt[0] = 1; pt[1] = -a[0] / a[1]; } else { pt[0] = -a[1] / a[0]; pt[1] = 1; }
+        double t1 = atan2(pt[1], pt[0]);
+        if (t1 < 0) t1 += M_PI;
+        thetas[k++] = t1; thetas[k++] = t1 + M_PI;
+      }
+      qsort(thetas, 2 * mn, sizeof(double), cmp_dless);
+      /* marg2d_get_SVs (no flip), :176-201 */
+      for (int i = 0; i < mn; i++) {
+        const double tt = (thetas[i + 1] + thetas[i]) / 2.0, p0 = cos(tt), p1 = sin(tt);
+        for (int j = 0; j < mn; j++) { const double sum = wA2[2 * j] * p0 + wA2[2 * j + 1] * p1; SVs[i * mn + j] = sum > 0 ? 1 : -1; }
+      }
+      for (int i = 0; i < mn; i++) { As[2 * i] = wA2[2 * i] * wp2[i]; As[2 * i + 1] = wA2[2 * i + 1] * wp2[i]; }
+      mceo_c2d* c = cache + count++;
+      c->m = mn; c->b[0] = b2[0]; c->b[1] = b2[1];
+      c->sin_t = malloc(sizeof(double) * (mn + 1)); c->cos_t = malloc(sizeof(double) * (mn + 1));
+      c->g1 = malloc(sizeof(double) * (mn + 1)); c->g2 = malloc(sizeof(double) * (mn + 1)); c->gv = malloc(sizeof(double complex) * (mn + 1));
+      const int two_to_mp_minus1 = 1 << (m - 1), rev_mp_mask = (1 << m) - 1;
+      for (int i = 0; i < mn; i++) {                                                              /* :1548-1600 */
+        const double* SV = SVs + i * mn; int enc = 0;
+        if (!use_maps) { for (int j = 0; j < mn; j++) if (SV[j] < 0) enc |= 1 << j; }
+        else for (int j = 0; j < m; j++) {
+          if (c_map[j] == MCEO_ZERO_HP) { if (dot_prod(t->A + j * d, bar_nu, d) < 0) enc |= 1 << j; }
+          else { const int sgn = (int)(SV[c_map[j]] * cs_map[j]); if (sgn < 0) enc |= 1 << j; }
+        }
+        c->gv[i] = g_num_binsearch(enc, two_to_mp_minus1, rev_mp_mask, t->gtable_p, t->cells_gtable_p);
+        double g1 = 0, g2 = 0;
+        for (int j = 0; j < mn; j++) { g1 -= As[2 * j] * SV[j]; g2 -= As[2 * j + 1] * SV[j]; }
+        c->g1[i] = g1; c->g2[i] = g2;
+        c->sin_t[i] = sin(thetas[i]); c->cos_t[i] = cos(thetas[i]);
+      }
+      c->sin_t[mn] = sin(thetas[mn]); c->cos_t[mn] = cos(thetas[mn]);
+    }
+  }
+  const double norm_factor = creal(e->fz), R2PI = 1.0 / (2.0 * M_PI);
+  for (int i = 0; i < ny; i++) {
+    double y = gy[0] + i * gy[2]; if (y > gy[1]) y = gy[1];
+    for (int j = 0; j < nx; j++) {
+      double x = gx[0] + j * gx[2]; if (x > gx[1]) x = gx[1];
+      double fx = 0;
+      for (int k = 0; k < count; k++) fx += c2d_eval(cache + k, x, y);
+      double* o = out + 3 * ((size_t)i * nx + j);
+      o[0] = x; o[1] = y; o[2] = 2 * fx * R2PI * R2PI / norm_factor;                         /* :1446 */
+    }
+  }
+  for (int k = 0; k < count; k++) { free(cache[k].sin_t); free(cache[k].cos_t); free(cache[k].g1); free(cache[k].g2); free(cache[k].gv); }
+  free(cache); free(wA); free(wA2); free(wp); free(wp2); free(c_map); free(cs_map); free(F); free(F_idxs); free(thetas); free(SVs); free(As);
+  return nx * ny;
+}
+
 void mceo_reset(mceo* e) {                                 /* est:1247-1300 */
   arena_reset(&e->gen[0]); arena_reset(&e->gen[1]); arena_reset(&e->step_arena); e->cur_gen = 0;
   for (int i = 0; i < e->shape_range; i++) { free(e->terms_dp[i]); e->terms_dp[i] = (mceo_term*)malloc(sizeof(mceo_term) * (i == e->d ? e->d + 1 : 1)); }

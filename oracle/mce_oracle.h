@@ -60,6 +60,8 @@ void mceo_shift_b(mceo* e, const double* delta);   /* b <- b - delta on every te
 /* point-wise 1-D marginal cpdf on a grid (cpdf_ndim.hpp:1233-1354, 2055-2139); returns the number of grid points */
 int  mceo_marginal_1d_grid(const mceo* e, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res,
                            double* xs, double* ys);
+/* point-wise 2-D marginal cpdf on a grid (cpdf_ndim.hpp:1356-1455, 1474-1747, 1816-1919); out[ny*nx][3] = (x, y, z) */
+int  mceo_marginal_2d_grid(const mceo* e, int idx1, int idx2, const double* bar_nu, const double* gx, const double* gy, double* out);
 void mceo_reset(mceo* e);
 void mceo_destroy(mceo* e);
 

@@ -97,7 +97,7 @@ static void dump_ftr(mceo* e, dump_ctx* c) {
 
 int main(int argc, char** argv) {
   const char* scen = NULL; const char* out = NULL; int full_upto = 0, max_steps = 1 << 30, verbose = 0, time_only = 0, print_info = 0;
-  double cg[3] = {0, 0, 0}; const char* csteps = NULL;   /* --cpdf1d lo hi res step[,step..]: same arrays as oracle/ref_cpdf.cpp */
+  double cg[3] = {0, 0, 0}; const char* csteps = NULL; double cg2[6] = {0, 0, 0, 0, 0, 0}; int with_2d = 0;   /* --cpdf2d xlo xhi xres ylo yhi yres */   /* --cpdf1d lo hi res step[,step..]: same arrays as oracle/ref_cpdf.cpp */
   for (int i = 1; i < argc; i++) {
     if (!strcmp(argv[i], "--full-upto")) full_upto = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--max-steps")) max_steps = atoi(argv[++i]);
@@ -105,6 +105,7 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--time-only")) time_only = 1;
     else if (!strcmp(argv[i], "--print-basic-info")) print_info = 1;
     else if (!strcmp(argv[i], "--no-F")) {}
+    else if (!strcmp(argv[i], "--cpdf2d")) { for (int k = 0; k < 6; k++) cg2[k] = atof(argv[i + 1 + k]); with_2d = 1; i += 6; }
     else if (!strcmp(argv[i], "--cpdf1d")) { cg[0] = atof(argv[i + 1]); cg[1] = atof(argv[i + 2]); cg[2] = atof(argv[i + 3]); csteps = argv[i + 4]; i += 4; }
     else if (!scen) scen = argv[i];
     else out = argv[i];
@@ -158,6 +159,18 @@ int main(int argc, char** argv) {
             sprintf(nm, "s%d/cpdf1d/i%d", k + 1, idx); mced_put2(ctx.f, nm, MCED_F64, np, 2, xy);
           }
           free(xs); free(ys); free(xy);
+        }
+        if (with_2d) {
+          const int n2 = mceo_marginal_2d_grid(e, 0, 1, bar_nu, cg2, cg2 + 3, NULL);
+          if (n2 > 0) {
+            double* o3 = malloc(sizeof(double) * 3 * n2);
+            for (int a = 0; a < d - 1; a++) {
+              const int i1 = (a < d - 2 || d == 2) ? a : 0, i2 = (a < d - 2 || d == 2) ? a + 1 : d - 1;
+              mceo_marginal_2d_grid(e, i1, i2, bar_nu, cg2, cg2 + 3, o3);
+              sprintf(nm, "s%d/cpdf2d/i%d_%d", k + 1, i1, i2); mced_put2(ctx.f, nm, MCED_F64, n2, 3, o3);
+            }
+            free(o3);
+          }
         }
       }
     }

@@ -22,7 +22,13 @@ int main(int argc, char** argv) {
   const double glo = atof(argv[3]), ghi = atof(argv[4]), gres = atof(argv[5]);
   std::vector<int> steps;
   { char* s = strdup(argv[6]); for (char* t = strtok(s, ","); t; t = strtok(NULL, ",")) steps.push_back(atoi(t)); }
-  const bool timing = argc > 7 && std::string(argv[7]) == "--time";
+  bool timing = false;
+  // --2d xlo xhi xres ylo yhi yres : additionally evaluate the 2-D marginal of every state pair (i, i+1) and (0, d-1)
+  double g2[6] = {0, 0, 0, 0, 0, 0}; bool with_2d = false;
+  for (int i = 7; i < argc; i++) {
+    if (std::string(argv[i]) == "--time") timing = true;
+    else if (std::string(argv[i]) == "--2d" && i + 6 < argc) { for (int k = 0; k < 6; k++) g2[k] = atof(argv[i + 1 + k]); with_2d = true; i += 6; }
+  }
 
   mces_scenario sc;
   mces_read(scen, &sc);
@@ -38,6 +44,7 @@ int main(int argc, char** argv) {
   double bar_nu[MCE_MAX_D];
   for (int i = 0; i < d; i++) { bar_nu[i] = 0.25 + 1.5 * sc.root_point[i] - (int)(1.5 * sc.root_point[i]); cpdf.bar_nu[i] = bar_nu[i]; }
   CauchyCPDFGridDispatcher1D grid(&cpdf, glo, ghi, gres, NULL);
+  CauchyCPDFGridDispatcher2D* grid2 = with_2d ? new CauchyCPDFGridDispatcher2D(&cpdf, g2[0], g2[1], g2[2], g2[3], g2[4], g2[5], NULL) : NULL;
 
   FILE* f = mced_open(out);
   int hdr[6] = {d, sc.cmcc, sc.pncc, sc.p, sc.steps, NUM_CPUS};
@@ -45,6 +52,7 @@ int main(int argc, char** argv) {
   mced_put1(f, "cpdf1d/bar_nu", MCED_F64, d, bar_nu);
   double g3[3] = {glo, ghi, gres};
   mced_put1(f, "cpdf1d/grid", MCED_F64, 3, g3);
+  if (with_2d) mced_put1(f, "cpdf2d/grid", MCED_F64, 6, g2);
 
   int last = 0; for (int s : steps) last = s > last ? s : last;
   for (int k = 0; k < sc.n_records && k < last; k++) {
@@ -70,6 +78,17 @@ int main(int argc, char** argv) {
       if (timing) printf("step %d idx %d: %d terms x %d points in %d ms\n", k + 1, idx, est.Nt, grid.num_grid_points, tmr.cpu_time_used);
       const std::string name = "s" + std::to_string(k + 1) + "/cpdf1d/i" + std::to_string(idx);
       mced_put2(f, name.c_str(), MCED_F64, grid.num_grid_points, 2, (double*)grid.points);
+    }
+    if (with_2d) {
+      for (int a = 0; a < d - 1; a++) {
+        const int i1 = a < d - 2 || d == 2 ? a : 0, i2 = a < d - 2 || d == 2 ? a + 1 : d - 1;     // (0,1), (1,2), ..., and (0, d-1) last
+        CPUTimer tmr; tmr.tic();
+        if (grid2->evaluate_point_grid(i1, i2, 1, false)) continue;
+        tmr.toc(false);
+        if (timing) printf("step %d pair %d,%d: %d terms x %d points in %d ms\n", k + 1, i1, i2, est.Nt, grid2->num_grid_points, tmr.cpu_time_used);
+        const std::string name = "s" + std::to_string(k + 1) + "/cpdf2d/i" + std::to_string(i1) + "_" + std::to_string(i2);
+        mced_put2(f, name.c_str(), MCED_F64, grid2->num_grid_points, 3, (double*)grid2->points);
+      }
     }
   }
   fclose(f);
