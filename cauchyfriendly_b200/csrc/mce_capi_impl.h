@@ -128,6 +128,31 @@ int mce_marginal_1d_grid(mce_handle* h, int marg_idx, const double* bar_nu, doub
   for (int i = 0; i < n; i++) { xy[2 * i] = xs[i]; xy[2 * i + 1] = ys[i]; }
   return n;
 }
+int mce_marginal_2d_points(mce_handle* h, int marg_idx1, int marg_idx2, const double* bar_nu, int n, const double* xs, const double* ys, double* zs) {
+  if (!h || !bar_nu || !xs || !ys || !zs || n < 1) { g_mce_error = "mce_marginal_2d_points: bad argument"; return MCE_ERR_BAD_ARG; }
+  h->e->be.make_current();
+  int rc;
+  try { rc = h->e->marginal_2d_points(marg_idx1, marg_idx2, bar_nu, n, xs, ys, zs); } catch (const std::exception& ex) { g_mce_error = std::string("mce_marginal_2d_points: ") + ex.what(); return MCE_ERR_CUDA; }
+  if (rc < 0) { g_mce_error = "mce_marginal_2d_points: " + h->e->error; return MCE_ERR_BAD_ARG; }
+  return rc;
+}
+int mce_marginal_2d_grid(mce_handle* h, int marg_idx1, int marg_idx2, const double* bar_nu, double xlo, double xhi, double xres, double ylo, double yhi, double yres,
+                         double* xyz, int n_cap, int* nx_out, int* ny_out) {
+  const int nx = mce_cpdf_grid_count(xlo, xhi, xres), ny = mce_cpdf_grid_count(ylo, yhi, yres);
+  if (!h || !xyz || nx < 1 || ny < 1 || (long long)nx * ny > n_cap) { g_mce_error = "mce_marginal_2d_grid: bad grid or capacity"; return MCE_ERR_BAD_ARG; }
+  const int n = nx * ny;
+  std::vector<double> xs(n), ys(n), zs(n);
+  for (int i = 0; i < ny; i++) {                                    // cpdf_ndim.hpp:1830-1847: y-major
+    double gy = ylo + i * yres; if (gy > yhi) gy = yhi;
+    for (int j = 0; j < nx; j++) { double gx = xlo + j * xres; if (gx > xhi) gx = xhi; xs[i * nx + j] = gx; ys[i * nx + j] = gy; }
+  }
+  const int rc = mce_marginal_2d_points(h, marg_idx1, marg_idx2, bar_nu, n, xs.data(), ys.data(), zs.data());
+  if (rc <= 0) return rc;
+  for (int k = 0; k < n; k++) { xyz[3 * k] = xs[k]; xyz[3 * k + 1] = ys[k]; xyz[3 * k + 2] = zs[k]; }
+  if (nx_out) *nx_out = nx;
+  if (ny_out) *ny_out = ny;
+  return n;
+}
 double mce_cpdf_last_ms(mce_handle* h) { return h ? h->e->cpdf_ms : 0.0; }
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
   if (!h || !out) return MCE_ERR_BAD_ARG;

@@ -110,7 +110,7 @@ class Engine {
   } gen[2];
   int cur = 0;
   DevBuf<BE> wsA, wsp, wsb, wsm, wsSgn, wsXor, wsTpB, wsTpBc;
-  DevBuf<BE> cpVal0, cpCache, cpXs, cpOut;   // point-wise marginal cpdf (mce_kern_cpdf.h)
+  DevBuf<BE> cpVal0, cpCache, cpXs, cpOut, cpYs, cpRecs, cpV, cpBad;   // point-wise marginal cpdf (mce_kern_cpdf.h)
   double cpdf_ms = 0;                          // device time of the last marginal_1d_points call (CUDA events)
   DevBuf<BE> slA, slp, slq, slb, slmeta, slcmap, slg, sly;
   DevBuf<BE> tvA, tvp, tvq, tvb, tvmeta, tvcmap, slotOfTerm;
@@ -146,7 +146,7 @@ class Engine {
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
                          &scratchI0, &scratchI1, &scratchI2, &scratchI3, &scratchK0, &scratchK1, &ftrF, &ftrWide, &grpOrder, &grpStart,
-                         &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys, &cpVal0, &cpCache, &cpXs, &cpOut};
+                         &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys, &cpVal0, &cpCache, &cpXs, &cpOut, &cpYs, &cpRecs, &cpV, &cpBad};
     for (auto* b : all) { b->be = &be; all_bufs.push_back(b); }
     gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0);
   }
@@ -855,6 +855,55 @@ class Engine {
     return n;
   }
 
+
+
+  // Point-wise 2-D marginal cpdf of states (idx1 < idx2) at the points (xs[k], ys[k]) (cpdf_ndim.hpp:1356-1455 as driven by
+  // CauchyCPDFGridDispatcher2D, :1850-1919).  Returns n, 0 when no tables exist, < 0 on misuse, -5 on the reference's
+  // "possible singularity" exit (cpdf_ndim.hpp:1624-1628).
+  int marginal_2d_points(int idx1, int idx2, const double* bar_nu, int n, const double* xs, const double* ys, double* zs) {
+    if (master_step < 1) { error = "marginal cpdf: the estimator has not been stepped (cpdf_ndim.hpp:1359)"; return -2; }
+    if (idx1 < 0 || idx1 >= idx2 || idx2 >= d || n < 1) { error = "marginal cpdf: state indices must satisfy 0 <= idx1 < idx2 < d (cpdf_ndim.hpp:1852-1855)"; return -2; }
+    if (master_step == num_estimation_steps || skip_post_mu) return 0;
+    GenStore& g = gen[cur];
+    const int nt = g.v.n_alive;
+    if (nt <= 0) return 0;
+    const int S = max_shape, R = cpdf2_rec_doubles(S);
+    double* recs = (double*)cpRecs.ensure(sizeof(double) * (size_t)R * nt);
+    double* dxs = (double*)cpXs.ensure(sizeof(double) * (size_t)n);
+    double* dys = (double*)cpYs.ensure(sizeof(double) * (size_t)n);
+    double* dout = (double*)cpOut.ensure(sizeof(double) * (size_t)n);
+    int* bad = (int*)cpBad.ensure(sizeof(int) * 4);
+    // terms per chunk: the value matrix V[chunk][n] stays below ~256 MB and a chunk is a whole number of term tiles
+    long long chunk = (256ll << 20) / (8ll * n);
+    chunk = chunk < CPDF2_TERMS ? CPDF2_TERMS : (chunk / CPDF2_TERMS) * CPDF2_TERMS;
+    if (chunk > nt) chunk = ((nt + CPDF2_TERMS - 1) / CPDF2_TERMS) * CPDF2_TERMS;
+    double* V = (double*)cpV.ensure(sizeof(double) * (size_t)chunk * n);
+    be.h2d(dxs, xs, sizeof(double) * (size_t)n);
+    be.h2d(dys, ys, sizeof(double) * (size_t)n);
+    be.memset(bad, 0, sizeof(int) * 4);
+    be.ev_record(10);
+    KCpdf2dTerms kt; memset(&kt, 0, sizeof(kt));
+    kt.gen = g.v; kt.d = d; kt.idx1 = idx1; kt.idx2 = idx2; kt.S = S; kt.recs = recs;
+    for (int i = 0; i < d; i++) kt.bar_nu[i] = bar_nu[i];
+    be.launch(kt, (nt + 63) / 64, 64, 0);
+    const int n_ptiles = (n + CPDF2_PTS - 1) / CPDF2_PTS;
+    for (long long t0 = 0; t0 < nt; t0 += chunk) {
+      const int cnt = (int)(nt - t0 < chunk ? nt - t0 : chunk), n_ttiles = (cnt + CPDF2_TERMS - 1) / CPDF2_TERMS;
+      KCpdf2dValues kv{S, (int)t0, cnt, n, n_ptiles, dxs, dys, recs, V, bad};
+      be.launch(kv, n_ptiles * n_ttiles, CPDF2_PTS, KCpdf2dValues::smem_bytes(S));
+      KCpdf2dSum ks{cnt, n, t0 == 0 ? 1 : 0, V, dout};
+      be.launch(ks, (n + 31) / 32, 32, 0);
+    }
+    be.ev_record(11);
+    int hbad = 0;
+    be.d2h(zs, dout, sizeof(double) * (size_t)n);
+    be.d2h(&hbad, bad, sizeof(int));
+    cpdf_ms = be.ev_elapsed(10, 11);
+    if (hbad) { error = "marginal cpdf: possible singularity, gamma1 and gamma2 both vanish at a grid point (cpdf_ndim.hpp:1624-1628)"; return -5; }
+    const double norm_factor = fz.re, RECIPRICAL_TWO_PI = 1.0 / (2.0 * M_PI);
+    for (int k = 0; k < n; k++) zs[k] = 2 * zs[k] * RECIPRICAL_TWO_PI * RECIPRICAL_TWO_PI / norm_factor;   // cpdf_ndim.hpp:1446
+    return n;
+  }
 
   // device self-test of div_nobranch (mce_math.h): out[0] = flagged-ok pairs that differ from a / b, out[1] = ok pairs
   int div_selftest(long long n, unsigned long long seed, unsigned long long* out) {

@@ -144,6 +144,8 @@ struct KCpdf1dGrid {
 // rounding noise, not bit for bit -- the tests use a relative tolerance (tests/test_gpu_cpdf.py).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int CPDF2_ZERO_HP = 32;            // ZERO_HP_MARKER_VALUE, cpdf_ndim.hpp:373
+constexpr double COALIGN_MU_EPS = COALIGN_EPS;        // cauchy_constants.hpp:32
+constexpr double INTEGRAL_GAMMA_EPS = 1e-8;          // cauchy_constants.hpp:76
 MCE_HD int cpdf2_rec_doubles(int S) { return 4 + 2 * (S + 1) + 4 * S; }
 // record: [0] m, [1] b0, [2] b1, [3] -, then (sin, cos)[S+1], then (gam1_real, gam2_real, g.re, g.im)[S]
 

@@ -196,6 +196,45 @@ class CauchyEstimator:
             return None, None
         return self.get_marginal_1D_pointwise_cpdf(0, gridx_low, gridx_high, gridx_resolution, log_dir)
 
+    def get_marginal_2D_pointwise_cpdf(self, marg_idx1, marg_idx2, gridx_low, gridx_high, gridx_resolution, gridy_low, gridy_high,
+                                       gridy_resolution, log_dir=None, reset_cache=True):
+        """X, Y, Z (each [num_gridy, num_gridx]) of the marginal cpdf of the state pair, like cauchy_estimator.py:954-989;
+        with `log_dir` the reference's files are written (cpdf_ndim.hpp:1921-1983).  `reset_cache` is accepted and ignored:
+        the device evaluation keeps no cache between calls."""
+        if self.master_step < 1:
+            print("Cannot evaluate Cauchy Estimator Marginal 2D CPDF before it has been stepped!")
+            return None, None, None
+        i1, i2 = int(marg_idx1), int(marg_idx2)
+        xl, xh, xr, yl, yh, yr = (float(v) for v in (gridx_low, gridx_high, gridx_resolution, gridy_low, gridy_high, gridy_resolution))
+        assert xh > xl and yh > yl and xr > 0 and yr > 0
+        assert -1 < i1 < i2 < self.d
+        nx, ny = self._lib.mce_cpdf_grid_count(xl, xh, xr), self._lib.mce_cpdf_grid_count(yl, yh, yr)
+        xyz = np.zeros((nx * ny, 3))
+        bar_nu = self._bar_nu()
+        rc = self._lib.mce_marginal_2d_grid(self._h, i1, i2, _dp(bar_nu), xl, xh, xr, yl, yh, yr, _dp(xyz), nx * ny, None, None)
+        if rc < 0:
+            raise RuntimeError(self._lib.mce_last_error().decode())
+        if rc == 0:
+            print("[WARN CauchyCPDFGridDispatcher2D:] Cannot evaluate cauchy estimator cpdf for the last step since SKIP_LAST_STEP == true!")
+            return np.zeros((0, 0)), np.zeros((0, 0)), np.zeros((0, 0))
+        if log_dir:
+            ld = str(log_dir).rstrip("/")
+            os.makedirs(ld, exist_ok=True)
+            counts = self.__dict__.setdefault("_cpdf_log_counts", {})
+            k = counts.get((ld, i1, i2), 0)
+            with open(os.path.join(ld, "grid_elems_%d%d.txt" % (i1, i2)), "w" if k == 0 else "a") as f:
+                f.write("%d,%d\n" % (nx, ny))
+            xyz.tofile(os.path.join(ld, "cpdf_%d%d_%d.bin" % (i1, i2, k + 1)))
+            counts[(ld, i1, i2)] = k + 1
+        g = xyz.reshape(ny, nx, 3)
+        return g[:, :, 0].copy(), g[:, :, 1].copy(), g[:, :, 2].copy()
+
+    def get_2D_pointwise_cpdf(self, gridx_low, gridx_high, gridx_resolution, gridy_low, gridy_high, gridy_resolution, log_dir=None):
+        if self.d != 2:                                            # cauchy_estimator.py:991-1001
+            print("Cannot evaluate Cauchy Estimator 2D CPDF for a {}-state system!".format(self.d))
+            return None, None, None
+        return self.get_marginal_2D_pointwise_cpdf(0, 1, gridx_low, gridx_high, gridx_resolution, gridy_low, gridy_high, gridy_resolution, log_dir)
+
     def marginal_1d_points(self, marg_idx, xs):
         """f(xs[k]) for arbitrary points; the first point is evaluated uncached like the grid dispatcher's first point."""
         xs = np.ascontiguousarray(xs, np.float64)

@@ -109,6 +109,13 @@ int mce_cpdf_grid_count(double grid_low, double grid_high, double grid_res);
 int mce_marginal_1d_points(mce_handle* h, int marg_idx, const double* bar_nu, int n, const double* xs, double* ys);
 int mce_marginal_1d_grid(mce_handle* h, int marg_idx, const double* bar_nu, double grid_low, double grid_high, double grid_res,
                          double* xy, int n_cap);
+/* Point-wise 2-D marginal cpdf of the state pair (marg_idx1 < marg_idx2): PointWiseNDimCauchyCPDF::evaluate_2D_marginal_cpdf
+ * (cpdf_ndim.hpp:1356-1455) as driven by CauchyCPDFGridDispatcher2D (cpdf_ndim.hpp:1774-1919; pycauchy.hpp:822-872).  The
+ * grid is y-major like the reference's CauchyPoint3D points[]: xyz[(i*nx + j)] = (x_j, y_i, f).  Sums run in the reference's
+ * term order; atan2 / sin / cos are the device's (values agree with the reference to rounding noise, not bit for bit). */
+int mce_marginal_2d_points(mce_handle* h, int marg_idx1, int marg_idx2, const double* bar_nu, int n, const double* xs, const double* ys, double* zs);
+int mce_marginal_2d_grid(mce_handle* h, int marg_idx1, int marg_idx2, const double* bar_nu, double xlo, double xhi, double xres,
+                         double ylo, double yhi, double yres, double* xyz /*[n_cap][3]*/, int n_cap, int* nx_out, int* ny_out);
 double mce_cpdf_last_ms(mce_handle* h);
 
 /* Statistics of the last step: device milliseconds per phase and algorithmic byte counts (bench.py roofline). */

@@ -26,7 +26,9 @@ int main()
     PointWiseNDimCauchyCPDF cpdf(&est);
     CauchyCPDFGridDispatcher1D ref_grid(&cpdf, -2.0, 2.0, 0.01, NULL);
     CauchyCPDFGridDispatcher1D_B200 dev_grid(&cpdf, -2.0, 2.0, 0.01, NULL);
-    long long compared = 0, differing = 0;
+    CauchyCPDFGridDispatcher2D ref_grid2(&cpdf, -1.0, 1.0, 0.1, -1.5, 1.5, 0.15, NULL);
+    CauchyCPDFGridDispatcher2D_B200 dev_grid2(&cpdf, -1.0, 1.0, 0.1, -1.5, 1.5, 0.15, NULL);
+    long long compared = 0, differing = 0, compared2 = 0; double worst2 = 0;
     for(int k = 0; k < steps - 1; k++)      // the window's last step has no tables (SKIP_LAST_STEP)
     {
         est.step(zs[k], Phi, Gamma, beta, H, gamma[0], NULL, NULL);
@@ -48,9 +50,26 @@ int main()
                 }
             }
         }
+        // 2-D marginals: same term order, but the device's atan2 / sin / cos differ from glibc's in the last bits
+        for(int pair = 0; pair < 2 && k < 6; pair++)
+        {
+            int i1 = 0, i2 = 1 + pair;
+            cpdf.reset_2D_marginal_cpdf();
+            if(ref_grid2.evaluate_point_grid(i1, i2, 1, false) || dev_grid2.evaluate_point_grid(i1, i2, 1, false)) { printf("2-D grid refused at step %d\n", k+1); return 1; }
+            double zmax = 0;
+            for(int i = 0; i < ref_grid2.num_grid_points; i++) zmax = fmax(zmax, fabs(ref_grid2.points[i].z));
+            for(int i = 0; i < ref_grid2.num_grid_points; i++)
+            {
+                compared2++;
+                if(ref_grid2.points[i].x != dev_grid2.points[i].x || ref_grid2.points[i].y != dev_grid2.points[i].y) { printf("2-D grid coordinates differ\n"); return 1; }
+                worst2 = fmax(worst2, fabs(ref_grid2.points[i].z - dev_grid2.points[i].z) / zmax);
+            }
+        }
         printf("step %d: %d terms, f(0) = %.12e %.12e %.12e\n", k+1, est.Nt, dev_grid.points[200].y, ref_grid.points[200].y, ref_grid.points[0].y);
     }
     printf("compared %lld grid values, %lld differ\n", compared, differing);
+    printf("compared %lld 2-D grid values, worst |dz| / max|z| = %.3e\n", compared2, worst2);
+    if(worst2 > 1e-9) { printf("2-D marginal outside tolerance\n"); return 1; }
     if(differing == 0 && compared > 0)
         printf("cpdf1d drop-in OK\n");
     return differing == 0 ? 0 : 1;

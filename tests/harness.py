@@ -255,3 +255,34 @@ def oracle_cpdf1d(scenario_path, out_path, lo, hi, res, steps, use_ref=False):
                "--cpdf1d", repr(lo), repr(hi), repr(res), st]
     subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return {n: v for n, v in read_dump(out_path).items() if "cpdf1d" in n}
+
+
+def run_cpdf2d(lib, sc, gold, max_step=None):
+    """2-D marginal grids of every state pair the golden dump holds (`s<k>/cpdf2d/i<a>_<b>`), through mce_marginal_2d_grid."""
+    xlo, xhi, xres, ylo, yhi, yres = [float(v) for v in gold["cpdf2d/grid"]]
+    bar_nu = np.ascontiguousarray(gold["cpdf1d/bar_nu"], np.float64)
+    names = [n for n in gold if "/cpdf2d/i" in n and (max_step is None or int(n.split("/")[0][1:]) <= max_step)]
+    want = sorted({int(n.split("/")[0][1:]) for n in names})
+    s = Session(lib, sc)
+    out = {}
+    try:
+        for k in range(max(want)):
+            r = sc.rec[k]
+            s.step(r)
+            mo = s.moments()
+            if r.shift_kind == SHIFT_EXPLICIT:
+                s.shift_b(r.delta, -1.0)
+            elif r.shift_kind == SHIFT_OWN_MEAN:
+                s.shift_b(np.array(mo.mean[: 2 * sc.d])[0::2], -1.0)
+            for nme in [n for n in names if int(n.split("/")[0][1:]) == k + 1]:
+                a, b = [int(v) for v in nme.split("/i")[1].split("_")]
+                n = lib.mce_cpdf_grid_count(xlo, xhi, xres) * lib.mce_cpdf_grid_count(ylo, yhi, yres)
+                xyz = np.zeros((n, 3))
+                nx, ny = ct.c_int(0), ct.c_int(0)
+                rc = lib.mce_marginal_2d_grid(s.h, a, b, _dp(bar_nu), xlo, xhi, xres, ylo, yhi, yres, _dp(xyz), n, ct.byref(nx), ct.byref(ny))
+                if rc != n:
+                    raise RuntimeError("mce_marginal_2d_grid returned %d: %s" % (rc, lib.mce_last_error().decode()))
+                out[nme] = xyz
+    finally:
+        s.close()
+    return out

@@ -71,3 +71,34 @@ def test_cpdf_misuse_is_reported(emu):
         assert abs(xy[:, 1].min()) >= 0
     finally:
         s.close()
+
+
+# ---- 2-D marginal: on the CPU both the oracle and the emulated kernels call the host libm, like the reference ----
+def _check2d(gold, got, steps):
+    names = [n for n in gold if "/cpdf2d/i" in n and int(n.split("/")[0][1:]) in steps]
+    assert names
+    for n in names:
+        assert n in got, n
+        assert np.array_equal(gold[n].view(np.uint64), np.ascontiguousarray(got[n]).view(np.uint64)), \
+            "%s: max abs diff %.3e" % (n, np.abs(gold[n] - got[n]).max())
+
+
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5"])
+def test_oracle_cpdf2d_matches_reference_golden(name, tmp_path):
+    gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
+    steps = [k for k in cpdf_steps(gold) if k <= {"lti3": 8, "lti4_2pnoise": 6, "syn5": 6, "leo5": 5}[name]]
+    lo, hi, res = [float(v) for v in gold["cpdf1d/grid"]]
+    out = str(tmp_path / "o.mced")
+    cmd = [os.path.join(ROOT, "oracle", "_build", "mce_oracle_run"), os.path.join(GOLD, name + ".mces"), out, "--max-steps", str(max(steps)),
+           "--cpdf1d", repr(lo), repr(hi), repr(res), ",".join(str(k) for k in steps), "--cpdf2d"] + [repr(float(v)) for v in gold["cpdf2d/grid"]]
+    subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    _check2d(gold, read_dump(out), steps)
+
+
+@pytest.mark.parametrize("name,last", [("lti3", 8), ("syn5", 4), ("leo5", 5), ("leo7", 6)])
+def test_emulated_cpdf2d_kernels_match_golden(emu, name, last):
+    from harness import run_cpdf2d
+    gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
+    steps = [k for k in cpdf_steps(gold) if k <= last]
+    got = run_cpdf2d(emu, read_scenario(os.path.join(GOLD, name + ".mces")), gold, max_step=last)
+    _check2d(gold, got, steps)

@@ -89,3 +89,47 @@ def test_branch_free_division_equals_ieee_division():
         assert tot_ok > 2 * 10**9          # the flag is set for the bulk of the pairs (the test is not vacuous)
     finally:
         s.close()
+
+
+# ---- 2-D marginal -------------------------------------------------------------------------------------------------
+# The sums run in the reference's term order and every arithmetic step restates the reference's, but the cache holds
+# atan2 / sin / cos values: CUDA's functions (<= 2 ulp) are not glibc's, so parity is a tolerance, written here.
+CPDF2D_RTOL = 1e-9          # |z - z_ref| <= CPDF2D_RTOL * max|z_ref| over the grid
+
+
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7"])
+def test_cpdf2d_matches_reference_golden(name):
+    from harness import run_cpdf2d
+    gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
+    names = [n for n in gold if "/cpdf2d/i" in n]
+    assert names
+    got = run_cpdf2d(load_product(), read_scenario(os.path.join(GOLD, name + ".mces")), gold)
+    for n in names:
+        a, b = gold[n], got[n]
+        assert a.shape == b.shape, n
+        assert np.array_equal(a[:, :2], b[:, :2]), n + ": grid coordinates"
+        scale = np.abs(a[:, 2]).max()
+        err = np.abs(a[:, 2] - b[:, 2]).max()
+        assert err <= CPDF2D_RTOL * scale, "%s: max |dz| %.3e vs scale %.3e" % (n, err, scale)
+
+
+def test_python_mirror_2d(tmp_path):
+    from cauchyfriendly_b200 import CauchyEstimator
+    sc = read_scenario(os.path.join(GOLD, "lti3.mces"))
+    gold = read_dump(os.path.join(GOLD, "lti3.cpdf.mced"))
+    g = [float(v) for v in gold["cpdf2d/grid"]]
+    est = CauchyEstimator(sc.A0, sc.p0, sc.b0, sc.steps, sc.d, sc.cmcc, sc.pncc, sc.p, root_point=sc.root_point, b_pert=sc.b_pert,
+                          tr_search_idxs_ordering=sc.tr_order)
+    est.bar_nu = gold["cpdf1d/bar_nu"]
+    for k in range(5):
+        r = sc.rec[k]
+        est.step(r.msmt, r.Phi, r.Gamma, r.beta, r.H, r.gamma)
+    X, Y, Z = est.get_marginal_2D_pointwise_cpdf(0, 1, *g, log_dir=str(tmp_path / "log2"))
+    ref = gold["s5/cpdf2d/i0_1"]
+    ny, nx = Z.shape
+    assert np.array_equal(np.stack([X.ravel(), Y.ravel()], 1), ref[:, :2])
+    assert np.abs(Z.ravel() - ref[:, 2]).max() <= CPDF2D_RTOL * np.abs(ref[:, 2]).max()
+    raw = np.fromfile(str(tmp_path / "log2" / "cpdf_01_1.bin")).reshape(-1, 3)
+    assert np.array_equal(raw[:, 2], Z.ravel())
+    assert open(str(tmp_path / "log2" / "grid_elems_01.txt")).read().strip() == "%d,%d" % (nx, ny)
+    est.shutdown()

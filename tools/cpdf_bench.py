@@ -55,4 +55,35 @@ if os.path.exists(ref) and "--no-ref" not in sys.argv:
         out["reference_grid_points"] = pts[0]
         out["reference_term_point_evals_per_s"] = nt * pts[0] / (np.median(ms) * 1e-3)
         out["speedup_e2e"] = out["term_point_evals_per_s"] / out["reference_term_point_evals_per_s"]
+if "--2d" in sys.argv:
+    # 2-D marginal of the pair (0, 1) on an n2 x n2 grid over the same span; the reference on a 21 x 21 grid, one thread
+    import ctypes as ct
+    s = Session(lib, sc)
+    for k in range(step):
+        r = sc.rec[k]
+        s.step(r)
+        if r.shift_kind == SHIFT_EXPLICIT:
+            s.shift_b(r.delta, -1.0)
+    n2 = 201
+    r2 = (hi - lo) / (n2 - 1)
+    cnt = lib.mce_cpdf_grid_count(lo, hi, r2) ** 2
+    xyz = np.zeros((cnt, 3))
+    ms2, wall2 = [], []
+    for rep in range(3):
+        t0 = time.perf_counter()
+        assert lib.mce_marginal_2d_grid(s.h, 0, 1, _dp(nu), lo, hi, r2, lo, hi, r2, _dp(xyz), cnt, None, None) == cnt
+        wall2.append((time.perf_counter() - t0) * 1e3)
+        ms2.append(lib.mce_cpdf_last_ms(s.h))
+    s.close()
+    out["cpdf2d"] = {"pair": [0, 1], "grid_points": int(cnt), "device_ms": float(np.median(ms2)), "e2e_ms": float(np.median(wall2)),
+                     "term_point_evals_per_s": nt * cnt / (np.median(wall2) * 1e-3)}
+    if os.path.exists(ref) and "--no-ref" not in sys.argv:
+        rr = (hi - lo) / 20
+        txt = subprocess.run([ref, scen, "/tmp/_cpdf_ref2.mced", repr(lo), repr(hi), repr((hi - lo) / 4), str(step), "--time", "--2d",
+                              repr(lo), repr(hi), repr(rr), repr(lo), repr(hi), repr(rr)], capture_output=True, text=True).stdout
+        m2 = re.search(r"pair 0,1: \d+ terms x (\d+) points in (\d+) ms", txt)
+        if m2:
+            rp, rms = int(m2.group(1)), int(m2.group(2))
+            out["cpdf2d"].update({"reference_grid_points": rp, "reference_cpu_ms": rms, "reference_term_point_evals_per_s": nt * rp / (rms * 1e-3),
+                                  "speedup_e2e": out["cpdf2d"]["term_point_evals_per_s"] / (nt * rp / (rms * 1e-3))})
 print(json.dumps(out))

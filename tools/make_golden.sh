@@ -20,10 +20,11 @@ $R tests/golden/leo5.mces         tests/golden/leo5.ref.mced         --full-upto
 # the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
 oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
 ls -la tests/golden
-# point-wise 1-D marginal cpdf of the reference (cpdf_ndim.hpp:1233-1354, 2055-2139) after selected steps, every state index
+# point-wise 1-D marginal cpdf of the reference (cpdf_ndim.hpp:1233-1354, 2055-2139) after selected steps, every state index,
+# and its 2-D marginal (cpdf_ndim.hpp:1356-1455, 1774-1919) of the state pairs (0,1), (1,2), ..., (0,d-1) on a 21 x 21 grid
 C=oracle/_ref/ref_cpdf_cpu1
-$C tests/golden/lti3.mces         tests/golden/lti3.cpdf.mced         -2.0 2.0 0.05  2,5,8,10
-$C tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.cpdf.mced -3.0 3.0 0.1   3,6
-$C tests/golden/syn5.mces         tests/golden/syn5.cpdf.mced         -1.0 1.0 0.04  4,6
-$C tests/golden/leo5.mces         tests/golden/leo5.cpdf.mced         -0.5 0.5 0.01  5,10
-$C tests/golden/leo7.mces         tests/golden/leo7.cpdf.mced         -0.2 0.2 0.005 6,11
+$C tests/golden/lti3.mces         tests/golden/lti3.cpdf.mced         -2.0 2.0 0.05  2,5,8,10 --2d -1.0 1.0 0.1 -1.5 1.5 0.15
+$C tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.cpdf.mced -3.0 3.0 0.1   3,6 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
+$C tests/golden/syn5.mces         tests/golden/syn5.cpdf.mced         -1.0 1.0 0.04  4,6 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
+$C tests/golden/leo5.mces         tests/golden/leo5.cpdf.mced         -0.5 0.5 0.01  5,10 --2d -0.3 0.3 0.03 -0.3 0.3 0.03
+$C tests/golden/leo7.mces         tests/golden/leo7.cpdf.mced         -0.2 0.2 0.005 6,11 --2d -0.1 0.1 0.01 -0.1 0.1 0.01
