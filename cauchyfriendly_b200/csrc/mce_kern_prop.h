@@ -140,7 +140,10 @@ MCE_HD cplx eval_g_yei(const double* A, const double* p, const double* b, int m,
       gm = g_lookup(lm ^ (int)enc_lhp, phc, pkeys, pG, pcells);
     }
   }
-  cplx g = csub(cdiv(gp, make_cplx(ygi + d_val, c_val)), cdiv(gm, make_cplx(ygi - d_val, c_val)));
+  const cplx vp = make_cplx(ygi + d_val, c_val), vm = make_cplx(ygi - d_val, c_val);
+  cplx rp, rm;
+  if (!cdiv2_fast(gp, vp, gm, vm, &rp, &rm)) { rp = cdiv(gp, vp); rm = cdiv(gm, vm); }   // common case: the six divisions overlap (mce_math.h)
+  cplx g = csub(rp, rm);
   g = cscale(g, 1.0 / (2.0 * M_PI));
   for (int j = 0; j < d; j++) { y[2 * j] = -tmp[j]; y[2 * j + 1] = b[j]; }
   return g;
