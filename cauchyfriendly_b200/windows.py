@@ -11,6 +11,8 @@ process per GPU, torch.distributed).  The only exchange per step is an all-gathe
 mean, covariance) -- 3 + n + n*n doubles per window -- after which every rank runs the same selection logic; there is no
 data-path collective.  This is the reference's own unit of distribution (one forked process per window,
 cauchy_windows.hpp:353-376)."""
+import os
+
 import numpy as np
 
 from .estimator import CauchyEstimator
@@ -41,13 +43,79 @@ def speyers_window_init(x1_hat, Var, H, gamma, z1):
     return A0, p0, b0
 
 
+LOG_NAMES = ("cond_means.txt", "cond_covars.txt", "norm_factors.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt",
+             "cerr_norm_factors.txt", "numeric_error_codes.txt")
+
+
+def _fmt(values):
+    # log_double_array_to_file, array_logging.hpp:60-70: "%.16lf" separated by single blanks
+    return " ".join("%.16f" % float(v) for v in np.atleast_1d(values))
+
+
+class WindowLogFiles:
+    """The reference's window-manager log layout: `<log_dir>/<name>` hold the best window per step as "<win_idx>:<values>"
+    lines, `<log_dir>/windows/win<i>/<name>` every window's own history without the prefix (cauchy_windows.hpp:1237-1373;
+    read back by scripts/cauchy_plotter.py and cauchy_estimator.py:1337-1373 load_cauchy_log_folder)."""
+
+    def __init__(self, log_dir, num_windows, log_windows=True):
+        self.log_dir = log_dir.rstrip("/")
+        os.makedirs(self.log_dir, exist_ok=True)
+        self.best = [open(os.path.join(self.log_dir, nme), "w") for nme in LOG_NAMES]
+        self.wins = None
+        if log_windows:
+            self.wins = []
+            for w in range(num_windows):
+                d = os.path.join(self.log_dir, "windows", "win%d" % w)
+                os.makedirs(d, exist_ok=True)
+                self.wins.append([open(os.path.join(d, nme), "w") for nme in LOG_NAMES])
+
+    @staticmethod
+    def _rows(row, n):
+        nn = n * n
+        return (_fmt(row[3:3 + n]), _fmt(row[3 + n:3 + n + nn]), _fmt(row[2]), _fmt(row[4 + n + nn]), _fmt(row[5 + n + nn]),
+                _fmt(row[3 + n + nn]), "%d" % int(row[1]))
+
+    def write_best(self, win_idx, row, n):
+        for f, txt in zip(self.best, self._rows(row, n)):
+            f.write("%d:%s\n" % (win_idx, txt))
+            f.flush()
+
+    def write_window(self, w, row, n):
+        if self.wins is None:
+            return
+        for f, txt in zip(self.wins[w], self._rows(row, n)):
+            f.write(txt + "\n")
+            f.flush()
+
+    def close(self):
+        for f in self.best + ([g for fs in self.wins for g in fs] if self.wins else []):
+            f.close()
+
+
+def load_window_data(path):          # cauchy_estimator.py:1337-1340
+    return np.array([[float(v) for v in line.split(":")[1].split(" ")] for line in open(path)])
+
+
+def load_data(path):                 # cauchy_estimator.py:1343-1346
+    return np.array([[float(v) for v in line.split(" ")] for line in open(path)])
+
+
+def load_cauchy_log_folder(log_dir, with_win_logging=True):      # cauchy_estimator.py:1348-1373
+    log_dir = log_dir if log_dir.endswith("/") else log_dir + "/"
+    rd = load_window_data if with_win_logging else load_data
+    covars = rd(log_dir + "cond_covars.txt")
+    n = int(np.sqrt(covars.shape[1]))
+    return {"x": rd(log_dir + "cond_means.txt"), "P": covars.reshape(covars.shape[0], n, n), "cerr_x": rd(log_dir + "cerr_cond_means.txt"),
+            "cerr_P": rd(log_dir + "cerr_cond_covars.txt"), "cerr_fz": rd(log_dir + "cerr_norm_factors.txt")}
+
+
 class SlidingWindowBank:
     """LTI/LTV sliding-window Cauchy estimator (W windows of depth W).
 
     step(msmts, controls) mirrors PySlidingWindowManager.step and returns (xhat, Phat, wavg_xhat, wavg_Phat)."""
 
     def __init__(self, num_windows, A0, p0, b0, Phi, B, Gamma, beta, H, gamma, *, estimator_cls=CauchyEstimator, est_kwargs=None,
-                 dist=None, seed=0, debug_print=False, concurrent=False):
+                 dist=None, seed=0, debug_print=False, concurrent=False, log_dir=None, log_windows=True):
         self.W = int(num_windows)
         self.n = int(np.asarray(p0).size)
         self.Phi = np.asarray(Phi, np.float64).reshape(self.n, self.n)
@@ -81,8 +149,13 @@ class SlidingWindowBank:
         self.moment_info = {"x": [], "P": [], "fz": [], "win_idx": [], "err_code": []}
         self.avg_moment_info = {"x": [], "P": [], "win_idx": [], "err_code": []}
         n = self.n
-        self._stats = np.zeros((self.W, 3 + n + n * n))      # per window: count, err, fz, mean[n], cov[n*n] (last measurement)
+        # per window: count, err, Re fz, mean[n], cov[n*n], then Im fz, max |Im mean|, max |Im cov| (last measurement)
+        self._stats = np.zeros((self.W, 3 + n + n * n + 3))
         self._last_msmts = None
+        # the reference's log files (cauchy_windows.hpp:1237-1476, array_logging.hpp:60-98), written by rank 0
+        self._log = None
+        if log_dir is not None and self.rank == 0:
+            self._log = WindowLogFiles(str(log_dir), self.W, log_windows)
 
     # ---- one estimator, one time step: p measurement updates (PyCauchyEstimator._call_step, cauchy_estimator.py:612-656) ----
     def _step_window(self, w, msmts, controls, first_msmt=0):
@@ -95,7 +168,11 @@ class SlidingWindowBank:
         row[1] = est.numeric_moment_errors
         row[2] = est.fz_after_mu.real if est.fz_after_mu.real != 0 else est.fz.real
         row[3:3 + n] = est.conditional_mean.real
-        row[3 + n:] = est.conditional_variance.real.ravel()
+        row[3 + n:3 + n + n * n] = est.conditional_variance.real.ravel()
+        fz = est.fz_after_mu if est.fz_after_mu.real != 0 else est.fz
+        row[3 + n + n * n] = fz.imag                                             # save_window_data, cauchy_windows.hpp:1478-1503
+        row[4 + n + n * n] = np.abs(est.conditional_mean.imag).max()
+        row[5 + n + n * n] = np.abs(est.conditional_variance.imag).max()
 
     def _exchange(self):
         """All ranks end up with every window's statistics (the only communication of a step)."""
@@ -130,7 +207,7 @@ class SlidingWindowBank:
 
     def _mean_cov(self, w):
         n = self.n
-        return self._stats[w, 3:3 + n].copy(), self._stats[w, 3 + n:].reshape(n, n).copy()
+        return self._stats[w, 3:3 + n].copy(), self._stats[w, 3 + n:3 + n + n * n].reshape(n, n).copy()
 
     def step(self, msmts, controls=None):
         msmts = np.asarray(msmts, np.float64).reshape(self.p)
@@ -168,6 +245,11 @@ class SlidingWindowBank:
         xavg /= wsum; Pavg /= wsum
         self.avg_moment_info["x"].append(xavg); self.avg_moment_info["P"].append(Pavg)
         self.avg_moment_info["win_idx"].append(-1); self.avg_moment_info["err_code"].append(err_or)
+        if self._log is not None:           # sequential_logger_best_window / _all_windows, cauchy_windows.hpp:1378-1421
+            self._log.write_best(best, self._stats[best], self.n)
+            for w in range(self.W):
+                if self.win_counts[w] > 0:
+                    self._log.write_window(w, self._stats[w], self.n)
         # re-seed the empty window about the best window's estimate and the last measurement (reset_about_estimator, :888-923)
         if self.step_idx > 0:
             if min_idx in self.ests:
@@ -186,6 +268,9 @@ class SlidingWindowBank:
         return xhat, Phat, xavg, Pavg
 
     def shutdown(self):
+        if self._log is not None:
+            self._log.close()
+            self._log = None
         if self._pool is not None:
             self._pool.shutdown()
             self._pool = None

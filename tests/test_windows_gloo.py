@@ -31,7 +31,7 @@ x = np.zeros(3); zs = []
 for _ in range(10):
     x = Phi @ x + Gamma * 0.1 * rng.standard_cauchy(); zs.append(H[0] @ x + 0.2 * rng.standard_cauchy())
 bank = SlidingWindowBank(4, np.eye(3), [.1, .08, .05], np.zeros(3), Phi, None, Gamma, beta, H, gamma,
-                         estimator_cls=functools.partial(CauchyEstimator, _lib=lib), dist=d, seed=5)
+                         estimator_cls=functools.partial(CauchyEstimator, _lib=lib), dist=d, seed=5, log_dir=os.environ.get("MCE_LOG"))
 out = []
 for z in zs:
     xh, Ph, xa, Pa = bank.step([z])
@@ -47,7 +47,7 @@ if d is not None:
 def _run(world, out, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MCE_ROOT=ROOT, MCE_OUT=str(out))
+    env = dict(os.environ, MCE_ROOT=ROOT, MCE_OUT=str(out), MCE_LOG=str(out) + ".log")
     if world == 1:
         subprocess.check_call([sys.executable, str(script)], env=env, timeout=600)
     else:
@@ -65,6 +65,19 @@ def test_sharded_window_bank_matches_single_process(tmp_path):
     assert np.array_equal(a, b)
     assert np.isfinite(a).all()
     assert set(a[:, -1].astype(int)) - {0} != set()      # windows other than the first did become "best" after the warm-up
+    # the reference's log layout (cauchy_windows.hpp:1237-1421), written by rank 0 and read back with the reference's parsers
+    from cauchyfriendly_b200.windows import LOG_NAMES, load_cauchy_log_folder, load_data
+    for world_dir in (str(tmp_path / "w1.npy") + ".log", str(tmp_path / "w2.npy") + ".log"):
+        logs = load_cauchy_log_folder(world_dir)
+        assert logs["x"].shape == (10, 3) and logs["P"].shape == (10, 3, 3)
+        assert np.allclose(logs["x"], a[:, :3], rtol=0, atol=1e-15) and np.allclose(logs["P"].reshape(10, 9), a[:, 3:12], rtol=0, atol=1e-15)
+        best = [int(line.split(":")[0]) for line in open(os.path.join(world_dir, "cond_means.txt"))]
+        assert best == list(a[:, -1].astype(int))
+        assert sorted(os.listdir(world_dir)) == sorted(list(LOG_NAMES) + ["windows"])
+        w0 = load_data(os.path.join(world_dir, "windows", "win0", "cond_means.txt"))
+        assert w0.shape[1] == 3 and w0.shape[0] >= 4
+        codes = [int(line.split(":")[1]) for line in open(os.path.join(world_dir, "numeric_error_codes.txt"))]
+        assert len(codes) == 10
 
 
 def test_speyer_init_reproduces_mean_and_covariance():
