@@ -28,3 +28,7 @@ $C tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.cpdf.mced -3.0 3.0 0
 $C tests/golden/syn5.mces         tests/golden/syn5.cpdf.mced         -1.0 1.0 0.04  4,6 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
 $C tests/golden/leo5.mces         tests/golden/leo5.cpdf.mced         -0.5 0.5 0.01  5,10 --2d -0.3 0.3 0.03 -0.3 0.3 0.03
 $C tests/golden/leo7.mces         tests/golden/leo7.cpdf.mced         -0.2 0.2 0.005 6,11 --2d -0.1 0.1 0.01 -0.1 0.1 0.01
+$C tests/golden/lti2.mces         tests/golden/lti2.cpdf.mced         -2.0 2.0 0.05  3,7,9 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
+$C tests/golden/lti3_3msmts.mces  tests/golden/lti3_3msmts.cpdf.mced  -2.0 2.0 0.05  4,8,12 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
+$C tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.cpdf.mced  -2.0 2.0 0.05  3,7,9 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
+$C tests/golden/syn8.mces         tests/golden/syn8.cpdf.mced         -1.0 1.0 0.04  2,4 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
