@@ -104,7 +104,7 @@ class Engine {
 
   // ---- device state ----
   struct GenStore {
-    GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G, rbm, rpf;
+    GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G, rbm, rpf, gmax;
     std::vector<int> alive_per_shape;   // survivors per shape
     long long sum_cells = 0;            // total table cells of the survivors
   } gen[2];
@@ -141,7 +141,7 @@ class Engine {
     fz = last_fz = make_cplx(0, 0);
     terms_per_shape.assign(shape_range, 0); muc_per_shape.assign(shape_range, 0);
     terms_per_shape[d] = 1;
-    DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G, &gen[0].rbm, &gen[0].rpf, &gen[1].rbm, &gen[1].rpf,
+    DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G, &gen[0].rbm, &gen[0].rpf, &gen[1].rbm, &gen[1].rpf, &gen[0].gmax, &gen[1].gmax,
                          &gen[1].g_m, &gen[1].cells, &gen[1].alive, &gen[1].A, &gen[1].p, &gen[1].b, &gen[1].keys, &gen[1].G,
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
@@ -192,6 +192,7 @@ class Engine {
     v.G = (cplx*)g.G.ensure(sizeof(cplx) * (size_t)(gt + 8));
     v.rbm = (unsigned*)g.rbm.ensure(sizeof(unsigned) * (size_t)(gr + 8));
     v.rpf = (unsigned short*)g.rpf.ensure(sizeof(unsigned short) * (size_t)(gr + 8));
+    v.gmax = (double*)g.gmax.ensure(sizeof(double) * ((size_t)gid + 8));
   }
 
   StepParams make_params(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,

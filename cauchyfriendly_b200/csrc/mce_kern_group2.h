@@ -159,6 +159,7 @@ struct Group2Member {              // everything the kernel needs to know about 
   long long rk_off;                // parent's rank structure inside prev.rbm / prev.rpf
   unsigned hflag, enc_lhp, csneg, mask, kflip;
   unsigned char z, is_child, has_cmap, pbc;
+  unsigned char skip;              // certified negligible from the parent's largest |G| alone: no cell needs evaluating
   double c, d, psq;
   unsigned char ksrc[MAXM];
 };
@@ -218,17 +219,30 @@ template <class Ctx> MCE_KERNEL_FN MCE_NOINLINE void bm_prefix_any(Ctx& c, const
 // Rank structure of every parent table (GenView::rbm / rpf): one CTA per surviving parent.
 struct KBuildRank {
   GenView gen;
-  static MCE_HD size_t smem_bytes(int nw_max, int nthreads) { return sizeof(unsigned) * (size_t)nw_max + sizeof(unsigned short) * ((size_t)nw_max + nthreads + 16) + 16; }
+  static MCE_HD size_t smem_bytes(int nw_max, int nthreads) { return sizeof(unsigned) * (size_t)nw_max + sizeof(unsigned short) * ((size_t)nw_max + nthreads + 16) + 16 + sizeof(double) * nthreads; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     const int gid = gen.alive[c.block()], m = gen_m(gen, gid), nw = rank_words(m), cells = gen.cells[gid];
     const unsigned* keys = gen_keys(gen, gid, m);
+    const cplx* G = gen_G(gen, gid, m);
     const long long off = gen_rk_off(gen, gid, m);
     unsigned* sbm = (unsigned*)c.smem();
     unsigned short* spf = (unsigned short*)(sbm + nw);
+    double* smx = (double*)(((uintptr_t)(spf + nw + c.nthreads() + 16) + 15) & ~(uintptr_t)15);
     c.par([&](int tid) { for (int i = tid; i < nw; i += c.nthreads()) sbm[i] = 0; });
-    c.par([&](int tid) { for (int i = tid; i < cells; i += c.nthreads()) { const unsigned k = keys[i]; c.atomic_or(&sbm[k >> 5], 1u << (k & 31)); } });
+    c.par([&](int tid) {
+      double mx = 0;              // largest |re| + |im| of the table: an upper bound of every |G| (see Group2Member::skip)
+      for (int i = tid; i < cells; i += c.nthreads()) {
+        const unsigned k = keys[i]; c.atomic_or(&sbm[k >> 5], 1u << (k & 31));
+        const cplx g = G[i]; const double a = fabs(g.re) + fabs(g.im);
+        if (!(a <= mx)) mx = a;   // NaN propagates: a NaN bound never certifies anything
+      }
+      smx[tid] = mx;
+    });
     bm_prefix_any(c, sbm, spf, nw, (int*)nullptr);
-    c.par([&](int tid) { for (int i = tid; i < nw; i += c.nthreads()) { gen.rbm[off + i] = sbm[i]; gen.rpf[off + i] = spf[i]; } });
+    c.par([&](int tid) {
+      for (int i = tid; i < nw; i += c.nthreads()) { gen.rbm[off + i] = sbm[i]; gen.rpf[off + i] = spf[i]; }
+      if (tid == 0) { double mx = 0; for (int t = 0; t < c.nthreads(); t++) if (!(smx[t] <= mx)) mx = smx[t]; gen.gmax[gid] = mx; }
+    });
   }
 };
 
@@ -294,6 +308,11 @@ struct KGTable2T {
     const double* p = term_p(tv, m, ti);
     double s = 0; for (int i = 0; i < m; i++) s += p[i];       // sum_vec, flat:106-107
     e->psq = s * s;
+    // Negligibility certificate (flat:242-247 keeps a member only if some cell has (sum p)^2 |G| > 1e-15).  Every cell is
+    // G = [G_p(l+)/(ygi + d + ic) - G_p(l-)/(ygi - d + ic)] * scale with |ygi +- d + ic| >= |c| and |G_p| <= gmax_p, hence
+    // |G| <= 2 gmax_p scale / |c| up to rounding (a few 1e-16 relative per operation).  With a factor 2 to spare the computed
+    // product of EVERY cell is below the threshold, so the member is negligible exactly as the cell-by-cell test would find.
+    { const double bound = 4.0 * prev.gmax[gidp] * fabs(sp.gscale) / fabs(me.c_val); e->skip = (e->psq * bound <= TERM_APPROXIMATION_EPS) ? 1 : 0; }
     e->kflip = 0;
     if ((me.flags & 3) == 3) {         // coaligned new child: parent position k <- child row cmap[l], flipped by cs_map[l] (flat:194-217)
       const unsigned char* cm = tv.cmap + gt * MAXM;
@@ -466,7 +485,11 @@ struct KGTable2T {
         if (sigma & top_m) sigma ^= rev_m;
       }
       c.par([&](int tid) {
-        MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm->q[0], e, &sm->flag[kk], key); }
+        if (e->skip) {                   // certified negligible (load_member): only the re-orientation of the table happens
+          if (sigma) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) Bk[i] ^= sigma; }
+        } else {
+          MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) { const unsigned key = Bk[i] ^ sigma; Bk[i] = key; acc[i] = eval_cell(sm->q[0], e, &sm->flag[kk], key); }
+        }
         if (sigma && tid == 0 && sm->owner >= 0 && primary) c.atomic_xor(ws.bxor + sm->owner, sigma);   // the table is a parent's B memory, shared with its children
       });
       if (sm->flag[kk]) { accepted = 1; break; }
@@ -506,6 +529,7 @@ struct KGTable2T {
       if (k - w.cbase >= G2_CHUNK || k < w.cbase) { c.par([&](int tid) { do_pending(tid); }); pend = 0; w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); staged = false; }
       const int kk = k - w.cbase, sl = k & 1;
       const Group2Member* et = &sm->mem[kk];
+      if (et->skip) { staged = false; continue; }       // certified negligible (load_member): contributes nothing, costs nothing
       if (!staged) c.par([&](int tid) { stage_qs(sm, et, sl, rsel, tid); });
       const bool next_here = (k + 1 < k_to) && (kk + 1 < G2_CHUNK);       // member k+1 is in the loaded chunk: stage it during this phase
       const Group2Member* en = et + 1;

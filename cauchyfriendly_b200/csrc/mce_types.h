@@ -77,6 +77,7 @@ struct GenView {
   long long rk_base[NSHAPE];
   unsigned* rbm;
   unsigned short* rpf;
+  double* gmax;                       // [n_groups] max over the table's cells of |re| + |im| (>= |G|), written by KBuildRank
 };
 MCE_HD int gen_m(const GenView& g, int gid) { return g.g_m[gid]; }
 MCE_HD int rank_words(int m) { return m >= 5 ? (1 << (m - 5)) : 1; }
