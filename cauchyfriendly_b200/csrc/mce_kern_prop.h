@@ -382,8 +382,10 @@ struct KMsmtUpdate2 {
     });
     // ---- P3: moment contribution (est:307-338) + slot meta, one (parent, child) per thread ----
     c.par([&](int tid) {
-      const int pb = tid >> 5, lane = tid & 31;
-      for (int s = lane; s < spp && pb < npb; s += 32) {
+      // (parent, child) items packed over the CTA's threads: a parent has at most MT + 1 children, so one warp per parent
+      // would leave two thirds of its lanes idle in this phase (the heaviest one: two table lookups, two complex divisions)
+      for (int it = tid; it < npb * spp; it += NT) {
+        const int pb = it / spp, s = it - pb * spp;
         const int ps = pb * spp + s;
         const Par& P = par[pb]; Slot& S = slot[ps];
         const long long ls = (long long)(pb0 + pb) * spp + s, gslot = sl.slot_begin[ms] + ls;
@@ -451,8 +453,8 @@ struct KMsmtUpdate2 {
     });
     // ---- P6: sequential merge of coaligned rows (mu_coalign, term:533-745), one (parent, child) per thread ----
     c.par([&](int tid) {
-      const int pb = tid >> 5, lane = tid & 31;
-      for (int s = lane; s < spp && pb < npb; s += 32) {
+      for (int it = tid; it < npb * spp; it += NT) {      // packed like P3
+        const int pb = it / spp, s = it - pb * spp;
         const int ps = pb * spp + s;
         Slot& S = slot[ps];
         if (!S.valid) continue;
