@@ -446,7 +446,7 @@ class Engine {
     int* counts = (int*)rankCounts.ensure(sizeof(int) * (size_t)nchunks * 2 * NSHAPE + 64);
     int* totals = (int*)rankTotals.ensure(sizeof(int) * 2 * NSHAPE + 64);
     be.launch(KRankCount{sl, nchunks, counts}, nchunks, RANK_CHUNK, sizeof(int) * 2 * NSHAPE);
-    be.launch(KRankScan{nchunks, counts, totals}, 2 * NSHAPE, 32, 0);
+    be.launch(KRankScan{nchunks, counts, totals}, 2 * NSHAPE, 64, KRankScan::smem_bytes(64));
     std::vector<int> tot(2 * NSHAPE);
     be.d2h(tot.data(), totals, sizeof(int) * 2 * NSHAPE);
     stats.ms_moments = toc(tph); tph = tic();

@@ -674,15 +674,29 @@ struct KRankCount {     // counts[(kind*NSHAPE + shape) * nchunks + chunk]
     c.par([&](int tid) { for (int i = tid; i < 2 * NSHAPE; i += c.nthreads()) counts[(long long)i * nchunks + c.block()] = hist[i]; });
   }
 };
-struct KRankScan {      // exclusive scan over chunks for every bin; one block per bin, serial (nchunks is small)
+struct KRankScan {      // exclusive scan over chunks for every bin; one block per bin: segment sums, scan of the sums, segment scans
   int nchunks; int* counts; int* totals;
+  static MCE_HD size_t smem_bytes(int nthreads) { return sizeof(int) * (nthreads + 1); }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    int* part = (int*)c.smem();
+    int* cc = counts + (long long)c.block() * nchunks;
+    const int NT = c.nthreads(), seg = (nchunks + NT - 1) / NT;
+    c.par([&](int tid) {
+      const int lo = tid * seg, hi = lo + seg < nchunks ? lo + seg : nchunks;
+      int acc = 0;
+      for (int i = lo; i < hi; i++) acc += cc[i];
+      part[tid] = acc;
+    });
     c.par([&](int tid) {
       if (tid != 0) return;
-      int* cc = counts + (long long)c.block() * nchunks;
       int acc = 0;
-      for (int i = 0; i < nchunks; i++) { int v = cc[i]; cc[i] = acc; acc += v; }
+      for (int t = 0; t < NT; t++) { const int v = part[t]; part[t] = acc; acc += v; }
       totals[c.block()] = acc;
+    });
+    c.par([&](int tid) {
+      const int lo = tid * seg, hi = lo + seg < nchunks ? lo + seg : nchunks;
+      int acc = part[tid];
+      for (int i = lo; i < hi; i++) { const int v = cc[i]; cc[i] = acc; acc += v; }
     });
   }
 };
