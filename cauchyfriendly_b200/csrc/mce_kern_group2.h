@@ -412,6 +412,14 @@ struct KGTable2T {
     c.par([&](int tid) { load_chunk(tid); if (tid == 0) sm->owner = -1; });
     const Group2Member* eR = &sm->mem[0];
     int nB = 0;
+    // A group rooted at a new child holds new children only (old terms sort first), so no candidate owns a parent's B memory and
+    // root election has no side effect.  When every member is certified negligible (load_member) the group dies right here,
+    // before its B-table is enumerated.
+    if (eR->is_child && ncomb <= G2_CHUNK) {
+      bool dead = true;
+      for (int k = 0; k < ncomb; k++) if (!sm->mem[k].skip || !sm->mem[k].is_child) dead = false;
+      if (dead) { *nB_out = 0; *k_out = ncomb; *rsel_out = -1; return false; }
+    }
     if (eR->is_child) {
       if (m <= d) {
         nB = 1 << (m - 1);
