@@ -13,8 +13,8 @@ from mceio import read_dump, read_scenario
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 # scenario -> last step replayed on the CPU
-ORACLE_CASES = {"lti3": 10, "lti4_2pnoise": 6, "syn5": 6, "leo5": 5, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 9, "syn8": 4}
-EMU_CASES = {"lti3": 8, "lti4_2pnoise": 3, "syn5": 4, "leo5": 5, "leo7": 6, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 7, "syn8": 4}
+ORACLE_CASES = {"lti3": 10, "lti4_2pnoise": 6, "syn5": 6, "leo5": 5, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 9, "syn8": 4, "homing3": 6}
+EMU_CASES = {"lti3": 8, "lti4_2pnoise": 3, "syn5": 4, "leo5": 5, "leo7": 6, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 7, "syn8": 4, "homing3": 6}
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -83,10 +83,10 @@ def _check2d(gold, got, steps):
             "%s: max abs diff %.3e" % (n, np.abs(gold[n] - got[n]).max())
 
 
-@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8"])
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8", "homing3"])
 def test_oracle_cpdf2d_matches_reference_golden(name, tmp_path):
     gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
-    steps = [k for k in cpdf_steps(gold) if k <= {"lti3": 8, "lti4_2pnoise": 6, "syn5": 6, "leo5": 5, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 9, "syn8": 4}[name]]
+    steps = [k for k in cpdf_steps(gold) if k <= {"lti3": 8, "lti4_2pnoise": 6, "syn5": 6, "leo5": 5, "lti2": 9, "lti3_3msmts": 12, "lti4_2msmts": 9, "syn8": 4, "homing3": 6}[name]]
     lo, hi, res = [float(v) for v in gold["cpdf1d/grid"]]
     out = str(tmp_path / "o.mced")
     cmd = [os.path.join(ROOT, "oracle", "_build", "mce_oracle_run"), os.path.join(GOLD, name + ".mces"), out, "--max-steps", str(max(steps)),
@@ -95,7 +95,7 @@ def test_oracle_cpdf2d_matches_reference_golden(name, tmp_path):
     _check2d(gold, read_dump(out), steps)
 
 
-@pytest.mark.parametrize("name,last", [("lti3", 8), ("syn5", 4), ("leo5", 5), ("leo7", 6), ("lti2", 9), ("lti3_3msmts", 12), ("lti4_2msmts", 7), ("syn8", 4)])
+@pytest.mark.parametrize("name,last", [("lti3", 8), ("syn5", 4), ("leo5", 5), ("leo7", 6), ("lti2", 9), ("lti3_3msmts", 12), ("lti4_2msmts", 7), ("syn8", 4), ("homing3", 6)])
 def test_emulated_cpdf2d_kernels_match_golden(emu, name, last):
     from harness import run_cpdf2d
     gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))

@@ -20,7 +20,7 @@ def _same(a, b, n):
     assert np.array_equal(a.view(np.uint64), np.ascontiguousarray(b).view(np.uint64)), "%s: max abs diff %.3e" % (n, np.abs(a - b).max())
 
 
-@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8"])
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8", "homing3"])
 def test_cpdf1d_matches_reference_golden(name):
     gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))
     got = run_cpdf1d(load_product(), read_scenario(os.path.join(GOLD, name + ".mces")), gold)
@@ -97,7 +97,7 @@ def test_branch_free_division_equals_ieee_division():
 CPDF2D_RTOL = 1e-9          # |z - z_ref| <= CPDF2D_RTOL * max|z_ref| over the grid
 
 
-@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8"])
+@pytest.mark.parametrize("name", ["lti3", "lti4_2pnoise", "syn5", "leo5", "leo7", "lti2", "lti3_3msmts", "lti4_2msmts", "syn8", "homing3"])
 def test_cpdf2d_matches_reference_golden(name):
     from harness import run_cpdf2d
     gold = read_dump(os.path.join(GOLD, name + ".cpdf.mced"))

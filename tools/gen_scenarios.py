@@ -100,10 +100,38 @@ def all_scenarios():
     return out
 
 
+def homing3():
+    """Homing-missile-shaped window (BASELINE.json configs[1], src/homing_missile.cpp:378-447, 520-682): 3 states (relative
+    position, relative velocity, target acceleration), one process noise, ONE CONTROL INPUT (the pursuer's acceleration command:
+    cmcc = 1, B and u passed to step()), a radar bearing linearised about the running estimate -- so H and gamma change every
+    step -- and the extended estimator's re-centring after every step (finalize_extended_moments, est:1358).  The closed loop
+    of the example (simulator, guidance law, time(NULL) seed) is replaced by a seeded open-loop recording of the same shape."""
+    n, steps, dt, tau, Vc, tf = 3, 8, 0.1, 2.0, 300.0, 10.0
+    rng = np.random.RandomState(2024)
+    Phi = np.array([[1.0, dt, dt * dt / 2.0], [0.0, 1.0, dt], [0.0, 0.0, np.exp(-dt / tau)]])
+    Gamma = np.array([[0.0], [0.0], [1.0]])
+    B = np.array([[-dt * dt / 2.0], [-dt], [0.0]])
+    beta = np.array([0.05])
+    max_shape = (steps - 1) * 1 + n
+    root_point, b_pert = _rand_vectors(311, n, max_shape)
+    s = Scenario(n, 1, 1, 1, steps, list(range(12)), root_point, b_pert, np.eye(n), np.array([0.6, 0.4, 0.3]), np.zeros(n))
+    x = np.array([0.5, -0.2, 0.3])
+    for k in range(steps):
+        t_k = (k + 1) * dt
+        u = np.array([3.0 * x[0] / ((tf - t_k) ** 2) + 0.4 * rng.standard_normal()])       # proportional-navigation-like command
+        x = Phi @ x + (B @ u) + Gamma[:, 0] * beta[0] * rng.standard_cauchy()
+        rng_h = 1.0 / (Vc * (tf - t_k + 1e-6))                                               # d atan(y / (Vc (tf - t))) / dy at y ~ 0
+        H = np.array([rng_h * Vc, 0.0, 0.0]) * (1.0 + 0.05 * k)                              # rescaled so that H is O(1) and varies per step
+        gamma = 0.08 * (1.0 + 0.1 * k)
+        z = float(H @ x + gamma * rng.standard_cauchy())
+        s.rec.append(StepRecord(z, float(gamma), Phi, Gamma, beta, H, B=B, u=u, shift_kind=1))
+    return "homing3", s
+
+
 if __name__ == "__main__":
     outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name, s in all_scenarios():
+    for name, s in all_scenarios() + [homing3()]:
         path = os.path.join(outdir, name + ".mces")
         write_scenario(path, s)
         print("wrote", path, "d=%d steps=%d records=%d" % (s.d, s.steps, len(s.rec)))

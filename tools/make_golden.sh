@@ -16,6 +16,7 @@ $R tests/golden/lti4_2pnoise.mces tests/golden/lti4_2pnoise.ref.mced --full-upto
 $R tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.ref.mced  --full-upto 5
 for n in 2 3 4 5 6 7 8; do $R tests/golden/syn$n.mces tests/golden/syn$n.ref.mced --full-upto 3; done
 $R tests/golden/leo7.mces         tests/golden/leo7.ref.mced         --full-upto 3
+$R tests/golden/homing3.mces      tests/golden/homing3.ref.mced      --full-upto 5    # control input (B, u) + own-mean re-centring
 $R tests/golden/leo5.mces         tests/golden/leo5.ref.mced         --full-upto 4 --max-steps 13
 # the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
 oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
@@ -32,3 +33,4 @@ $C tests/golden/lti2.mces         tests/golden/lti2.cpdf.mced         -2.0 2.0 0
 $C tests/golden/lti3_3msmts.mces  tests/golden/lti3_3msmts.cpdf.mced  -2.0 2.0 0.05  4,8,12 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
 $C tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.cpdf.mced  -2.0 2.0 0.05  3,7,9 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
 $C tests/golden/syn8.mces         tests/golden/syn8.cpdf.mced         -1.0 1.0 0.04  2,4 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
+$C tests/golden/homing3.mces      tests/golden/homing3.cpdf.mced      -1.0 1.0 0.02  3,6 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
