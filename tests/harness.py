@@ -286,3 +286,55 @@ def run_cpdf2d(lib, sc, gold, max_step=None):
     finally:
         s.close()
     return out
+
+
+def run_transforms(lib, sc, gold, k0):
+    """deterministic_time_prop / shift_cf_by_bias after k0 steps (oracle/ref_transforms.cpp): returns (arrays, problems) where
+    arrays follow the golden dump's names (t1/t2/t3 term lists, later moments) through the C ABI."""
+    d = sc.d
+    T = np.ascontiguousarray(gold["T"], np.float64)
+    bias = np.ascontiguousarray(gold["bias"], np.float64)
+    s = Session(lib, sc)
+    out = {}
+
+    def do_step(k):
+        r = sc.rec[k]
+        s.step(r)
+        mo = s.moments()
+        if r.shift_kind == SHIFT_EXPLICIT:
+            s.shift_b(r.delta, -1.0)
+        elif r.shift_kind == SHIFT_OWN_MEAN:
+            s.shift_b(np.array(mo.mean[: 2 * d])[0::2], -1.0)
+        return mo
+
+    def dump(pre):
+        cnt = s.counts(False)
+        for m in range(1, s.shape_range):
+            if cnt[m] > 0:
+                e = s.export_shape(m)
+                for nm in ("A", "p", "b"):
+                    out["%s/m%d/%s" % (pre, m, nm)] = e[nm]
+
+    try:
+        for k in range(k0):
+            do_step(k)
+        assert lib.mce_deterministic_time_prop(s.h, _dp(T), None, None) == 0
+        dump("t1")
+        assert lib.mce_shift_b(s.h, _dp(bias), 1.0) == 0            # shift_cf_by_bias, est:1312
+        dump("t2")
+        r0 = sc.rec[k0]
+        if r0.B is not None:
+            B = np.ascontiguousarray(r0.B, np.float64); u = np.ascontiguousarray(r0.u, np.float64)
+            assert lib.mce_deterministic_time_prop(s.h, _dp(T), _dp(B), _dp(u)) == 0
+            dump("t3")
+        for k in range(k0, len(sc.rec)):
+            mo = do_step(k)
+            mom = np.zeros(1 + d + d * d, np.complex128)
+            mom[0] = complex(mo.fz[0], mo.fz[1])                         # the public field est.fz after the whole step
+            mom[1:1 + d] = np.array(mo.mean[: 2 * d]).view(np.complex128)
+            mom[1 + d:] = np.array(mo.cov[: 2 * d * d]).view(np.complex128)
+            out["s%d/moments" % (k + 1)] = mom
+            out["s%d/info" % (k + 1)] = np.array([mo.Nt, mo.numeric_moment_errors], np.int32)
+    finally:
+        s.close()
+    return out

@@ -34,3 +34,6 @@ $C tests/golden/lti3_3msmts.mces  tests/golden/lti3_3msmts.cpdf.mced  -2.0 2.0 0
 $C tests/golden/lti4_2msmts.mces  tests/golden/lti4_2msmts.cpdf.mced  -2.0 2.0 0.05  3,7,9 --2d -2.0 2.0 0.2 -2.0 2.0 0.2
 $C tests/golden/syn8.mces         tests/golden/syn8.cpdf.mced         -1.0 1.0 0.04  2,4 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
 $C tests/golden/homing3.mces      tests/golden/homing3.cpdf.mced      -1.0 1.0 0.02  3,6 --2d -1.0 1.0 0.1 -1.0 1.0 0.1
+# deterministic_time_prop / shift_cf_by_bias golden vectors (oracle/ref_transforms.cpp)
+oracle/_ref/ref_transforms_cpu1 tests/golden/lti3.mces    tests/golden/lti3.transforms.mced    4
+oracle/_ref/ref_transforms_cpu1 tests/golden/homing3.mces tests/golden/homing3.transforms.mced 4
