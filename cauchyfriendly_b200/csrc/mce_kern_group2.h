@@ -154,6 +154,17 @@ struct KTpDce2 {
 
 constexpr int G2_CHUNK = 32;      // members staged per chunk
 
+// The "member is not negligible" flag is raised by whichever thread finds a qualifying cell and only ever read to skip a test:
+// an intended benign race (every writer stores 1).  Building with -DMCE_RACECHECK turns both sides into atomics so that
+// compute-sanitizer's racecheck reports everything else (tools/sanitize_pass.py).
+#if defined(MCE_RACECHECK) && defined(__CUDA_ARCH__)
+#define G2_FLAG_READ(f) atomicOr((f), 0)
+#define G2_FLAG_SET(f) atomicExch((f), 1)
+#else
+#define G2_FLAG_READ(f) (*(volatile int*)(f))
+#define G2_FLAG_SET(f) (*(f) = 1)
+#endif
+
 struct Group2Member {              // everything the kernel needs to know about one member, gathered in one parallel phase
   int ti, parent, gidp, phc, pc, own_cells;
   long long rk_off;                // parent's rank structure inside prev.rbm / prev.rpf
@@ -381,12 +392,12 @@ struct KGTable2T {
     if (!cdiv2_fast(gp, vp, gm, vm, &rp, &rm)) g2_cdiv_pair_full(gp, vp, gm, vm, &rp, &rm);   // rare: guards, absent cells (0 numerators)
     cplx g = csub(rp, rm);
     g = cscale(g, sp.gscale);
-    if (!*(volatile int*)flag) {           // |G| only matters until one cell is found non-negligible (flat:242-247)
+    if (!G2_FLAG_READ(flag)) {             // |G| only matters until one cell is found non-negligible (flat:242-247)
       // max(|re|,|im|) <= |G| <= |re|+|im| and rounding is monotone, so the two cheap bounds decide almost every cell
       // exactly as `psq * cabs(G) > eps` would; hypot runs only in between.
       const double ar = fabs(g.re), ai = fabs(g.im), mx = ar > ai ? ar : ai;
-      if ((e->psq * mx) > TERM_APPROXIMATION_EPS) *flag = 1;
-      else if ((e->psq * (ar + ai)) > TERM_APPROXIMATION_EPS) { if ((e->psq * cabs_(g)) > TERM_APPROXIMATION_EPS) *flag = 1; }
+      if ((e->psq * mx) > TERM_APPROXIMATION_EPS) G2_FLAG_SET(flag);
+      else if ((e->psq * (ar + ai)) > TERM_APPROXIMATION_EPS) { if ((e->psq * cabs_(g)) > TERM_APPROXIMATION_EPS) G2_FLAG_SET(flag); }
     }
     return g;
   }
