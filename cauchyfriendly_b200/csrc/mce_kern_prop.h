@@ -740,7 +740,7 @@ struct KRegroup {
           double* bo = tv.b + gt * d; const double* bi = sl.b + slot * d;
           for (int i = 0; i < d; i++) bo[i] = bi[i];
           const unsigned long long* ci = (const unsigned long long*)(sl.cmap + slot * MAXM); unsigned long long* co = (unsigned long long*)(tv.cmap + gt * MAXM);
-          for (int i = 0; i < MAXM / 8; i++) co[i] = ci[i];
+          if (me.flags & 2) for (int i = 0; i < MAXM / 8; i++) co[i] = ci[i];       // only coaligned children own a map (initcheck-clean)
           tv.meta[gt] = me; slot_of_term[gt] = slot;
         }
         desc[k] = e;
