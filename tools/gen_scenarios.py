@@ -128,10 +128,38 @@ def homing3():
     return "homing3", s
 
 
+# Deep-DECLARED windows: the same recordings with a larger declared `steps`, so that max_shape = d + (steps-1) pncc
+# (est:97) exceeds 16 and the engine takes its max_shape > 16 kernels (sort/hash G-table and DCE-TP variants; the bitmap
+# kernels serve max_shape <= 16 only) while the replayed prefix stays cheap for the CPU reference.  The reference supports
+# up to 31 hyperplanes (est:231-235).  name -> (source scenario, declared steps, records kept)
+DEEP = {"lti3_deep": ("lti3", 20, 9), "lti4_2pnoise_deep": ("lti4_2pnoise", 10, 6), "leo5_deep": ("leo5", 13, 8),
+        "lti3_3msmts_deep": ("lti3_3msmts", 16, 12)}
+
+
+def deepen(outdir, name):
+    from mceio import read_scenario
+    src, steps, nrec = DEEP[name]
+    s = read_scenario(os.path.join(outdir, src + ".mces"))
+    s.steps = steps
+    rng = np.random.RandomState(9000 + steps)
+    extra = 2.0 * (rng.randint(0, 2**31 - 1, s.max_shape) + 1.0) / 2.0**31 - 1.0
+    s.b_pert = np.concatenate([s.b_pert, extra])[: s.max_shape]
+    s.rec = s.rec[:nrec]
+    return name, s
+
+
 if __name__ == "__main__":
     outdir = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(__file__), "..", "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name, s in all_scenarios() + [homing3()]:
+    made = all_scenarios() + [homing3()]
+    for name, s in made:
         path = os.path.join(outdir, name + ".mces")
         write_scenario(path, s)
         print("wrote", path, "d=%d steps=%d records=%d" % (s.d, s.steps, len(s.rec)))
+    for name in sorted(DEEP):
+        if not os.path.exists(os.path.join(outdir, DEEP[name][0] + ".mces")):
+            continue        # leo5.mces is recorded by oracle/_ref/ref_gen_leo5 (tools/make_golden.sh runs this script again after it)
+        name, s = deepen(outdir, name)
+        path = os.path.join(outdir, name + ".mces")
+        write_scenario(path, s)
+        print("wrote", path, "d=%d steps=%d max_shape=%d records=%d" % (s.d, s.steps, s.max_shape, len(s.rec)))
