@@ -31,7 +31,7 @@ EXCHANGE_FN = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_lo
 
 # every symbol include/mce_b200.h declares
 SYMBOLS = ["mce_default_options", "mce_create", "mce_destroy", "mce_step", "mce_get_moments", "mce_shape_range",
-           "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_shift_b",
+           "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_set_first_term", "mce_shift_b",
            "mce_deterministic_time_prop", "mce_export_shape", "mce_cpdf_grid_count", "mce_marginal_1d_points", "mce_marginal_1d_grid", "mce_marginal_2d_points", "mce_marginal_2d_grid", "mce_cpdf_last_ms", "mce_get_step_stats", "mce_debug_div_selftest", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback",
            "mce_last_error", "mce_version"]
 
@@ -51,6 +51,7 @@ def bind(lib):
     lib.mce_set_master_step.restype = None
     lib.mce_reset.argtypes = [ct.c_void_p]
     lib.mce_reinitialize_start_statistics.argtypes = [ct.c_void_p, dp, dp, dp]
+    lib.mce_set_first_term.argtypes = [ct.c_void_p, dp, dp, dp]
     lib.mce_shift_b.argtypes = [ct.c_void_p, dp, ct.c_double]
     lib.mce_deterministic_time_prop.argtypes = [ct.c_void_p, dp, dp, dp]
     lib.mce_export_shape.argtypes = [ct.c_void_p, ct.c_int, ip, ct.POINTER(ct.c_longlong), dp, dp, dp, ip, ct.POINTER(ct.c_uint32), dp]

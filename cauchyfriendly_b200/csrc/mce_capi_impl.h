@@ -88,6 +88,14 @@ int mce_reinitialize_start_statistics(mce_handle* h, const double* A0, const dou
   if (!h || !A0 || !p0 || !b0) return MCE_ERR_BAD_ARG;
   EngineT* e = h->e;
   e->A0.assign(A0, A0 + e->d * e->d); e->p0.assign(p0, p0 + e->d); e->b0.assign(b0, b0 + e->d);
+  e->A1 = e->A0; e->p1 = e->p0; e->b1 = e->b0;      // est:1306-1308: the first term is re-seeded at once
+  return 0;
+}
+int mce_set_first_term(mce_handle* h, const double* A, const double* p, const double* b) {
+  if (!h || !A || !p || !b) return MCE_ERR_BAD_ARG;
+  EngineT* e = h->e;
+  if (e->master_step != 0) { g_mce_error = "mce_set_first_term: only before the first step of a window (master_step == 0)"; return MCE_ERR_STATE; }
+  e->A1.assign(A, A + e->d * e->d); e->p1.assign(p, p + e->d); e->b1.assign(b, b + e->d);
   return 0;
 }
 int mce_shift_b(mce_handle* h, const double* delta, double sign) {

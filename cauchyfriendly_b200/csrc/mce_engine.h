@@ -94,6 +94,7 @@ class Engine {
   int master_step = 0, Nt = 1, Nt_muc = 1, numeric_moment_errors = 0, skip_post_mu = 0, print_basic_info = 0;
   int tr_order[12];
   std::vector<double> A0, p0, b0, root_point, b_pert;
+  std::vector<double> A1, p1, b1;   // the first term as the next first step will read it (the reference keeps it in childterms_workspace: term:772-785)
   double G_SCALE_FACTOR = 0;
   cplx fz, last_fz, fz_mu; std::vector<cplx> mean, var, last_mean, last_var, mean_mu, var_mu;   // *_mu: as of the end of the measurement update
   std::vector<int> terms_per_shape, muc_per_shape;
@@ -134,6 +135,7 @@ class Engine {
     print_basic_info = print_info;
     for (int i = 0; i < 12; i++) tr_order[i] = tr_order_ ? tr_order_[i] : i;
     A0.assign(A0_, A0_ + d * d); p0.assign(p0_, p0_ + d); b0.assign(b0_, b0_ + d);
+    A1 = A0; p1 = p0; b1 = b0;
     root_point.assign(root_point_, root_point_ + d);
     b_pert.assign(MAXM, 0.0);
     for (int i = 0; i < max_shape && i < MAXM; i++) b_pert[i] = b_pert_[i];
@@ -301,9 +303,9 @@ class Engine {
     std::vector<int> groups(NSHAPE, 0); groups[d] = d + 1;
     fill_gen_layout(ng, groups);
     double* init = (double*)initBuf.ensure(sizeof(double) * (d * d + 2 * d));
-    be.h2d(init, A0.data(), sizeof(double) * d * d);
-    be.h2d(init + d * d, p0.data(), sizeof(double) * d);
-    be.h2d(init + d * d + d, b0.data(), sizeof(double) * d);
+    be.h2d(init, A1.data(), sizeof(double) * d * d);
+    be.h2d(init + d * d, p1.data(), sizeof(double) * d);
+    be.h2d(init + d * d + d, b1.data(), sizeof(double) * d);
     const int nq = 1 + d + d * d;
     double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
     int* cnt = (int*)unkBuf.ensure(64);
@@ -554,7 +556,7 @@ class Engine {
       std::vector<int> still;
       for (int m : active) if (nu[m] != 0) still.push_back(m);
       active.swap(still);
-      if (rounds > (int)nterms + 4) { error = "FTR resolution did not converge"; return -3; }
+      if (rounds > (int)nterms + 4) { be.side_join(); error = "FTR resolution did not converge"; return -6; }
     }
     stats.ftr_rounds_max = rounds;
     if (capture) for (int m : shapes) capture_shape(tv, m, F_all + tv.t_begin[m], ws, with_tp);
@@ -800,6 +802,10 @@ class Engine {
   // ------------------------------------------------------------------------------------------
   int shift_b(const double* delta, double sign) {
     if (skip_post_mu) return 0;                 // est:1314, 1365
+    if (master_step == 0) {                     // before the first step the CF is the initial term (terms_dp[d][0], est:1316-1326)
+      for (int j = 0; j < d; j++) { if (sign < 0) b1[j] -= delta[j]; else b1[j] += delta[j]; }
+      return 0;
+    }
     GenStore& g = gen[cur];
     if (g.v.n_alive == 0) return 0;
     KShiftB k; k.gen = g.v; k.d = d; k.sign = sign;
@@ -809,10 +815,21 @@ class Engine {
   }
   int det_time_prop(const double* T, const double* B, const double* u) {
     GenStore& g = gen[cur];
-    if (g.v.n_alive == 0 || master_step == 0) return 0;
     KDetTimeProp k; memset(&k, 0, sizeof(k)); k.gen = g.v; k.d = d;
     for (int i = 0; i < d * d; i++) k.T[i] = T[i];
     if (B && u && cmcc > 0) { k.has_bu = 1; for (int i = 0; i < d; i++) { double s = 0.0; for (int j = 0; j < cmcc; j++) s += B[i * cmcc + j] * u[j]; k.bu[i] = s; } }
+    if (master_step == 0) {                     // the initial term is propagated like any other (est:1346-1354 walks terms_dp[d][0]); d x d host work, same operation order as KDetTimeProp
+      double work[MAXD];
+      for (int i = 0; i < d; i++) {
+        for (int kk = 0; kk < d; kk++) work[kk] = A1[i * d + kk];
+        for (int j = 0; j < d; j++) { double sum = 0.0; for (int kk = 0; kk < d; kk++) sum += work[kk] * T[kk + j * d]; A1[i * d + j] = sum; }
+      }
+      for (int kk = 0; kk < d; kk++) work[kk] = b1[kk];
+      for (int i = 0; i < d; i++) { double sum = 0.0; for (int j = 0; j < d; j++) sum += T[i * d + j] * work[j]; b1[i] = sum; }
+      if (k.has_bu) for (int i = 0; i < d; i++) b1[i] += 1.0 * k.bu[i];
+      return 0;
+    }
+    if (g.v.n_alive == 0) return 0;
     be.launch(k, (g.v.n_alive + 127) / 128, 128, 0);
     return 0;
   }
@@ -820,6 +837,7 @@ class Engine {
     master_step = 0; Nt = 1; numeric_moment_errors = 0; finished = false; skip_post_mu = 0;
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = 1;
     gen[0].v.n_alive = 0; gen[1].v.n_alive = 0;
+    A1 = A0; p1 = p0; b1 = b0;                   // setup_first_term(A0_init, p0_init, b0_init), est:1280
     cur = 0;          // same buffer parity on every pass of a window: the grow-only buffers settle after the first pass
   }
 

@@ -57,6 +57,11 @@ struct CauchyEstimator
     int* B_dense;
     ChildTermWorkSpace childterms_workspace;
     bool auto_mirror;
+    // While master_step == 0 the CF is ONE host term, terms_dp[d][0], whose A / p / b point into childterms_workspace exactly as
+    // in the reference (setup_first_term, cauchy_term.hpp:772-785).  Callers write it through those pointers
+    // (pycauchy_single_step_reset, pycauchy.hpp:818) and through shift_cf_by_bias / deterministic_time_prop before the first
+    // step; step() hands its current contents to the device (mce_set_first_term) when master_step == 0.
+    bool first_term_live;
 
     CauchyEstimator(double* _A0, double* _p0, double* _b0, int _steps, int _d, int _cmcc, int _pncc, int _p, const bool _print_basic_info)
     {
@@ -86,6 +91,8 @@ struct CauchyEstimator
         terms_dp = (CauchyTerm**) calloc(shape_range, sizeof(CauchyTerm*));
         B_dense = NULL; auto_mirror = false;
         childterms_workspace.init(shape_range-1, d);
+        first_term_live = false;
+        seed_first_term();
         print_basic_info = _print_basic_info;
         skip_post_mu = false; win_num = 0; numeric_moment_errors = 0; G_SCALE_FACTOR = 0;
         fz = MAKE_CMPLX(0, 0);
@@ -102,8 +109,24 @@ struct CauchyEstimator
         }
     }
 
+    // est:1262-1280 (reset) / est:110-123 (constructor): terms_dp[d] = d+1 terms, the first one set up from the start statistics
+    void seed_first_term()
+    {
+        free_host_mirror();
+        terms_dp[d] = (CauchyTerm*) calloc(d+1, sizeof(CauchyTerm));
+        null_ptr_check(terms_dp[d]);
+        first_term_live = true;
+        setup_first_term(&childterms_workspace, terms_dp[d], A0_init, p0_init, b0_init, d);
+    }
+
     void free_host_mirror()
     {
+        if(first_term_live)
+        {
+            free(terms_dp[d]);      // its arrays belong to childterms_workspace
+            terms_dp[d] = NULL;
+            first_term_live = false;
+        }
         for(int m = 0; m < shape_range; m++)
         {
             if(terms_dp[m] != NULL)
@@ -220,6 +243,14 @@ struct CauchyEstimator
         set_function_pointers();        // est:1213
         CPUTimer tmr; tmr.tic();
         mce_set_master_step(handle, master_step);      // callers may have written the field (cauchy_windows.hpp:538,659)
+        if(master_step == 0)
+        {
+            // step_first reads the initial term where the reference keeps it (est:1181-1183: terms_dp[d][0] -> workspace)
+            if(!first_term_live)
+                seed_first_term();
+            mce_set_first_term(handle, terms_dp[d][0].A, terms_dp[d][0].p, terms_dp[d][0].b);
+            free_host_mirror();     // the initial term is consumed; terms_dp is a lazily filled mirror from here on
+        }
         int rc = mce_step(handle, msmt, Phi, Gamma, beta, H, gamma, B, u);
         if(rc < 0)
         {
@@ -256,11 +287,14 @@ struct CauchyEstimator
 
     void reset()        // est:1247
     {
+        // callers overwrite A0_init / p0_init / b0_init in place before calling reset() (pycauchy_single_step_reset,
+        // pycauchy.hpp:807-815); the reference re-seeds from those fields (est:1280), so they are pushed first
+        mce_reinitialize_start_statistics(handle, A0_init, p0_init, b0_init);
         mce_reset(handle);
-        free_host_mirror();
         memset(terms_per_shape, 0, shape_range * sizeof(int));
         terms_per_shape[d] = 1;
         Nt = 1; master_step = 0; numeric_moment_errors = 0;
+        seed_first_term();
     }
 
     void reinitialize_start_statistics(double* A_0, double* p_0, double* b_0)     // est:1302
@@ -269,16 +303,38 @@ struct CauchyEstimator
         memcpy(p0_init, p_0, d*sizeof(double));
         memcpy(b0_init, b_0, d*sizeof(double));
         mce_reinitialize_start_statistics(handle, A0_init, p0_init, b0_init);
+        if(master_step == 0)
+            seed_first_term();      // est:1307-1308
     }
 
-    void shift_cf_by_bias(double* bias) { mce_shift_b(handle, bias, 1.0); }       // est:1312
+    void shift_cf_by_bias(double* bias)       // est:1312
+    {
+        if(master_step == 0 && first_term_live)
+        {
+            if(!skip_post_mu)
+                for(int j = 0; j < d; j++)
+                    terms_dp[d][0].b[j] += bias[j];
+            return;
+        }
+        mce_shift_b(handle, bias, 1.0);
+    }
 
     void deterministic_time_prop(double* Phi, double* B, double* u)               // est:1331
     {
-        if( mce_deterministic_time_prop(handle, Phi, B, u) < 0 )
+        if( (B == NULL) != (u == NULL) )
         {
             printf("Illegal use of arguments B and u! Either B or u set, both not both!\n");
             assert(false);
+        }
+        if(master_step == 0 && first_term_live)
+        {
+            terms_dp[d][0].time_prop(Phi, B, u, (B != NULL) ? cmcc : 0);      // est:1346-1354 on the initial term
+            return;
+        }
+        if( mce_deterministic_time_prop(handle, Phi, B, u) < 0 )
+        {
+            printf(RED "[CauchyEstimator/B200] deterministic_time_prop failed: %s" NC "\n", mce_last_error());
+            exit(1);
         }
     }
 

@@ -31,7 +31,8 @@ enum {
   MCE_ERR_BAD_ARG = -2,
   MCE_ERR_CUDA = -3,
   MCE_ERR_STATE = -4,     /* e.g. stepping past num_estimation_steps (the reference exit(1)s, est:1220-1225) */
-  MCE_ERR_CAPACITY = -5
+  MCE_ERR_CAPACITY = -5,
+  MCE_ERR_FTR = -6        /* the term-reduction rounds did not reach a fixed point (cannot happen for finite inputs) */
 };
 
 typedef struct mce_options {
@@ -85,6 +86,10 @@ int mce_get_terms_per_shape(mce_handle* h, int* counts /*[shape_range]*/, int af
 void mce_set_master_step(mce_handle* h, int master_step);   /* callers write this field: cauchy_windows.hpp:538,659 */
 int mce_reset(mce_handle* h);                                                       /* reset(), est:1247-1300 */
 int mce_reinitialize_start_statistics(mce_handle* h, const double* A0, const double* p0, const double* b0); /* est:1302 */
+/* The initial term as the next first step reads it, WITHOUT changing the statistics reset() re-seeds from.  The reference
+ * keeps that term in childterms_workspace (setup_first_term, cauchy_term.hpp:772-785); callers write it directly
+ * (pycauchy_single_step_reset, pycauchy.hpp:818).  Only valid while master_step == 0. */
+int mce_set_first_term(mce_handle* h, const double* A, const double* p, const double* b);
 /* b <- b + sign*delta on every term: finalize_extended_moments (sign=-1, delta=Re mean; est:1358-1394) and
  * shift_cf_by_bias (sign=+1; est:1312-1328). A no-op after the window's last step, like the reference. */
 int mce_shift_b(mce_handle* h, const double* delta, double sign);

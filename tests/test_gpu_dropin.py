@@ -82,3 +82,82 @@ def test_device_cpdf_dispatcher_equals_the_reference_cpu_cpdf(tmp_path):
     assert "cpdf1d drop-in OK" in out, out[-2000:]
     m = re.search(r"compared (\d+) grid values, (\d+) differ", out)
     assert m and int(m.group(1)) == 7 * 3 * 401 and int(m.group(2)) == 0
+
+
+def test_leo5_example_runs_on_the_gpu_path(tmp_path):
+    """src/leo_satellite_5state.cpp unchanged (BASELINE.json configs[2]: 5-state LEO EMCE, 14 measurement updates, closed loop
+    through finalize_extended_moments): same counts and moments as the NUM_CPUS=1 reference (tests/golden/ex_leo5_cpu1.txt)."""
+    exe = os.path.join(ROOT, "build", "dropin", "leo_satellite_5state")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    work = tmp_path / "bin"
+    work.mkdir()
+    (tmp_path / "log" / "leo5" / "dense" / "w8").mkdir(parents=True)
+    c_our, m_our = _parse(_run(exe, str(work)))
+    c_ref, m_ref = _golden("ex_leo5_cpu1")
+    assert len(m_ref) == 14
+    assert c_our == c_ref
+    assert m_our == m_ref
+
+
+def test_swig_shim_reset_paths_match_the_reference(tmp_path):
+    """tests/dropin/pycauchy_dropin.cpp: the reference's pycauchy.hpp (what the Swig module and the mex files call) driven from a
+    C++ main -- steps, pycauchy_single_step_reset in both of its branches (reset() re-seeding from A0_init written in place;
+    setup_first_term at master_step == 0), deterministic transforms before and after the first step.  The text must equal the
+    output of the same program built from the unmodified reference (tests/golden/ex_pycauchy_cpu1.txt), digit for digit."""
+    exe = os.path.join(ROOT, "build", "dropin", "pycauchy_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    ours = [l for l in _run(exe, str(tmp_path)).splitlines() if l.startswith(("#", "z ", "  xhat", "  Phat", "  cerr", "pycauchy"))]
+    gold = open(os.path.join(ROOT, "tests", "golden", "ex_pycauchy_cpu1.txt")).read().splitlines()
+    assert len(gold) == 78 and gold[-1] == "pycauchy drop-in done"
+    diff = [(i, a, b) for i, (a, b) in enumerate(zip(gold, ours)) if a != b]
+    assert len(ours) == len(gold) and not diff, "first differing lines:\n" + "\n".join("%d\n  ref %s\n  got %s" % t for t in diff[:5])
+
+
+def _bank_logs_equal(gold_dir, got_dir, files):
+    bad = []
+    for f in files:
+        a = open(os.path.join(gold_dir, f)).read().split()
+        b = open(os.path.join(got_dir, f)).read().split()
+        if a != b:
+            n = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
+            bad.append("%s: %d of %d tokens differ" % (f, n, len(a)))
+    return bad
+
+
+def test_reference_window_bank_logs_match_the_reference(tmp_path):
+    """The reference's SlidingWindowManager (8 forked windows, each with its own estimator and CUDA context) on the inputs of
+    src/window_manager.cpp (srand(11), 201 measurements), logging enabled (tests/dropin/winbank_dropin.cpp): the bank's
+    conditional means / covariances / normalisation factors / error codes -- printed with 16 decimals -- must equal the logs
+    of the same program built from the unmodified NUM_CPUS=1 reference (tests/golden/winbank_cpu1/)."""
+    exe = os.path.join(ROOT, "build", "dropin", "winbank_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    logs = tmp_path / "logs"
+    logs.mkdir()
+    out = subprocess.run([exe, str(logs)], cwd=str(tmp_path), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500).stdout.decode(errors="replace")
+    assert "winbank drop-in done: 201 measurements" in out, out[-2000:]
+    files = ["cond_means.txt", "cond_covars.txt", "norm_factors.txt", "numeric_error_codes.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt", "cerr_norm_factors.txt"]
+    bad = _bank_logs_equal(os.path.join(ROOT, "tests", "golden", "winbank_cpu1"), str(logs), files)
+    assert not bad, "\n".join(bad)
+
+
+def test_homing_missile_example_matches_the_reference(tmp_path):
+    """src/homing_missile.cpp unchanged (BASELINE.json configs[1]: 3-state nonlinear EMCE with a control input, 8 windows, 99
+    steps, CLOSED LOOP -- the guidance command is computed from the bank's estimate, so any deviation feeds back).  time() is
+    pinned to the author's seed by an LD_PRELOAD shim (tests/dropin/fixed_time.c).  Controls, measurements and every bank log
+    must equal those of the unmodified NUM_CPUS=1 reference (tests/golden/homing_cpu1/)."""
+    exe = os.path.join(ROOT, "build", "dropin", "homing_missile")
+    shim = os.path.join(ROOT, "build", "dropin", "fixed_time.so")
+    if not os.path.exists(exe) or not os.path.exists(shim):
+        pytest.skip("drop-in example binaries not built (needs /root/reference at build time: tools/build_dropin.sh)")
+    logs = tmp_path / "hm"
+    logs.mkdir()
+    env = dict(os.environ, LD_PRELOAD=shim)
+    out = subprocess.run([exe, "8", str(logs), "5.0", "1.3", "1"], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=1500).stdout.decode(errors="replace")
+    assert "Seeding with 1658778374" in out and "All children have exited" in out, out[-2000:]
+    files = ["cond_means.txt", "cond_covars.txt", "norm_factors.txt", "numeric_error_codes.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt", "cerr_norm_factors.txt",
+             "cauchy_controls.txt", "cauchy_with_controller_msmts.txt", "cauchy_with_controller_true_states.txt"]
+    bad = _bank_logs_equal(os.path.join(ROOT, "tests", "golden", "homing_cpu1"), str(logs / "w8_bs5_sas13" / "mct1"), files)
+    assert not bad, "\n".join(bad)

@@ -7,19 +7,23 @@ set -e
 REF=${REF:-/root/reference}
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 OV=$ROOT/build/overlay
-rm -rf "$OV" && mkdir -p "$OV/include" "$OV/src" "$ROOT/build/dropin"
+rm -rf "$OV" && mkdir -p "$OV/include" "$OV/src" "$OV/scripts/swig/cauchy" "$OV/tests" "$ROOT/build/dropin"
 for f in "$REF"/include/*; do ln -s "$f" "$OV/include/"; done
 for f in "$REF"/src/*; do ln -s "$f" "$OV/src/"; done
+ln -s "$REF/scripts/swig/cauchy/pycauchy.hpp" "$OV/scripts/swig/cauchy/pycauchy.hpp"
+for f in "$ROOT"/tests/dropin/*.cpp; do ln -s "$f" "$OV/tests/"; done
 rm "$OV/include/cauchy_estimator.hpp"
 ln -s "$ROOT/include/cauchy_estimator.hpp" "$OV/include/cauchy_estimator.hpp"
-for t in cauchy_estimator leo_satellite_7state_gps window_manager; do
+for t in cauchy_estimator leo_satellite_7state_gps window_manager homing_missile leo_satellite_5state; do
   g++ -O3 -w -ffp-contract=off -I"$ROOT/include" "$OV/src/$t.cpp" -o "$ROOT/build/dropin/$t" \
       -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
   echo "built build/dropin/$t"
 done
 # the device cpdf dispatcher checked against the reference's own CPU cpdf code over the host mirror (tests/dropin/cpdf1d_dropin.cpp)
-mkdir -p "$OV/tests"
-ln -sf "$ROOT/tests/dropin/cpdf1d_dropin.cpp" "$OV/tests/cpdf1d_dropin.cpp"
-g++ -O3 -w -ffp-contract=off -I"$OV/include" -I"$ROOT/include" "$OV/tests/cpdf1d_dropin.cpp" -o "$ROOT/build/dropin/cpdf1d_dropin" \
-    -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
-echo "built build/dropin/cpdf1d_dropin"
+# ... the Swig shim driven from C++ (tests/dropin/pycauchy_dropin.cpp) and the window bank with logging (winbank_dropin.cpp)
+for t in cpdf1d_dropin pycauchy_dropin winbank_dropin; do
+  g++ -O3 -w -ffp-contract=off -I"$OV/include" -I"$ROOT/include" "$OV/tests/$t.cpp" -o "$ROOT/build/dropin/$t" \
+      -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
+  echo "built build/dropin/$t"
+done
+gcc -O2 -shared -fPIC -o "$ROOT/build/dropin/fixed_time.so" "$ROOT/tests/dropin/fixed_time.c"
