@@ -13,7 +13,8 @@ One bench *step* = one full pass of that 12-MU window through CauchyEstimator::s
   N > 1  : one independent window per GPU (the reference's SlidingWindowManager runs one estimator process per
            window, cauchy_windows.hpp:353-376), aggregate child terms/s, max-over-ranks time.  scaling = "weak".
 --impl reference times the reference's own CPU implementation (oracle/_ref/ref_run_cpu8, the unmodified
-reference compiled with its default NUM_CPUS = 8) on a bounded prefix of the same window.
+reference compiled with its default NUM_CPUS = 8) on the SAME full window (one pass; `config` is identical in both
+arms) and, for repeatability, on the prefix MUs 1..9, which both arms report as `matched`.
 """
 import argparse
 import json
@@ -101,32 +102,58 @@ def run_reference_sample(n_mu):
     return kind, rows, step_ms, wall
 
 
+MATCHED_MUS = 9          # prefix of the window both arms also report on its own (cheap enough to repeat on the CPU)
+
+
+def _config(n_mus):
+    """Identical in both arms: the workload (inputs) both time.  Everything arm-specific lives in other keys of the line --
+    including the child-term count: the reference's 8-thread build walks the terms in another order than its 1-thread build
+    (the canonical order this repository reproduces bit for bit), elects other reduction-group roots and from MU 10 on carries
+    ~13 % more terms through the same window (2 402 755 child terms against 2 115 431)."""
+    return {"workload": WORKLOAD, "mus_per_step": n_mus}
+
+
 def reference_arm(args):
+    """The reference's own CPU implementation (unmodified, NUM_CPUS = 8 pthreads) on this box's host cores.
+    `value` is measured on the SAME work the GPU arm times: the full 12-MU window, run --ref-full-passes times (default 1,
+    about half a minute).  The remaining steps / warm-ups are the bounded sample MUs 1..9 of the same window, reported as
+    `matched` (the GPU arm reports the same prefix from its per-MU CUDA events), so that the K + W passes end within minutes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # size the sample so that (steps + warmup) passes end within a few minutes: MU k costs about 2.2x MU k-1
-    budget_s = 150.0 / max(1, args.steps + args.warmup)
-    kind, rows, ms, _ = run_reference_sample(8)
-    n_mu = 8
-    est = ms / 1e3
-    while n_mu < 11 and est * 3.2 <= budget_s:      # predicted cumulative cost of one more MU
-        est *= 3.2
-        n_mu += 1
-    for _ in range(args.warmup):
-        run_reference_sample(n_mu)
-    tot_ms, tot_child = 0.0, 0
-    for _ in range(args.steps):
-        kind, rows, ms, _ = run_reference_sample(n_mu)
-        tot_ms += ms
-        tot_child += _child_terms(rows)
+    for _ in range(min(1, args.warmup)):
+        run_reference_sample(MATCHED_MUS)
+    full = []
+    for _ in range(max(1, args.ref_full_passes)):
+        kind, rows, ms, _ = run_reference_sample(12)
+        full.append((rows, ms))
+    pre_ms, pre_child, n_pre = 0.0, 0, 0
+    budget_s = 120.0
+    t0 = time.time()
+    for _ in range(max(0, args.steps - len(full))):
+        if time.time() - t0 > budget_s:
+            break
+        kind, rows, ms, _ = run_reference_sample(MATCHED_MUS)
+        pre_ms += ms
+        pre_child += _child_terms(rows)
+        n_pre += 1
+    if n_pre == 0:          # the prefix of a full pass is the same computation
+        rows, _ = full[0]
+        pre_ms = sum(r[3] for r in rows[:MATCHED_MUS]); pre_child = _child_terms(rows[:MATCHED_MUS]); n_pre = 1
+    tot_ms = sum(ms for _, ms in full)
+    tot_child = sum(_child_terms(rows) for rows, _ in full)
     value = tot_child / (tot_ms / 1e3)
     cores = 8 if kind == "reference" else 1
-    sample = "MUs 1..%d of the 12-MU window per step (%d child terms), %s" % (
-        n_mu, tot_child // max(1, args.steps), "unmodified reference, NUM_CPUS=8 pthreads" if kind == "reference" else "plain-C oracle port, 1 thread")
+    who = "unmodified reference, NUM_CPUS=8 pthreads" if kind == "reference" else "plain-C oracle port, 1 thread"
+    sample = "the full 12-MU window, %d pass(es) (%d child terms, %.1f s of step() time each); %d further passes of MUs 1..%d as `matched`; %s" % (
+        len(full), tot_child // len(full), tot_ms / 1e3 / len(full), n_pre, MATCHED_MUS, who)
+    heaviest = max(full[0][0], key=lambda r: r[3])
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "child terms/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": tot_ms / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_mus": n_mu},
+            "warmup": args.warmup, "ms_per_step": tot_ms / len(full), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": _config(12), "child_terms_per_step": tot_child // len(full),
+            "matched": {"mus": MATCHED_MUS, "child_terms": pre_child // n_pre, "value": pre_child / (pre_ms / 1e3), "ms": pre_ms / n_pre, "passes": n_pre},
+            "detail": {"full_window_passes": len(full), "heaviest_mu": {"mu": heaviest[0], "ms": heaviest[3], "terms_after_muc": heaviest[1], "survivors": heaviest[2]},
+                       "ms_per_mu": [r[3] for r in full[0][0]]},
             "cpu_baseline": {"value": value, "unit": "child terms/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "child terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -161,11 +188,14 @@ def gpu_arm(args):
         prev = 1
         child = 0
         heaviest = (0.0, 0)
+        pre_ev, pre_child, pre_wall = 0.0, 0, 0.0
         for k, r in enumerate(sc.rec):
             s.step(r)
             st = s.stats()
             ev_ms += st.ev_step_ms
             child += st.terms_after_muc - prev
+            if k < MATCHED_MUS:
+                pre_ev += st.ev_step_ms; pre_child += st.terms_after_muc - prev; pre_wall = time.perf_counter() - wall0
             prev = st.survivors if k + 1 < len(sc.rec) else st.terms_after_muc
             gt_ms += st.ev_gtable_ms
             gt_bytes += st.bytes_gtable_algorithmic
@@ -182,7 +212,7 @@ def gpu_arm(args):
         wall = time.perf_counter() - wall0
         lib.mce_reset(s.h)
         return dict(ev_ms=ev_ms, wall_s=wall, child=child, gt_ms=gt_ms, gt_bytes=gt_bytes, gt_launch=gt_launch, h2d=h2d, d2h=d2h,
-                    launches=launches, heaviest=heaviest, Nt=mo.Nt)
+                    launches=launches, heaviest=heaviest, Nt=mo.Nt, pre_ev=pre_ev, pre_child=pre_child, pre_wall=pre_wall)
 
     for _ in range(max(3, args.warmup)):
         one_pass(False)
@@ -231,8 +261,10 @@ def gpu_arm(args):
         line = {"metric": METRIC, "value": child / ev_s, "unit": "child terms/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "strong" if term_sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "child_terms_per_step": child // (args.steps * (1 if term_sharded else world)), "mus_per_step": len(sc.rec),
-                           "ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
+                "config": _config(len(sc.rec)), "child_terms_per_step": child // (args.steps * (1 if term_sharded else world)),
+                "matched": {"mus": MATCHED_MUS, "child_terms": a0["pre_child"], "value": sum(a["pre_child"] for a in acc) / (sum(a["pre_ev"] for a in acc) / 1e3),
+                            "e2e_value": sum(a["pre_child"] for a in acc) / sum(a["pre_wall"] for a in acc), "ms": sum(a["pre_ev"] for a in acc) / len(acc), "passes": len(acc)},
+                "detail": {"ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
                            "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
                            "parallelism": ("one window, terms sharded over %d gpus (NCCL all-gather of DCE-TP and G-table outputs)" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
                            "moments": "reference serial order (bit-exact)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
@@ -245,10 +277,11 @@ def gpu_arm(args):
                 "timed_region_wall_s": region_s}
         # CPU baseline: the reference itself on this box's host cores, bounded sample (MUs 1..9 of the same window)
         if world == 1 and not args.no_cpu_baseline:
-            kind, rows, ms, _ = run_reference_sample(9)
+            kind, rows, ms, _ = run_reference_sample(12 if not args.short_cpu_baseline else MATCHED_MUS)
             cb = _child_terms(rows) / (ms / 1e3)
             line["cpu_baseline"] = {"value": cb, "unit": "child terms/s", "cores": 8 if kind == "reference" else 1, "kind": kind,
-                                    "sample": "MUs 1..9 of the 12-MU window (%d child terms, %.1f s of step() time), %s" % (
+                                    "sample": "%s of the 12-MU window, one pass (%d child terms, %.1f s of step() time), %s" % (
+                                        "all 12 MUs" if not args.short_cpu_baseline else "MUs 1..%d" % MATCHED_MUS,
                                         _child_terms(rows), ms / 1e3, "unmodified reference NUM_CPUS=8" if kind == "reference" else "plain-C oracle, 1 thread")}
         print(json.dumps(line), flush=True)
     s.close()
@@ -263,6 +296,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--short-cpu-baseline", action="store_true", help="cpu_baseline leg on MUs 1..9 only (2 s instead of ~30 s)")
+    ap.add_argument("--ref-full-passes", type=int, default=1, help="--impl reference: passes of the FULL window `value` is measured on")
     ap.add_argument("--shard", default="windows", choices=["windows", "terms"],
                     help="N > 1: one window per GPU (default, weak scaling) or ONE window with its terms sharded over the GPUs (strong scaling)")
     a = ap.parse_args()

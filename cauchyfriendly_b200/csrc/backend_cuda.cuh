@@ -8,6 +8,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <atomic>
 #include <stdexcept>
 #include <string>
 #include <string.h>
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(launch_traits<K>::max_threads, launch_traits<K
   c.smem_ = mce_dyn_smem;
   k.run(c);
 }
+
+constexpr int kMaxDynSmem = 227 * 1024;      // sm_100: 227 KB of dynamic shared memory per CTA
 
 struct CudaBackend {
   cudaStream_t stream = nullptr;
@@ -182,7 +185,18 @@ struct CudaBackend {
   void launch_on(cudaStream_t st, const K& k, int nblocks, int nthreads, size_t smem) {
     if (nblocks <= 0) return;
     static_assert(sizeof(K) <= 32000, "kernel functor exceeds the 32 KB parameter space (CUDA >= 12.1, sm_70+)");
-    if (smem > 48 * 1024) MCE_CUDA_CHECK(cudaFuncSetAttribute(mce_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) {
+      // The attribute belongs to (kernel, device), not to an engine: several estimators are stepped from a thread pool on one GPU
+      // (SlidingWindowBank, concurrent = True), so every kernel template is opted in ONCE per device, to the device maximum --
+      // setting the exact per-launch size would let another thread shrink it between this thread's set and its launch.
+      static std::atomic<unsigned> opted{0};
+      const unsigned bit = 1u << (device & 31);
+      if (!(opted.load(std::memory_order_acquire) & bit)) {
+        MCE_CUDA_CHECK(cudaFuncSetAttribute(mce_kernel_entry<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem));
+        opted.fetch_or(bit, std::memory_order_release);
+      }
+      if (smem > (size_t)kMaxDynSmem) throw std::runtime_error("kernel needs " + std::to_string(smem) + " B of shared memory; the device limit is " + std::to_string(kMaxDynSmem));
+    }
     mce_kernel_entry<K><<<nblocks, nthreads, smem, st>>>(k);
     MCE_CUDA_CHECK(cudaGetLastError());
     launch_count++;

@@ -168,6 +168,17 @@ class Engine {
       *why = "a window this deep gives tables of up to " + std::to_string(Hcap) + " cells; the group kernel holds a table in shared memory (227 KB, about 5500 cells)";
       return false;
     }
+    // every other kernel whose shared memory grows with the deepest shape of the window, at that shape
+    const int cgen = cell_count_general(max_shape, d);
+    const size_t need_mu = KMsmtUpdate2::smem_bytes(max_shape, d), need_ftr = KFtrRoundTiled::smem_bytes(max_shape, d);
+    const size_t need_tp = max_shape <= 16 ? KTpDce2::smem_bytes((1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1, 128, d)
+                                           : KTpDce::smem_bytes(next_pow2(DCE_STORAGE_MULT * cgen), next_pow2(cgen + 1), 128);
+    const size_t worst = need_mu > need_ftr ? (need_mu > need_tp ? need_mu : need_tp) : (need_ftr > need_tp ? need_ftr : need_tp);
+    if (worst > 227 * 1024) {
+      *why = "a window this deep (" + std::to_string(max_shape) + " hyperplanes in " + std::to_string(d) + " dimensions) needs " + std::to_string(worst / 1024) +
+             " KB of shared memory in the " + (worst == need_mu ? "measurement-update" : worst == need_ftr ? "term-reduction" : "time-propagation cell-enumeration") + " kernel; the limit is 227 KB";
+      return false;
+    }
     return true;
   }
 
@@ -282,6 +293,7 @@ class Engine {
   int step(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
            const double* B, const double* u) {
     if (numeric_moment_errors & (1 << ERROR_FZ_NEGATIVE)) return numeric_moment_errors;     // est:1214-1219
+    if (master_step < 0 || master_step > num_estimation_steps) { error = "master_step was set outside [0, num_estimation_steps]"; return -4; }
     if (master_step == num_estimation_steps || finished) { error = "master_step == num_estimation_steps: reset() the estimator first (est:1220-1225)"; return -4; }
     skip_post_mu = (master_step == num_estimation_steps - 1);                               // SKIP_LAST_STEP, est:1229
     stats = StepStats();
@@ -331,6 +343,11 @@ class Engine {
     StepParams sp = make_params(msmt, Phi, Gamma, beta, H, gamma, B, u, with_tp);
     GenStore& pg = gen[cur]; GenStore& ng = gen[1 - cur];
     const int n_alive = pg.v.n_alive;
+    // A caller that rewinds master_step (cauchy_windows.hpp:538, 659 write the field) can drive a window deeper than declared:
+    // the per-parent buffers hold max_shape rows, so a time propagation that would append beyond that is refused, not clamped.
+    if (with_tp)
+      for (int m = 1; m < NSHAPE; m++)
+        if (pg.alive_per_shape[m] > 0 && m + sp.npn > max_shape) { error = "time propagation would give a term more than max_shape = " + std::to_string(max_shape) + " hyperplanes (window stepped past its declared depth)"; return -5; }
     const int nq = 1 + d + d * d;
     stats.parents = n_alive;
     int* diag = (int*)diagBuf.ensure(sizeof(int) * (16 + NSHAPE + 8)); be.memset(diag, 0, sizeof(int) * (16 + NSHAPE + 8));   // [16] diagnostics, then the survivor bounds per shape
@@ -933,7 +950,28 @@ class Engine {
     return 0;
   }
 
-  // Host copy of the parents of shape m (canonical order).
+  // ---- term-list export: gather kernels + one bulk copy per array ----
+  struct KExportCells {     // cells[i] of the i-th surviving term of a shape
+    GenView gen; int rank0, n; int* cells;
+    template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+      c.par([&](int tid) { const int i = c.block() * c.nthreads() + tid; if (i < n) cells[i] = gen.cells[gen.alive[rank0 + i]]; });
+    }
+  };
+  struct KExportGather {    // one CTA per term: hyperplanes, weights, offset and the table (keys + values) into contiguous staging arrays
+    GenView gen; int rank0, m, d; const int* off; double *A, *p, *b; unsigned* keys; cplx* G;
+    template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+      const int i = c.block(), gid = gen.alive[rank0 + i], nc = gen.cells[gid]; const long long o = off[i];
+      const double* As = gen_A(gen, gid, m, d); const double* ps = gen_p(gen, gid, m); const double* bs = gen_b(gen, gid, d);
+      const unsigned* ks = gen_keys(gen, gid, m); const cplx* Gs = gen_G(gen, gid, m);
+      c.par([&](int tid) {
+        for (int k = tid; k < m * d; k += c.nthreads()) A[(long long)i * m * d + k] = As[k];
+        for (int k = tid; k < m; k += c.nthreads()) p[(long long)i * m + k] = ps[k];
+        for (int k = tid; k < d; k += c.nthreads()) b[(long long)i * d + k] = bs[k];
+        for (int k = tid; k < nc; k += c.nthreads()) { keys[o + k] = ks[k]; G[o + k] = Gs[k]; }
+      });
+    }
+  };
+  // Host copy of the parents of shape m (canonical order): two kernels and six device-to-host copies per shape.
   int export_shape(int m, int* n_terms, long long* n_cells_total, double* A, double* pp, double* b, int* cells, uint32_t* keys, double* G) {
     GenStore& g = gen[cur];
     if (m < 1 || m >= NSHAPE || master_step == 0) { *n_terms = 0; *n_cells_total = 0; return 0; }
@@ -941,23 +979,24 @@ class Engine {
     *n_terms = n;
     if (n == 0) { *n_cells_total = 0; return 0; }
     int rank0 = 0; for (int k = 1; k < m; k++) rank0 += g.alive_per_shape[k];
-    std::vector<int> alive(n), hc(n);
-    be.d2h(alive.data(), g.v.alive + rank0, sizeof(int) * n);
+    int* dcells = (int*)scratchI0.ensure(sizeof(int) * (size_t)(n + 4));
+    int* doff = (int*)scratchI1.ensure(sizeof(int) * (size_t)(n + 4));
+    be.launch(KExportCells{g.v, rank0, n, dcells}, (n + 127) / 128, 128, 0);
+    std::vector<int> hc(n);
+    be.d2h(hc.data(), dcells, sizeof(int) * n);
     long long tot = 0;
-    for (int i = 0; i < n; i++) { be.d2h(&hc[i], g.v.cells + alive[i], sizeof(int)); tot += hc[i]; }
+    for (int i = 0; i < n; i++) tot += hc[i];
     *n_cells_total = tot;
     if (!A) return 0;
-    long long o = 0;
-    for (int i = 0; i < n; i++) {
-      const int gid = alive[i];
-      be.d2h(A + (size_t)i * m * d, gen_A(g.v, gid, m, d), sizeof(double) * m * d);
-      be.d2h(pp + (size_t)i * m, gen_p(g.v, gid, m), sizeof(double) * m);
-      be.d2h(b + (size_t)i * d, gen_b(g.v, gid, d), sizeof(double) * d);
-      cells[i] = hc[i];
-      be.d2h(keys + o, gen_keys(g.v, gid, m), sizeof(unsigned) * hc[i]);
-      be.d2h(G + 2 * o, gen_G(g.v, gid, m), sizeof(cplx) * hc[i]);
-      o += hc[i];
-    }
+    if (tot > 0x7fffffffLL) { error = "export_shape: more than 2^31 table cells in one shape"; return -5; }
+    be.exclusive_scan(dcells, doff, n);
+    const size_t nA = (size_t)n * m * d, np = (size_t)n * m, nb = (size_t)n * d;
+    cplx* sG = (cplx*)cpV.ensure(sizeof(double) * (nA + np + nb + 2 * (size_t)tot + 8) + sizeof(unsigned) * ((size_t)tot + 8));   // 16-byte values first
+    double* sA = (double*)(sG + tot); double* sp_ = sA + nA; double* sb = sp_ + np; unsigned* sk = (unsigned*)(sb + nb);
+    be.launch(KExportGather{g.v, rank0, m, d, doff, sA, sp_, sb, sk, sG}, n, 128, 0);
+    be.d2h(A, sA, sizeof(double) * nA); be.d2h(pp, sp_, sizeof(double) * np); be.d2h(b, sb, sizeof(double) * nb);
+    if (tot > 0) { be.d2h(keys, sk, sizeof(unsigned) * (size_t)tot); be.d2h(G, sG, sizeof(cplx) * (size_t)tot); }
+    memcpy(cells, hc.data(), sizeof(int) * n);
     return 0;
   }
 };

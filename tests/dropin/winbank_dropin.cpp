@@ -31,6 +31,9 @@ int main(int argc, char** argv)
     for(int i = 0; i < total_steps; i++)
         swm.step(sim_log.msmt_history + i*p, NULL);
     swm.shutdown();
+    char path[4096];
+    sprintf(path, "%s/msmts.txt", argv[1]);          // the simulated measurement sequence, for replays through other front ends
+    log_double_array_to_file(path, sim_log.msmt_history, total_steps, p);
     printf("winbank drop-in done: %d measurements\n", total_steps);
     return 0;
 }

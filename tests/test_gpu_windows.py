@@ -38,3 +38,48 @@ def test_window_bank_concurrent_windows_same_results():
     """Windows stepped from a thread pool (one estimator per thread, own CUDA streams) give the same estimates."""
     from cauchyfriendly_b200.estimator import CauchyEstimator
     assert np.array_equal(_run(CauchyEstimator), _run(CauchyEstimator, concurrent=True))
+
+
+def _load_best(path):
+    """`<win_idx>:<values>` lines of the reference's bank logs (cauchy_windows.hpp:1378-1400)."""
+    idx, rows = [], []
+    for line in open(path):
+        a, b = line.split(":")
+        idx.append(int(a)); rows.append([float(v) for v in b.split()])
+    return np.array(idx), np.array(rows)
+
+
+def test_window_bank_matches_the_reference_window_manager(tmp_path):
+    """The Python bank against the REFERENCE's SlidingWindowManager: tests/golden/winbank_cpu1/ holds the log files the
+    unmodified NUM_CPUS=1 reference wrote for the inputs of src/window_manager.cpp (srand(11), 201 measurements, 8 windows;
+    tests/dropin/winbank_dropin.cpp) together with the measurement sequence.  Replaying the measurements through
+    SlidingWindowBank must select the same window at every step and write the same means / covariances / normalisation
+    factors into the same log layout.  Tolerance: 1e-9 relative to the largest entry of the row (north_star's moment
+    tolerance) -- the bank's Speyer initialisation uses LAPACK's symmetric eigen-solver where the reference uses its own
+    (eigenvector signs / last bits differ), everything inside a window is bit-exact."""
+    import os
+    from harness import ROOT
+    from cauchyfriendly_b200.estimator import CauchyEstimator
+    from cauchyfriendly_b200.windows import SlidingWindowBank
+    gold = os.path.join(ROOT, "tests", "golden", "winbank_cpu1")
+    zs = np.loadtxt(os.path.join(gold, "msmts.txt"))
+    Phi = np.array([[1.4, -0.6, -1.0], [-0.2, 1.0, 0.5], [0.6, -0.6, -0.2]])
+    Gamma = np.array([.1, .3, -.2]); H = np.array([[1.0, .5, .2]])
+    bank = SlidingWindowBank(8, np.eye(3), [.10, .08, .05], np.zeros(3), Phi, None, Gamma, [.1], H, [.2], estimator_cls=CauchyEstimator, seed=5,
+                             log_dir=str(tmp_path / "logs"), log_windows=False)
+    for z in zs:
+        bank.step([z])
+    bank.shutdown()
+    worst = {}
+    for name in ("cond_means.txt", "cond_covars.txt", "norm_factors.txt"):
+        gi, gv = _load_best(os.path.join(gold, name))
+        oi, ov = _load_best(str(tmp_path / "logs" / name))
+        assert gv.shape == ov.shape and gi.shape == oi.shape, name
+        assert np.array_equal(gi, oi), "%s: a different window was selected at steps %s" % (name, np.nonzero(gi != oi)[0][:10])
+        rel = np.max(np.abs(gv - ov), axis=1) / np.max(np.abs(gv), axis=1)
+        worst[name] = float(rel.max())
+        assert rel.max() <= 1e-9, "%s: worst row deviates by %.3e (step %d)" % (name, rel.max(), int(rel.argmax()))
+    gi, gv = _load_best(os.path.join(gold, "numeric_error_codes.txt"))
+    oi, ov = _load_best(str(tmp_path / "logs" / "numeric_error_codes.txt"))
+    assert np.array_equal(gv, ov)
+    print("window bank vs reference manager, worst relative row deviation:", worst)

@@ -132,8 +132,7 @@ def homing3():
 # (est:97) exceeds 16 and the engine takes its max_shape > 16 kernels (sort/hash G-table and DCE-TP variants; the bitmap
 # kernels serve max_shape <= 16 only) while the replayed prefix stays cheap for the CPU reference.  The reference supports
 # up to 31 hyperplanes (est:231-235).  name -> (source scenario, declared steps, records kept)
-DEEP = {"lti3_deep": ("lti3", 20, 9), "lti4_2pnoise_deep": ("lti4_2pnoise", 10, 6), "leo5_deep": ("leo5", 13, 8),
-        "lti3_3msmts_deep": ("lti3_3msmts", 16, 12)}
+DEEP = {"lti3_deep": ("lti3", 20, 9), "lti4_2pnoise_deep": ("lti4_2pnoise", 8, 6), "lti3_3msmts_deep": ("lti3_3msmts", 16, 12)}
 
 
 def deepen(outdir, name):

@@ -20,8 +20,7 @@ $R tests/golden/homing3.mces      tests/golden/homing3.ref.mced      --full-upto
 $R tests/golden/leo5.mces         tests/golden/leo5.ref.mced         --full-upto 4 --max-steps 13
 python tools/gen_scenarios.py tests/golden      # again: the deep-declared variants of leo5 need leo5.mces
 $R tests/golden/lti3_deep.mces         tests/golden/lti3_deep.ref.mced         --full-upto 4    # max_shape 22
-$R tests/golden/lti4_2pnoise_deep.mces tests/golden/lti4_2pnoise_deep.ref.mced --full-upto 3    # max_shape 22
-$R tests/golden/leo5_deep.mces         tests/golden/leo5_deep.ref.mced         --full-upto 3    # max_shape 17
+$R tests/golden/lti4_2pnoise_deep.mces tests/golden/lti4_2pnoise_deep.ref.mced --full-upto 3    # max_shape 18
 $R tests/golden/lti3_3msmts_deep.mces  tests/golden/lti3_3msmts_deep.ref.mced  --full-upto 5    # max_shape 18
 # the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
 oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
