@@ -19,6 +19,8 @@ from .estimator import CauchyEstimator
 
 COV_UNSTABLE_FINAL = 1 << 1   # ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT (cauchy_constants.hpp:114)
 COV_DNE = 1 << 3              # ERROR_COVARIANCE_AT_CURRENT_STEP_DNE
+MEAN_DNE = 1 << 7             # ERROR_MEAN_AT_CURRENT_STEP_DNE
+FZ_NEGATIVE = 1 << 9          # ERROR_FZ_NEGATIVE
 
 
 def speyers_window_init(x1_hat, Var, H, gamma, z1):
@@ -115,7 +117,13 @@ class SlidingWindowBank:
     step(msmts, controls) mirrors PySlidingWindowManager.step and returns (xhat, Phat, wavg_xhat, wavg_Phat)."""
 
     def __init__(self, num_windows, A0, p0, b0, Phi, B, Gamma, beta, H, gamma, *, estimator_cls=CauchyEstimator, est_kwargs=None,
-                 dist=None, seed=0, debug_print=False, concurrent=False, log_dir=None, log_windows=True):
+                 dist=None, seed=0, debug_print=False, concurrent=False, log_dir=None, log_windows=True, selection="python"):
+        # The reference has two window managers with different usable-window rules: PySlidingWindowManager skips windows whose
+        # covariance is unstable on the final measurement or does not exist (cauchy_estimator.py:1181-1204, selection="python");
+        # the C++ SlidingWindowManager skips fz < 0, covariance-DNE and mean-DNE (stratgey_choose_fullest_window_first,
+        # cauchy_windows.hpp:1578-1610, selection="cpp").
+        assert selection in ("python", "cpp")
+        self.selection = selection
         self.W = int(num_windows)
         self.n = int(np.asarray(p0).size)
         self.Phi = np.asarray(Phi, np.float64).reshape(self.n, self.n)
@@ -194,7 +202,8 @@ class SlidingWindowBank:
         for i in range(self.W):
             if self.win_counts[i] > 0:
                 err = int(self._stats[i, 1])
-                if not ((err & COV_UNSTABLE_FINAL) or (err & COV_DNE)):
+                bad = (err & (FZ_NEGATIVE | COV_DNE | MEAN_DNE)) if self.selection == "cpp" else (err & (COV_UNSTABLE_FINAL | COV_DNE))
+                if not bad:
                     idxs.append((i, self.win_counts[i]))
                     okays[i] = True
         if self.step_idx == 0:

@@ -25,6 +25,8 @@
 #include "cpu_timer.hpp"
 
 #include "mce_b200.h"   // add -I<repo>/include
+#include <vector>
+#include <unistd.h>
 
 struct CauchyEstimator
 {
@@ -79,6 +81,7 @@ struct CauchyEstimator
         for(int i = 0; i < d; i++)
             root_point[i] = 1.0 + random_uniform();
         double* b_pert = (double*) malloc((max_hp_shape + 1) * sizeof(double));
+        double* b_pert_keep = b_pert;
         for(int t = 0; t < NUM_CPUS; t++)
             for(int i = 0; i < max_hp_shape; i++)
             {
@@ -93,6 +96,8 @@ struct CauchyEstimator
         childterms_workspace.init(shape_range-1, d);
         first_term_live = false;
         seed_first_term();
+        rec_dir = getenv("MCE_RECORD_DIR"); rec_serial = 0; rec_declared_steps = _steps;
+        if(rec_dir != NULL) rec_bpert.assign(b_pert_keep, b_pert_keep + max_hp_shape);
         print_basic_info = _print_basic_info;
         skip_post_mu = false; win_num = 0; numeric_moment_errors = 0; G_SCALE_FACTOR = 0;
         fz = MAKE_CMPLX(0, 0);
@@ -174,6 +179,65 @@ struct CauchyEstimator
         }
     }
 
+    // ---- optional recorder: with MCE_RECORD_DIR set in the environment every estimator writes the arguments of its calls as an
+    // open-loop scenario file (<dir>/win<win_num>_pid<pid>_<serial>.mces; layout: oracle/mce_io.h / tests/mceio.py), one file
+    // per window pass (a new file starts at reset()).  Recorded production inputs can be replayed through the C ABI, the
+    // plain-C oracle and the unmodified reference (oracle/_ref/ref_run_cpu1) to localise a discrepancy.
+    struct RecStep { double msmt, gamma; std::vector<double> Phi, Gamma, beta, H, B, u, delta; int has_bu, shift_kind; };
+    std::vector<RecStep> rec_steps;
+    std::vector<double> rec_A0, rec_p0, rec_b0, rec_bpert;
+    int rec_serial, rec_declared_steps;
+    const char* rec_dir;
+    void rec_flush()
+    {
+        if(rec_dir == NULL || rec_steps.empty()) return;
+        char path[4096];
+        snprintf(path, sizeof(path), "%s/win%d_pid%d_%d.mces", rec_dir, win_num, (int)getpid(), rec_serial);
+        FILE* f = fopen(path, "wb");
+        if(f == NULL) return;
+        const unsigned magic = 0x5345434D; fwrite(&magic, 4, 1, f);
+        int hdr[7] = {1, d, cmcc, pncc, p, rec_declared_steps, (int)rec_steps.size()}; fwrite(hdr, 4, 7, f);
+        int order[12]; for(int i = 0; i < 12; i++) order[i] = TR_SEARCH_IDXS_ORDERING[i]; fwrite(order, 4, 12, f);
+        fwrite(root_point, 8, d, f);
+        int ms = shape_range - 1; fwrite(&ms, 4, 1, f); fwrite(rec_bpert.data(), 8, ms, f);
+        fwrite(rec_A0.data(), 8, d*d, f); fwrite(rec_p0.data(), 8, d, f); fwrite(rec_b0.data(), 8, d, f);
+        for(size_t k = 0; k < rec_steps.size(); k++)
+        {
+            const RecStep& r = rec_steps[k];
+            fwrite(&r.msmt, 8, 1, f); fwrite(&r.gamma, 8, 1, f);
+            fwrite(r.Phi.data(), 8, d*d, f); fwrite(r.Gamma.data(), 8, d*pncc, f); fwrite(r.beta.data(), 8, pncc, f); fwrite(r.H.data(), 8, d, f);
+            fwrite(&r.has_bu, 4, 1, f);
+            if(r.has_bu) { fwrite(r.B.data(), 8, d*cmcc, f); fwrite(r.u.data(), 8, cmcc, f); }
+            fwrite(&r.shift_kind, 4, 1, f); fwrite(r.delta.data(), 8, d, f);
+        }
+        fclose(f);
+    }
+    void rec_step(double msmt, double* Phi, double* Gamma, double* beta, double* H, double gamma, double* B, double* u)
+    {
+        if(rec_dir == NULL) return;
+        if(master_step == 0)
+        {
+            rec_steps.clear(); rec_serial++;
+            rec_A0.assign(terms_dp[d][0].A, terms_dp[d][0].A + d*d); rec_p0.assign(terms_dp[d][0].p, terms_dp[d][0].p + d); rec_b0.assign(terms_dp[d][0].b, terms_dp[d][0].b + d);
+        }
+        RecStep r; r.msmt = msmt; r.gamma = gamma; r.has_bu = (cmcc > 0 && B != NULL && u != NULL) ? 1 : 0; r.shift_kind = 0;
+        r.Phi.assign(d*d, 0.0); r.Gamma.assign(d*pncc, 0.0); r.beta.assign(pncc, 0.0); r.delta.assign(d, 0.0);
+        if(Phi != NULL) r.Phi.assign(Phi, Phi + d*d);
+        if(Gamma != NULL) r.Gamma.assign(Gamma, Gamma + d*pncc);
+        if(beta != NULL) r.beta.assign(beta, beta + pncc);
+        r.H.assign(H, H + d);
+        if(r.has_bu) { r.B.assign(B, B + d*cmcc); r.u.assign(u, u + cmcc); }
+        rec_steps.push_back(r);
+    }
+    void rec_shift(const double* delta, double sign)      // b <- b + sign*delta after the last recorded step (2 = explicit shift by -delta)
+    {
+        if(rec_dir == NULL || rec_steps.empty()) return;
+        RecStep& r = rec_steps.back();
+        r.shift_kind = 2;
+        for(int i = 0; i < d; i++) r.delta[i] += -sign * delta[i];
+        rec_flush();
+    }
+
     void set_win_num(int _win_num) { win_num = _win_num; }
     // est:192-222.  The device path has one storage mode (sorted keys, half storage); the reference's side consumers
     // (cpdf_ndim.hpp, cauchy_prediction.hpp) still call the global function pointers of cauchy_types.hpp:69-78 when they
@@ -248,9 +312,12 @@ struct CauchyEstimator
             // step_first reads the initial term where the reference keeps it (est:1181-1183: terms_dp[d][0] -> workspace)
             if(!first_term_live)
                 seed_first_term();
+            rec_step(msmt, Phi, Gamma, beta, H, gamma, B, u);
             mce_set_first_term(handle, terms_dp[d][0].A, terms_dp[d][0].p, terms_dp[d][0].b);
             free_host_mirror();     // the initial term is consumed; terms_dp is a lazily filled mirror from here on
         }
+        else
+            rec_step(msmt, Phi, Gamma, beta, H, gamma, B, u);
         int rc = mce_step(handle, msmt, Phi, Gamma, beta, H, gamma, B, u);
         if(rc < 0)
         {
@@ -258,6 +325,7 @@ struct CauchyEstimator
             exit(1);
         }
         pull_state();
+        rec_flush();
         if(auto_mirror && !skip_post_mu)
             sync_host_mirror();
         if(print_basic_info)
@@ -317,6 +385,7 @@ struct CauchyEstimator
             return;
         }
         mce_shift_b(handle, bias, 1.0);
+        rec_shift(bias, 1.0);
     }
 
     void deterministic_time_prop(double* Phi, double* B, double* u)               // est:1331
@@ -344,6 +413,7 @@ struct CauchyEstimator
         double delta_xk[32];
         for(int i = 0; i < d; i++) delta_xk[i] = creal(conditional_mean[i]);
         mce_shift_b(handle, delta_xk, -1.0);
+        if(!skip_post_mu) rec_shift(delta_xk, -1.0);
         for(int i = 0; i < d; i++) conditional_mean[i] += x_bar[i];
         for(int i = 0; i < d; i++) x_bar[i] = creal(conditional_mean[i]);
     }

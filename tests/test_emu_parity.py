@@ -13,7 +13,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = {"lti3": (8, 5), "lti2": (10, 6), "lti4": (6, 4), "lti3_3msmts": (12, 7), "lti4_2pnoise": (5, 3), "lti4_2msmts": (9, 5),
          "syn2": (12, 3), "syn3": (8, 3), "syn5": (5, 3), "syn7": (4, 2), "syn8": (4, 2), "leo7": (6, 3), "leo5": (7, 4), "homing3": (8, 5),
          # declared deeper than replayed: max_shape > 16 routes through KTpDce / KGTable (sort + hash variants)
-         "lti3_deep": (8, 4), "lti4_2pnoise_deep": (5, 3), "lti3_3msmts_deep": (12, 5)}
+         "homing_real": (8, 5), "lti3_deep": (8, 4), "lti4_2pnoise_deep": (5, 3), "lti3_3msmts_deep": (12, 5)}
 
 
 def _upto(d, k):

@@ -122,7 +122,9 @@ def _bank_logs_equal(gold_dir, got_dir, files):
         b = open(os.path.join(got_dir, f)).read().split()
         if a != b:
             n = sum(1 for x, y in zip(a, b) if x != y) + abs(len(a) - len(b))
-            bad.append("%s: %d of %d tokens differ" % (f, n, len(a)))
+            first = next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), min(len(a), len(b)))
+            bad.append("%s: %d of %d tokens differ (%d vs %d tokens); first at token %d: ref %s, got %s" % (
+                f, n, len(a), len(a), len(b), first, a[first:first + 3], b[first:first + 3]))
     return bad
 
 
@@ -160,4 +162,6 @@ def test_homing_missile_example_matches_the_reference(tmp_path):
     files = ["cond_means.txt", "cond_covars.txt", "norm_factors.txt", "numeric_error_codes.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt", "cerr_norm_factors.txt",
              "cauchy_controls.txt", "cauchy_with_controller_msmts.txt", "cauchy_with_controller_true_states.txt"]
     bad = _bank_logs_equal(os.path.join(ROOT, "tests", "golden", "homing_cpu1"), str(logs / "w8_bs5_sas13" / "mct1"), files)
-    assert not bad, "\n".join(bad)
+    if bad:
+        print("\n".join(bad))
+    assert not bad, bad[0][:300]

@@ -18,7 +18,7 @@ GOLDEN_CASES = {"lti3": (11, 5), "lti2": (10, 6), "lti4": (8, 4), "lti3_3msmts":
                 "syn2": (12, 3), "syn3": (10, 3), "syn4": (8, 3), "syn5": (7, 3), "syn6": (6, 2), "syn7": (6, 2), "syn8": (5, 2),
                 "leo7": (12, 3), "leo5": (13, 4), "homing3": (8, 5),
                 # declared deeper than replayed: max_shape > 16 routes through KTpDce / KGTable (sort + hash variants)
-                "lti3_deep": (9, 4), "lti4_2pnoise_deep": (6, 3), "lti3_3msmts_deep": (12, 5)}
+                "homing_real": (8, 5), "lti3_deep": (9, 4), "lti4_2pnoise_deep": (6, 3), "lti3_3msmts_deep": (12, 5)}
 
 
 @pytest.fixture(scope="module")

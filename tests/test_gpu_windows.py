@@ -66,7 +66,7 @@ def test_window_bank_matches_the_reference_window_manager(tmp_path):
     Phi = np.array([[1.4, -0.6, -1.0], [-0.2, 1.0, 0.5], [0.6, -0.6, -0.2]])
     Gamma = np.array([.1, .3, -.2]); H = np.array([[1.0, .5, .2]])
     bank = SlidingWindowBank(8, np.eye(3), [.10, .08, .05], np.zeros(3), Phi, None, Gamma, [.1], H, [.2], estimator_cls=CauchyEstimator, seed=5,
-                             log_dir=str(tmp_path / "logs"), log_windows=False)
+                             log_dir=str(tmp_path / "logs"), log_windows=False, selection="cpp")
     for z in zs:
         bank.step([z])
     bank.shutdown()

@@ -8,7 +8,10 @@ REF=${REF:-/root/reference}
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 OV=$ROOT/build/overlay
 rm -rf "$OV" && mkdir -p "$OV/include" "$OV/src" "$OV/scripts/swig/cauchy" "$OV/tests" "$ROOT/build/dropin"
-for f in "$REF"/include/*; do ln -s "$f" "$OV/include/"; done
+for f in "$REF"/include/*; do      # sub-directories (models/) are re-created so that their "../x.hpp" includes stay inside the overlay
+  if [ -d "$f" ]; then mkdir -p "$OV/include/$(basename "$f")"; for g in "$f"/*; do ln -s "$g" "$OV/include/$(basename "$f")/"; done
+  else ln -s "$f" "$OV/include/"; fi
+done
 for f in "$REF"/src/*; do ln -s "$f" "$OV/src/"; done
 ln -s "$REF/scripts/swig/cauchy/pycauchy.hpp" "$OV/scripts/swig/cauchy/pycauchy.hpp"
 for f in "$ROOT"/tests/dropin/*.cpp; do ln -s "$f" "$OV/tests/"; done

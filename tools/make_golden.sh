@@ -18,6 +18,9 @@ for n in 2 3 4 5 6 7 8; do $R tests/golden/syn$n.mces tests/golden/syn$n.ref.mce
 $R tests/golden/leo7.mces         tests/golden/leo7.ref.mced         --full-upto 3
 $R tests/golden/homing3.mces      tests/golden/homing3.ref.mced      --full-upto 5    # control input (B, u) + own-mean re-centring
 $R tests/golden/leo5.mces         tests/golden/leo5.ref.mced         --full-upto 4 --max-steps 13
+# BASELINE.json configs[1]: the reference's homing-missile EMCE (closed loop, author's seed) recorded open-loop by oracle/ref_gen_homing.cpp
+[ -f tests/golden/homing_real.mces ] || oracle/_ref/ref_gen_homing tests/golden/homing_real.mces 8
+$R tests/golden/homing_real.mces  tests/golden/homing_real.ref.mced  --full-upto 5
 python tools/gen_scenarios.py tests/golden      # again: the deep-declared variants of leo5 need leo5.mces
 $R tests/golden/lti3_deep.mces         tests/golden/lti3_deep.ref.mced         --full-upto 4    # max_shape 22
 $R tests/golden/lti4_2pnoise_deep.mces tests/golden/lti4_2pnoise_deep.ref.mced --full-upto 3    # max_shape 18
