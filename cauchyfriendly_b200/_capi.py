@@ -3,7 +3,8 @@ import ctypes as ct
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libmce_b200.so")
+# MCE_B200_LIB selects another build of the same library (A/B measurements of kernel variants; tools/ab_build.sh)
+LIB_PATH = os.environ.get("MCE_B200_LIB") or os.path.join(PKG_DIR, "libmce_b200.so")
 MAXM = 32
 
 

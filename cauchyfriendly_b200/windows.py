@@ -11,6 +11,7 @@ process per GPU, torch.distributed).  The only exchange per step is an all-gathe
 mean, covariance) -- 3 + n + n*n doubles per window -- after which every rank runs the same selection logic; there is no
 data-path collective.  This is the reference's own unit of distribution (one forked process per window,
 cauchy_windows.hpp:353-376)."""
+import math
 import os
 
 import numpy as np
@@ -23,26 +24,200 @@ MEAN_DNE = 1 << 7             # ERROR_MEAN_AT_CURRENT_STEP_DNE
 FZ_NEGATIVE = 1 << 9          # ERROR_FZ_NEGATIVE
 
 
+def _pythag(a, b):      # evs_pythag, eig_solve.hpp:254-261
+    absa, absb = abs(a), abs(b)
+    if absa > absb:
+        t = absb / absa
+        return absa * math.sqrt(1.0 + t * t)
+    if absb == 0.0:
+        return 0.0
+    t = absa / absb
+    return absb * math.sqrt(1.0 + t * t)
+
+
+def _esign(a, b):       # EVS_SIGN, eig_solve.hpp:11
+    return abs(a) if b >= 0.0 else -abs(a)
+
+
+def sym_eig(A, n):
+    """Eigenvalues / eigenvectors of a symmetric matrix exactly as the reference computes them (sym_eig, eig_solve.hpp:404-427:
+    Householder tridiagonalisation evs_tred2 :263-331 followed by QL with implicit shifts evs_tqli :334-389), operation for
+    operation in IEEE double -- LAPACK's eigenvectors differ from these in sign and last bits, and the windows re-seeded from
+    them would drift from the reference's by ~1e-9.  Returns (evals[n], evecs[n][n]) with eigenvector k in COLUMN k."""
+    a = [[float(A[i][j]) for j in range(n)] for i in range(n)]
+    d = [0.0] * n
+    e = [0.0] * n
+    for i in range(n - 1, 0, -1):           # evs_tred2
+        l = i - 1
+        h = scale = 0.0
+        if l > 0:
+            for k in range(l + 1):
+                scale += abs(a[i][k])
+            if scale == 0.0:
+                e[i] = a[i][l]
+            else:
+                for k in range(l + 1):
+                    a[i][k] /= scale
+                    h += a[i][k] * a[i][k]
+                f = a[i][l]
+                g = -math.sqrt(h) if f >= 0.0 else math.sqrt(h)
+                e[i] = scale * g
+                h -= f * g
+                a[i][l] = f - g
+                f = 0.0
+                for j in range(l + 1):
+                    a[j][i] = a[i][j] / h
+                    g = 0.0
+                    for k in range(j + 1):
+                        g += a[j][k] * a[i][k]
+                    for k in range(j + 1, l + 1):
+                        g += a[k][j] * a[i][k]
+                    e[j] = g / h
+                    f += e[j] * a[i][j]
+                hh = f / (h + h)
+                for j in range(l + 1):
+                    f = a[i][j]
+                    e[j] = g = e[j] - hh * f
+                    for k in range(j + 1):
+                        a[j][k] -= (f * e[k] + g * a[i][k])
+        else:
+            e[i] = a[i][l]
+        d[i] = h
+    d[0] = 0.0
+    e[0] = 0.0
+    for i in range(n):
+        l = i
+        if d[i] != 0.0:
+            for j in range(l):
+                g = 0.0
+                for k in range(l):
+                    g += a[i][k] * a[k][j]
+                for k in range(l):
+                    a[k][j] -= g * a[k][i]
+        d[i] = a[i][i]
+        a[i][i] = 1.0
+        for j in range(l):
+            a[j][i] = a[i][j] = 0.0
+    z = a                                   # evs_tqli
+    for i in range(1, n):
+        e[i - 1] = e[i]
+    e[n - 1] = 0.0
+    for l in range(n):
+        it = 0
+        while True:
+            m = l
+            while m < n - 1:
+                dd = abs(d[m]) + abs(d[m + 1])
+                if abs(e[m]) + dd == dd:
+                    break
+                m += 1
+            if m != l:
+                if it == 30:
+                    it += 1
+                    break
+                it += 1
+                g = (d[l + 1] - d[l]) / (2.0 * e[l])
+                r = _pythag(g, 1.0)
+                g = d[m] - d[l] + e[l] / (g + _esign(r, g))
+                s = c = 1.0
+                p = 0.0
+                i = m - 1
+                broke = False
+                while i >= l:
+                    f = s * e[i]
+                    b = c * e[i]
+                    r = _pythag(f, g)
+                    e[i + 1] = r
+                    if r == 0.0:
+                        d[i + 1] -= p
+                        e[m] = 0.0
+                        broke = True
+                        break
+                    s = f / r
+                    c = g / r
+                    g = d[i + 1] - p
+                    r = (d[i] - g) * s + 2.0 * c * b
+                    p = s * r
+                    d[i + 1] = g + p
+                    g = c * r - b
+                    for k in range(n):
+                        f = z[k][i + 1]
+                        z[k][i + 1] = s * z[k][i] + c * f
+                        z[k][i] = c * z[k][i] - s * f
+                    i -= 1
+                if broke and r == 0.0 and i >= l:
+                    continue
+                d[l] -= p
+                e[l] = g
+                e[m] = 0.0
+            if m == l:
+                break
+    return d, z
+
+
 def speyers_window_init(x1_hat, Var, H, gamma, z1):
-    """Speyer's window initialisation, cauchy_util.hpp:23-112 (window_var_boost = NULL): returns A0 (n x n), p0, b0 of a
-    one-term characteristic function whose first measurement update reproduces (x1_hat, Var)."""
-    x1_hat = np.asarray(x1_hat, np.float64)
-    Var = np.array(Var, np.float64)
-    H = np.asarray(H, np.float64).reshape(-1)
-    n = x1_hat.size
-    w = np.linalg.eigvalsh(Var)
-    if np.any(w < -1e-5):                       # COV_EIGENVALUE_TOLERANCE: make the covariance more positive definite
-        Var = Var + np.eye(n) * (-1e-5 - w.min())
-    resid = z1 - H @ x1_hat
-    scale = gamma * gamma + resid * resid
-    M = Var + (Var @ np.outer(H, H) @ Var) / scale
-    eigs, vecs = np.linalg.eigh(M)
-    A0 = vecs.T.copy()                          # rows are the eigenvectors
-    b0 = x1_hat - (Var @ H) * (resid / scale)
-    HA = A0 @ H
-    scale3 = (scale + H @ Var @ H) / gamma
-    p0 = eigs / scale3 * HA / np.sign(HA)
-    return A0, p0, b0
+    """Speyer's window initialisation restated operation for operation from cauchy_util.hpp:23-112 (window_var_boost = NULL):
+    returns A0 (n x n), p0, b0 of a one-term characteristic function whose first measurement update reproduces (x1_hat, Var).
+    Scalar IEEE-double loops in the reference's order (n <= 8, once per bank step), so the re-seeded window starts from the same
+    bits as the reference's."""
+    n = len(x1_hat)
+    x1 = [float(v) for v in x1_hat]
+    V = [[float(np.asarray(Var)[i][j]) for j in range(n)] for i in range(n)]
+    Hh = [float(v) for v in np.asarray(H, np.float64).reshape(-1)]
+    ev, _ = sym_eig(V, n)
+    if any(w < -1e-5 for w in ev):          # COV_EIGENVALUE_TOLERANCE (:46-68): make the covariance more positive definite
+        boost = -1e-5 - min(ev)
+        for i in range(n):
+            V[i][i] += boost
+    HH = [[Hh[i] * Hh[j] for j in range(n)] for i in range(n)]                 # inner_mat_prod(H, work, 1, N): sum of one product
+    HH = [[0.0 + HH[i][j] for j in range(n)] for i in range(n)]
+    W2 = [[0.0] * n for _ in range(n)]
+    for i in range(n):                      # matmatmul(Var, work, work2)
+        for j in range(n):
+            sm = 0.0
+            for k in range(n):
+                sm += V[i][k] * HH[k][j]
+            W2[i][j] = sm
+    W = [[0.0] * n for _ in range(n)]
+    for i in range(n):                      # matmatmul(work2, Var, work)
+        for j in range(n):
+            sm = 0.0
+            for k in range(n):
+                sm += W2[i][k] * V[k][j]
+            W[i][j] = sm
+    Hx = 0.0
+    for i in range(n):
+        Hx += Hh[i] * x1[i]
+    scale = gamma * gamma + (z1 - Hx) * (z1 - Hx)
+    inv = 1.0 / scale
+    M = [[V[i][j] + (W[i][j] * inv) * 1.0 for j in range(n)] for i in range(n)]     # scale_mat(work, 1/scale); add_mat(A_0, Var, work, 1.0)
+    eigs, vec = sym_eig(M, n)               # vec: eigenvector k in column k (A_0 before reflect_array)
+    scale2 = (z1 - Hx) / scale
+    VH = [0.0] * n
+    for i in range(n):                      # matvecmul(Var, H, work)
+        sm = 0.0
+        for j in range(n):
+            sm += V[i][j] * Hh[j]
+        VH[i] = sm
+    b0 = [x1[i] - VH[i] * scale2 for i in range(n)]
+    HA = [0.0] * n
+    for i in range(n):                      # matvecmul(A_0, H, work2, N, N, true): sum_j A_0[i + j*N] * H[j]
+        sm = 0.0
+        for j in range(n):
+            sm += vec[j][i] * Hh[j]
+        HA[i] = sm
+    HVH = 0.0
+    for i in range(n):
+        HVH += Hh[i] * VH[i]
+    scale3 = (scale + HVH) / gamma
+    p0 = []
+    for i in range(n):
+        v = eigs[i] / scale3
+        v *= HA[i]
+        v /= float((HA[i] > 0) - (HA[i] < 0))
+        p0.append(v)
+    A0 = np.array([[vec[j][i] for j in range(n)] for i in range(n)], np.float64)     # reflect_array: rows are the eigenvectors
+    return A0, np.array(p0, np.float64), np.array(b0, np.float64)
 
 
 LOG_NAMES = ("cond_means.txt", "cond_covars.txt", "norm_factors.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt",

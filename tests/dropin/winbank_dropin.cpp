@@ -28,12 +28,23 @@ int main(int argc, char** argv)
     sim_log.run_simulation_and_log();
     const int total_steps = num_steps + 1, num_windows = 8;
     SlidingWindowManager swm(num_windows, total_steps, A0, p0, b0, &duc, false, false, false, false, NULL, NULL, NULL, NULL, argv[1]);
+    // Every window process inherited this RNG state at fork() and drew its root_point (est:125-128) and b_pert
+    // (cell_enumeration.hpp:467-470) from it; the same draws here give the values all windows use (for replays elsewhere).
+    double rp_bp[n + (n + num_windows - 1)];
+    for(int i = 0; i < n; i++) rp_bp[i] = 1.0 + random_uniform();
+    for(int i = 0; i < n + num_windows - 1; i++) rp_bp[n + i] = 2*random_uniform() - 1;
     for(int i = 0; i < total_steps; i++)
         swm.step(sim_log.msmt_history + i*p, NULL);
     swm.shutdown();
     char path[4096];
     sprintf(path, "%s/msmts.txt", argv[1]);          // the simulated measurement sequence, for replays through other front ends
-    log_double_array_to_file(path, sim_log.msmt_history, total_steps, p);
+    FILE* f = fopen(path, "w");                        // %.17g round-trips a double; the reference's loggers print %.16lf, which does not
+    for(int i = 0; i < total_steps*p; i++) fprintf(f, "%.17g\n", sim_log.msmt_history[i]);
+    fclose(f);
+    sprintf(path, "%s/root_point_b_pert.txt", argv[1]);
+    f = fopen(path, "w");
+    for(int i = 0; i < n + (n + num_windows - 1); i++) fprintf(f, "%.17g\n", rp_bp[i]);
+    fclose(f);
     printf("winbank drop-in done: %d measurements\n", total_steps);
     return 0;
 }

@@ -1,44 +1,13 @@
-"""The sliding-window bank (cauchyfriendly_b200/windows.py, mirror of PySlidingWindowManager) on the GPU path: the same
-host logic must give the same estimates over libmce_b200.so as over the emulated kernels (both bit-exact restatements)."""
+"""The sliding-window bank against the REFERENCE's SlidingWindowManager on the CPU-only box: same check as
+tests/test_gpu_windows.py::test_window_bank_matches_the_reference_window_manager, with the estimators running the sequential
+emulation of the kernel bodies (tests/emu, test infrastructure).  Pins the host-side bank logic -- window selection by the C++
+manager's rule, Speyer re-initialisation through the restated eigen-solver, log layout -- to the reference's own log files."""
 import functools
+import os
 
 import numpy as np
-import pytest
 
-pytestmark = pytest.mark.gpu
-
-
-def _run(est_cls, concurrent=False):
-    from cauchyfriendly_b200.windows import SlidingWindowBank
-    Phi = np.array([[1.4, -0.6, -1.0], [-0.2, 1.0, 0.5], [0.6, -0.6, -0.2]])
-    Gamma = np.array([.1, .3, -.2]); H = np.array([[1.0, .5, .2]])
-    rng = np.random.RandomState(3)
-    x = np.zeros(3); zs = []
-    for _ in range(14):
-        x = Phi @ x + Gamma * 0.1 * rng.standard_cauchy(); zs.append(H[0] @ x + 0.2 * rng.standard_cauchy())
-    bank = SlidingWindowBank(5, np.eye(3), [.1, .08, .05], np.zeros(3), Phi, None, Gamma, [.1], H, [.2], estimator_cls=est_cls, seed=5, concurrent=concurrent)
-    out = []
-    for z in zs:
-        xh, Ph, xa, Pa = bank.step([z])
-        out.append(np.concatenate([xh, Ph.ravel(), xa, Pa.ravel(), [bank.moment_info["win_idx"][-1]]]))
-    bank.shutdown()
-    return np.array(out)
-
-
-def test_window_bank_gpu_matches_emulated_kernels():
-    from cauchyfriendly_b200.estimator import CauchyEstimator
-    from harness import load_emu
-    gpu = _run(CauchyEstimator)
-    emu = _run(functools.partial(CauchyEstimator, _lib=load_emu()))
-    assert np.array_equal(gpu, emu)
-    assert np.isfinite(gpu).all() and gpu.shape[0] == 14
-
-
-def test_window_bank_concurrent_windows_same_results():
-    """Windows stepped from a thread pool (one estimator per thread, own CUDA streams) give the same estimates."""
-    from cauchyfriendly_b200.estimator import CauchyEstimator
-    assert np.array_equal(_run(CauchyEstimator), _run(CauchyEstimator, concurrent=True))
-
+from harness import ROOT, load_emu
 
 def _load_best(path):
     """`<win_idx>:<values>` lines of the reference's bank logs (cauchy_windows.hpp:1378-1400)."""
@@ -49,7 +18,7 @@ def _load_best(path):
     return np.array(idx), np.array(rows)
 
 
-def test_window_bank_matches_the_reference_window_manager(tmp_path):
+def test_window_bank_over_emulated_kernels_matches_the_reference_window_manager(tmp_path):
     """The Python bank against the REFERENCE's SlidingWindowManager: tests/golden/winbank_cpu1/ holds the log files the
     unmodified NUM_CPUS=1 reference wrote for the inputs of src/window_manager.cpp (srand(11), 201 measurements, 8 windows;
     tests/dropin/winbank_dropin.cpp) together with the measurement sequence.  Replaying the measurements through
@@ -57,9 +26,8 @@ def test_window_bank_matches_the_reference_window_manager(tmp_path):
     factors into the same log layout -- digit for digit (16 decimals): the estimators are bit-exact, the bank's Speyer
     initialisation restates the reference's own symmetric eigen-solver operation for operation (windows.py::sym_eig), and
     the windows get the root_point / b_pert the reference's window processes drew."""
-    import os
-    from harness import ROOT
-    from cauchyfriendly_b200.estimator import CauchyEstimator
+    from cauchyfriendly_b200.estimator import CauchyEstimator as _Est
+    CauchyEstimator = functools.partial(_Est, _lib=load_emu())
     from cauchyfriendly_b200.windows import SlidingWindowBank
     gold = os.path.join(ROOT, "tests", "golden", "winbank_cpu1")
     zs = np.loadtxt(os.path.join(gold, "msmts.txt"))

@@ -42,7 +42,7 @@ def main():
         os.makedirs(wb)
         run([os.path.join(REF, "ex_winbank_cpu1"), wb], td)
         os.makedirs(os.path.join(GOLD, "winbank_cpu1"), exist_ok=True)
-        for f in BANK_FILES + ["msmts.txt"]:
+        for f in BANK_FILES + ["msmts.txt", "root_point_b_pert.txt"]:
             shutil.copy(os.path.join(wb, f), os.path.join(GOLD, "winbank_cpu1", f))
         hm = os.path.join(td, "hm")
         os.makedirs(hm)
