@@ -349,11 +349,10 @@ class SlidingWindowBank:
         n = self.n
         row = self._stats[w]
         row[1] = est.numeric_moment_errors
-        row[2] = est.fz_after_mu.real if est.fz_after_mu.real != 0 else est.fz.real
+        row[2] = est.fz.real            # the public field both reference managers report: 1 after a non-final step (est:1172-1176)
         row[3:3 + n] = est.conditional_mean.real
         row[3 + n:3 + n + n * n] = est.conditional_variance.real.ravel()
-        fz = est.fz_after_mu if est.fz_after_mu.real != 0 else est.fz
-        row[3 + n + n * n] = fz.imag                                             # save_window_data, cauchy_windows.hpp:1478-1503
+        row[3 + n + n * n] = est.fz.imag                                             # save_window_data, cauchy_windows.hpp:1478-1503
         row[4 + n + n * n] = np.abs(est.conditional_mean.imag).max()
         row[5 + n + n * n] = np.abs(est.conditional_variance.imag).max()
 

@@ -72,7 +72,7 @@ def test_window_bank_matches_the_reference_window_manager(tmp_path):
         bank.step([z])
     bank.shutdown()
     worst = {}
-    for name in ("cond_means.txt", "cond_covars.txt", "norm_factors.txt"):
+    for name in ("cond_means.txt", "cond_covars.txt", "norm_factors.txt", "cerr_cond_means.txt", "cerr_cond_covars.txt", "cerr_norm_factors.txt"):
         gi, gv = _load_best(os.path.join(gold, name))
         oi, ov = _load_best(str(tmp_path / "logs" / name))
         assert gv.shape == ov.shape and gi.shape == oi.shape, name
