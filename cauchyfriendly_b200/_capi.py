@@ -28,12 +28,22 @@ class MceStepStats(ct.Structure):
                 ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_ftr_ms", ct.c_double), ("ev_mu_ms", ct.c_double)]
 
 
+class MceAllToAllV(ct.Structure):      # mce_alltoallv_args
+    _fields_ = [("send", ct.c_void_p), ("recv", ct.c_void_p), ("soff", ct.POINTER(ct.c_longlong)), ("scnt", ct.POINTER(ct.c_longlong)),
+                ("roff", ct.POINTER(ct.c_longlong)), ("rcnt", ct.POINTER(ct.c_longlong))]
+
+
+class MceShardStats(ct.Structure):     # mce_shard_stats
+    _fields_ = [("rank", ct.c_int), ("world", ct.c_int), ("owned_terms", ct.c_int), ("imported_parents", ct.c_int), ("local_parents", ct.c_int), ("pad_", ct.c_int),
+                ("bytes_terms", ct.c_longlong), ("bytes_parents", ct.c_longlong), ("bytes_moments", ct.c_longlong), ("bytes_keys", ct.c_longlong)]
+
+
 EXCHANGE_FN = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_longlong)
 
 # every symbol include/mce_b200.h declares
 SYMBOLS = ["mce_default_options", "mce_create", "mce_destroy", "mce_step", "mce_get_moments", "mce_shape_range",
            "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_set_first_term", "mce_shift_b",
-           "mce_deterministic_time_prop", "mce_export_shape", "mce_cpdf_grid_count", "mce_marginal_1d_points", "mce_marginal_1d_grid", "mce_marginal_2d_points", "mce_marginal_2d_grid", "mce_cpdf_last_ms", "mce_get_step_stats", "mce_debug_div_selftest", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback",
+           "mce_deterministic_time_prop", "mce_export_shape", "mce_cpdf_grid_count", "mce_marginal_1d_points", "mce_marginal_1d_grid", "mce_marginal_2d_points", "mce_marginal_2d_grid", "mce_cpdf_last_ms", "mce_get_step_stats", "mce_debug_div_selftest", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback", "mce_shard_set_moments_mode", "mce_shard_export_gpos", "mce_shard_get_stats",
            "mce_last_error", "mce_version"]
 
 
@@ -69,6 +79,9 @@ def bind(lib):
     lib.mce_shard_unique_id.argtypes = [ct.c_int, ct.c_void_p]
     lib.mce_shard_init.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, ct.c_void_p]
     lib.mce_shard_init_callback.argtypes = [ct.c_void_p, ct.c_int, ct.c_int, EXCHANGE_FN, ct.c_void_p]
+    lib.mce_shard_set_moments_mode.argtypes = [ct.c_void_p, ct.c_int]
+    lib.mce_shard_export_gpos.argtypes = [ct.c_void_p, ip, ct.c_int]
+    lib.mce_shard_get_stats.argtypes = [ct.c_void_p, ct.POINTER(MceShardStats)]
     lib.mce_debug_muc_shape.argtypes = [ct.c_void_p, ct.c_int, ip, dp, dp, dp, dp, dp, ip, ct.POINTER(ct.c_uint8), ct.POINTER(ct.c_int8), ip]
     lib.mce_last_error.restype = ct.c_char_p
     lib.mce_version.restype = ct.c_char_p

@@ -76,6 +76,8 @@ struct CudaBackend {
     int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr; int (*GroupEnd)() = nullptr; int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
   } nccl;
@@ -90,6 +92,8 @@ struct CudaBackend {
     nccl.CommInitRank = (decltype(nccl.CommInitRank))sym("ncclCommInitRank");
     nccl.AllGather = (decltype(nccl.AllGather))sym("ncclAllGather");
     nccl.AllReduce = (decltype(nccl.AllReduce))sym("ncclAllReduce");
+    nccl.Send = (decltype(nccl.Send))sym("ncclSend");
+    nccl.Recv = (decltype(nccl.Recv))sym("ncclRecv");
     nccl.GroupStart = (decltype(nccl.GroupStart))sym("ncclGroupStart");
     nccl.GroupEnd = (decltype(nccl.GroupEnd))sym("ncclGroupEnd");
     nccl.CommDestroy = (decltype(nccl.CommDestroy))sym("ncclCommDestroy");
@@ -127,6 +131,24 @@ struct CudaBackend {
     if (n == 0) return;
     if (shard.fn) { if (shard.fn(shard.fn_ctx, MCE_XCHG_ALLREDUCE_SUM_U32, base, (long long)n) != 0) throw std::runtime_error("exchange callback failed"); return; }
     nccl_check(nccl.AllReduce(base, base, n, /*ncclUint32*/ 3, /*ncclSum*/ 0, nccl.comm, stream), "ncclAllReduce");
+  }
+
+  // Personalised exchange: `cnt[h]` bytes at `send + soff[h]` go to rank h, `rcnt[h]` bytes from rank h land at `recv + roff[h]`
+  // (grouped ncclSend / ncclRecv over NVLink; the rank's own chunk is a device-to-device copy).  Call between xchg_begin / xchg_end.
+  void xchg_alltoallv(const void* send, const long long* soff, const long long* scnt, void* recv, const long long* roff, const long long* rcnt) {
+    if (shard.fn) {
+      mce_alltoallv_args a{send, recv, soff, scnt, roff, rcnt};
+      if (shard.fn(shard.fn_ctx, MCE_XCHG_ALLTOALLV, &a, (long long)shard.world) != 0) throw std::runtime_error("exchange callback failed");
+      return;
+    }
+    for (int h = 0; h < shard.world; h++) {
+      if (h == shard.rank) {
+        if (scnt[h] > 0) MCE_CUDA_CHECK(cudaMemcpyAsync((char*)recv + roff[h], (const char*)send + soff[h], (size_t)scnt[h], cudaMemcpyDeviceToDevice, stream));
+        continue;
+      }
+      if (scnt[h] > 0) nccl_check(nccl.Send((const char*)send + soff[h], (size_t)scnt[h], /*ncclInt8*/ 0, h, nccl.comm, stream), "ncclSend");
+      if (rcnt[h] > 0) nccl_check(nccl.Recv((char*)recv + roff[h], (size_t)rcnt[h], /*ncclInt8*/ 0, h, nccl.comm, stream), "ncclRecv");
+    }
   }
 
   // the calling host thread may be new (window banks step their estimators from a thread pool): bind it to this device

@@ -205,6 +205,8 @@ int mce_shard_unique_id(int device, void* id128) {
 static int shard_check(mce_handle* h, int rank, int world) {
   if (!h || world < 1 || rank < 0 || rank >= world) { g_mce_error = "mce_shard_init: bad argument"; return MCE_ERR_BAD_ARG; }
   if (h->e->max_shape > 16) { g_mce_error = "mce_shard_init: term-level sharding needs at most 16 hyperplanes per term"; return MCE_ERR_BAD_ARG; }
+  if (world > mce::PART_MAXW) { g_mce_error = "mce_shard_init: at most 16 ranks per estimator"; return MCE_ERR_BAD_ARG; }
+  if (h->e->print_basic_info) { g_mce_error = "mce_shard_init: print_basic_info (post-reduction moment re-evaluation) is not available on a partitioned estimator"; return MCE_ERR_BAD_ARG; }
   if (h->e->master_step != 0) { g_mce_error = "mce_shard_init: call before the first step"; return MCE_ERR_BAD_ARG; }
   return 0;
 }
@@ -221,6 +223,25 @@ int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn 
   if (rc) return rc;
   if (!fn) return MCE_ERR_BAD_ARG;
   h->e->be.shard_init_callback(rank, world, (mce::mce_exchange_fn)fn, ctx);
+  return 0;
+}
+
+int mce_shard_set_moments_mode(mce_handle* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return MCE_ERR_BAD_ARG;
+  h->e->moments_mode = mode;
+  return 0;
+}
+int mce_shard_export_gpos(mce_handle* h, int* out, int cap) {
+  if (!h) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
+  try { return h->e->export_gpos(out, cap); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
+int mce_shard_get_stats(mce_handle* h, mce_shard_stats* out) {
+  if (!h || !out) return MCE_ERR_BAD_ARG;
+  memset(out, 0, sizeof(*out));
+  out->rank = h->e->be.shard.rank; out->world = h->e->be.shard.world;
+  out->owned_terms = h->e->pstats.owned; out->imported_parents = h->e->pstats.imports; out->local_parents = h->e->gen[h->e->cur].v.n_alive;
+  out->bytes_terms = h->e->pstats.bytes_terms; out->bytes_parents = h->e->pstats.bytes_parents; out->bytes_moments = h->e->pstats.bytes_moments; out->bytes_keys = h->e->pstats.bytes_keys;
   return 0;
 }
 

@@ -17,8 +17,10 @@
 #include "mce_kern_group2.h"
 #include "mce_kern_prop.h"
 #include "mce_kern_cpdf.h"
+#include "mce_kern_part.h"
 
 namespace mce {
+#define PTRACE(x) do { if (getenv("MCE_TRACE")) { fprintf(stderr, "[r%d s%d] %s\n", be.shard.rank, master_step, x); fflush(stderr); } } while (0)
 
 // reference error bits, cauchy_constants.hpp:104-116
 enum { ERROR_COVARIANCE_UNSTABLE_ANY_STEP = 0, ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT = 1,
@@ -106,9 +108,10 @@ class Engine {
   // ---- device state ----
   struct GenStore {
     GenView v; DevBuf<BE> g_m, cells, alive, A, p, b, keys, G, rbm, rpf, gmax;
+    DevBuf<BE> gpos;                    // partitioned estimator: global alive rank of every local survivor
     std::vector<int> alive_per_shape;   // survivors per shape
     long long sum_cells = 0;            // total table cells of the survivors
-  } gen[2];
+  } gen[2], imp;                        // imp: the parents this rank's terms descend from, fetched from their home ranks (partitioned estimator)
   int cur = 0;
   DevBuf<BE> wsA, wsp, wsb, wsm, wsSgn, wsXor, wsTpB, wsTpBc;
   DevBuf<BE> cpVal0, cpCache, cpXs, cpOut, cpYs, cpRecs, cpV, cpBad;   // point-wise marginal cpdf (mce_kern_cpdf.h)
@@ -118,6 +121,13 @@ class Engine {
   DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
   DevBuf<BE> ftrF, ftrWide, grpOrder, grpStart, aliveFlag, diagBuf, unkBuf, initBuf;
   DevBuf<BE> bigGroups, bigParts, bigCnt, bigRows, bigFlags, bigKeys;
+  // ---- partitioned estimator (mce_kern_part.h): every term lives on one rank ----
+  DevBuf<BE> ptKeys, ptAllKeys, ptAllSorted, ptIdx0, ptIdx1, ptSplit, ptDest, ptCnt, ptRunOff, ptSend, ptRecv, ptGk, ptGkS, ptOrd, ptGidx, ptNold;
+  DevBuf<BE> ptIKey, ptIKeyS, ptIIdx, ptIIdxS, ptFlag, ptPos, ptIList, ptRList, ptSeg, ptNImp, ptReq, ptPRecS, ptPRecR, ptIgpos, ptBxG, ptSKey, ptSAll, ptHost, ptGg;
+  DevBuf<BE> iwsSgn, iwsXor, iwsTpB, iwsTpBc, txA, txp, txq, txb, txmeta, txcmap;
+  std::vector<int> g_alive_per_shape;           // survivors per shape over all ranks
+  int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order
+  struct PartStats { long long bytes_terms = 0, bytes_parents = 0, bytes_moments = 0, bytes_keys = 0; int imports = 0, owned = 0; double ev_xchg_ms = 0; } pstats;
   bool phase_timing = false;                    // mce_options.phase_timing
   int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
   long long big_scratch_cap = 6LL << 30;       // bytes of addend rows above which group splitting is skipped for a step
@@ -147,10 +157,15 @@ class Engine {
                          &gen[1].g_m, &gen[1].cells, &gen[1].alive, &gen[1].A, &gen[1].p, &gen[1].b, &gen[1].keys, &gen[1].G,
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
                          &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
+                         &gen[0].gpos, &gen[1].gpos, &imp.g_m, &imp.cells, &imp.alive, &imp.A, &imp.p, &imp.b, &imp.keys, &imp.G, &imp.rbm, &imp.rpf, &imp.gmax, &imp.gpos,
+                         &ptKeys, &ptAllKeys, &ptAllSorted, &ptIdx0, &ptIdx1, &ptSplit, &ptDest, &ptCnt, &ptRunOff, &ptSend, &ptRecv, &ptGk, &ptGkS, &ptOrd, &ptGidx, &ptNold,
+                         &ptIKey, &ptIKeyS, &ptIIdx, &ptIIdxS, &ptFlag, &ptPos, &ptIList, &ptRList, &ptSeg, &ptNImp, &ptReq, &ptPRecS, &ptPRecR, &ptIgpos, &ptBxG, &ptSKey, &ptSAll, &ptHost, &ptGg,
+                         &iwsSgn, &iwsXor, &iwsTpB, &iwsTpBc, &txA, &txp, &txq, &txb, &txmeta, &txcmap,
                          &scratchI0, &scratchI1, &scratchI2, &scratchI3, &scratchK0, &scratchK1, &ftrF, &ftrWide, &grpOrder, &grpStart,
                          &aliveFlag, &diagBuf, &unkBuf, &initBuf, &bigGroups, &bigParts, &bigCnt, &bigRows, &bigFlags, &bigKeys, &cpVal0, &cpCache, &cpXs, &cpOut, &cpYs, &cpRecs, &cpV, &cpBad};
     for (auto* b : all) { b->be = &be; all_bufs.push_back(b); }
-    gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0);
+    gen[0].alive_per_shape.assign(NSHAPE, 0); gen[1].alive_per_shape.assign(NSHAPE, 0); imp.alive_per_shape.assign(NSHAPE, 0);
+    g_alive_per_shape.assign(NSHAPE, 0);
   }
   ~Engine() {}
   std::vector<DevBuf<BE>*> all_bufs;
@@ -311,30 +326,315 @@ class Engine {
 
   int step_first(double msmt, const double* H, double gamma) {
     StepParams sp = make_params(msmt, nullptr, nullptr, nullptr, H, gamma, nullptr, nullptr, false);
+    const int W = be.shard.world, R = be.shard.rank;        // partitioned estimator: the first term lives on rank 0
     GenStore& ng = gen[cur];
-    std::vector<int> groups(NSHAPE, 0); groups[d] = d + 1;
+    std::vector<int> groups(NSHAPE, 0); if (R == 0) groups[d] = d + 1;
     fill_gen_layout(ng, groups);
-    double* init = (double*)initBuf.ensure(sizeof(double) * (d * d + 2 * d));
-    be.h2d(init, A1.data(), sizeof(double) * d * d);
-    be.h2d(init + d * d, p1.data(), sizeof(double) * d);
-    be.h2d(init + d * d + d, b1.data(), sizeof(double) * d);
     const int nq = 1 + d + d * d;
-    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
-    int* cnt = (int*)unkBuf.ensure(64);
-    KFirstStep k{sp, init, init + d * d, init + d * d + d, ng.v, mom, cnt};
-    size_t smem = sizeof(double) * ((d + 1) * (2 + 2 * d) + 4) + sizeof(int) * (d + 4);
-    be.launch(k, 1, 32, smem);
     std::vector<double> raw(2 * nq); int nt = 0;
-    be.d2h(raw.data(), mom, sizeof(double) * 2 * nq); be.d2h(&nt, cnt, sizeof(int));
+    if (R == 0) {
+      double* init = (double*)initBuf.ensure(sizeof(double) * (d * d + 2 * d));
+      be.h2d(init, A1.data(), sizeof(double) * d * d);
+      be.h2d(init + d * d, p1.data(), sizeof(double) * d);
+      be.h2d(init + d * d + d, b1.data(), sizeof(double) * d);
+      double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+      int* cnt = (int*)unkBuf.ensure(64);
+      KFirstStep k{sp, init, init + d * d, init + d * d + d, ng.v, mom, cnt};
+      size_t smem = sizeof(double) * ((d + 1) * (2 + 2 * d) + 4) + sizeof(int) * (d + 4);
+      be.launch(k, 1, 32, smem);
+      be.d2h(raw.data(), mom, sizeof(double) * 2 * nq); be.d2h(&nt, cnt, sizeof(int));
+    }
+    if (W > 1) {
+      std::vector<long long> mine(2 * nq + 1, 0);
+      memcpy(mine.data(), raw.data(), sizeof(double) * 2 * nq); mine[2 * nq] = nt;
+      const std::vector<long long> all = allgather_ll(mine);
+      memcpy(raw.data(), all.data(), sizeof(double) * 2 * nq); nt = (int)all[2 * nq];
+    }
     finalize_moments(raw.data(), false);        // compute_moments(true): no numerical check on the first step (quirk A.9 iv)
-    ng.v.n_alive = nt;
-    std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0); ng.alive_per_shape[d] = nt;
-    Nt = nt; Nt_muc = nt; ng.sum_cells = (long long)nt << (d - 1);
+    const int nt_loc = R == 0 ? nt : 0;
+    ng.v.n_alive = nt_loc;
+    std::fill(ng.alive_per_shape.begin(), ng.alive_per_shape.end(), 0); ng.alive_per_shape[d] = nt_loc;
+    std::fill(g_alive_per_shape.begin(), g_alive_per_shape.end(), 0); g_alive_per_shape[d] = nt;
+    if (W > 1) { int* gp = (int*)ng.gpos.ensure(sizeof(int) * (size_t)(nt_loc + 4)); be.launch(KIota{nt_loc, gp}, 1, 64, 0); }
+    Nt = nt; Nt_muc = nt; ng.sum_cells = (long long)nt_loc << (d - 1);
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = nt; muc_per_shape = terms_per_shape;
-    if (print_basic_info) post_ftr_moments(sp); else fz = make_cplx(1, 0);       // est:1198-1204
+    if (print_basic_info && W == 1) post_ftr_moments(sp); else fz = make_cplx(1, 0);       // est:1198-1204
     last_mean = mean; last_var = var; last_fz = fz;
     stats.parents = 1; stats.slots = d + 1; stats.terms_after_muc = nt; stats.groups = nt; stats.survivors = nt;
     return 0;
+  }
+
+  // ---- partitioned estimator: host-side collectives ----
+  // all-gather of n 64-bit values per rank through a device buffer (the transports move device memory)
+  std::vector<long long> allgather_ll(const std::vector<long long>& mine) {
+    const int W = be.shard.world, R = be.shard.rank; const size_t n = mine.size();
+    long long* buf = (long long*)ptHost.ensure(sizeof(long long) * n * W);
+    be.h2d(buf + (size_t)R * n, mine.data(), sizeof(long long) * n);
+    be.xchg_begin(); be.xchg_allgather(buf, sizeof(long long) * n); be.xchg_end();
+    std::vector<long long> all(n * W);
+    be.d2h(all.data(), buf, sizeof(long long) * n * W);
+    return all;
+  }
+  // the same block of `bytes` from every rank lands at recv + roff[h] (all-gather with unequal contributions)
+  void allgatherv(const void* send, long long bytes, void* recv, const std::vector<long long>& roff, const std::vector<long long>& rcnt) {
+    const int W = be.shard.world;
+    std::vector<long long> soff(W, 0), scnt(W, bytes);
+    be.xchg_alltoallv(send, soff.data(), scnt.data(), recv, roff.data(), rcnt.data());
+  }
+
+  // Ordered moments (moments_mode 0): every slot's (g, y) is placed at its canonical position of the global slot list and the
+  // list is combined over the ranks (each word has one non-zero contributor, so the integer sum is the value); every rank then
+  // adds ALL slots in the reference's order.  Returns the global slot count; *g_out / *y_out point at the combined list.
+  long long part_gather_slots(const SlotView& sl, const GenStore& pg, cplx** g_out, double** y_out) {
+    KSlotScatter k; memset(&k, 0, sizeof(k));
+    long long ng_slots = 0; int base = 0;
+    for (int m = 0; m < NSHAPE; m++) { k.gslot_begin[m] = ng_slots; k.gshape_base[m] = base; ng_slots += (long long)g_alive_per_shape[m] * (sl.MT[m] + 1); base += g_alive_per_shape[m]; }
+    const size_t words = (size_t)ng_slots * (2 + 2 * d);
+    double* buf = (double*)ptGg.ensure(sizeof(double) * (words + 8));
+    be.memset(buf, 0, sizeof(double) * words);
+    k.sl = sl; k.d = d; k.gpos = pg.gpos.template as<int>(); k.g_out = (cplx*)buf; k.y_out = buf + 2 * ng_slots;
+    if (sl.n_slots > 0) be.launch(k, (int)((sl.n_slots + 127) / 128), 128, 0);
+    be.xchg_begin(); be.xchg_allreduce_u32(buf, words * 2); be.xchg_end();
+    pstats.bytes_moments = (long long)(sizeof(double) * words);
+    *g_out = (cplx*)buf; *y_out = buf + 2 * ng_slots;
+    return ng_slots;
+  }
+
+  // Routes the post-coalignment terms to the owners of their reduction keys and fetches the parents the owned terms descend
+  // from (mce_kern_part.h).  In: the local TermView `tl` (+ slot_of_term) and every rank's (old, child) counts per shape.
+  // Out: *tvx = the owned terms in canonical (gidx) order, `imp` + *iws = the imported parents the G-table kernel reads.
+  void part_exchange(const StepParams& sp, const SlotView& sl, const TermView& tl, const long long* sot, const std::vector<long long>& all_tot,
+                     bool with_tp, GenStore& pg, const ParentWs& ws, TermView* tvx, ParentWs* iws) {
+    const int W = be.shard.world, R = be.shard.rank;
+    std::vector<std::vector<long long>> nloc(W, std::vector<long long>(NSHAPE, 0));
+    std::vector<long long> gN(NSHAPE, 0), gtb(NSHAPE + 1, 0);
+    for (int h = 0; h < W; h++) for (int m = 0; m < NSHAPE; m++) { nloc[h][m] = all_tot[(size_t)h * 2 * NSHAPE + m] + all_tot[(size_t)h * 2 * NSHAPE + NSHAPE + m]; gN[m] += nloc[h][m]; }
+    for (int m = 0; m < NSHAPE; m++) gtb[m + 1] = gtb[m] + gN[m];
+    const long long nl = tl.t_begin[NSHAPE], gtot = gtb[NSHAPE];
+    pstats = PartStats();
+    PTRACE("1. reduction keys");
+    // 1. reduction keys of the local terms, all ranks' keys per shape, splitters
+    unsigned long long* kloc = (unsigned long long*)ptKeys.ensure(sizeof(unsigned long long) * (size_t)(nl + 4));
+    unsigned long long* kall = (unsigned long long*)ptAllKeys.ensure(sizeof(unsigned long long) * (size_t)(gtot + 4));
+    unsigned long long* ksrt = (unsigned long long*)ptAllSorted.ensure(sizeof(unsigned long long) * (size_t)(gtot + 4));
+    int* dmy0 = (int*)ptIdx0.ensure(sizeof(int) * (size_t)(gtot + 4)); int* dmy1 = (int*)ptIdx1.ensure(sizeof(int) * (size_t)(gtot + 4));
+    unsigned long long* split_d = (unsigned long long*)ptSplit.ensure(sizeof(unsigned long long) * NSHAPE * PART_MAXW);
+    for (int m = 1; m < NSHAPE; m++) if (tl.n[m] > 0) be.launch(KPartKeys{tl, m, d, tr_order[0], kloc + tl.t_begin[m]}, (tl.n[m] + 127) / 128, 128, 0);
+    be.xchg_begin();
+    for (int m = 1; m < NSHAPE; m++) if (gN[m] > 0) {
+      std::vector<long long> roff(W), rcnt(W); long long o = gtb[m];
+      for (int h = 0; h < W; h++) { roff[h] = o * 8; rcnt[h] = nloc[h][m] * 8; o += nloc[h][m]; }
+      allgatherv(kloc + tl.t_begin[m], 8LL * tl.n[m], kall, roff, rcnt);
+    }
+    be.xchg_end();
+    pstats.bytes_keys = 8 * gtot;
+    be.memset(dmy0, 0, sizeof(int) * (size_t)gtot);
+    for (int m = 1; m < NSHAPE; m++) if (gN[m] > 0) {
+      be.sort_pairs(kall + gtb[m], ksrt + gtb[m], dmy0 + gtb[m], dmy1 + gtb[m], (int)gN[m]);
+      be.launch(KPartSplit{ksrt + gtb[m], (int)gN[m], W, split_d + m * PART_MAXW}, W - 1, 128, sizeof(int) * 130);
+    }
+    PTRACE("2. destination of");
+    // 2. destination of every local term, send counts
+    unsigned char* dest = (unsigned char*)ptDest.ensure((size_t)nl + 16);
+    int* cnt_d = (int*)ptCnt.ensure(sizeof(int) * 2 * NSHAPE * PART_MAXW); int* cur_d = cnt_d + NSHAPE * PART_MAXW;
+    be.memset(cnt_d, 0, sizeof(int) * 2 * NSHAPE * PART_MAXW);
+    for (int m = 1; m < NSHAPE; m++) if (tl.n[m] > 0)
+      be.launch(KPartDest{kloc + tl.t_begin[m], tl.n[m], W, split_d + m * PART_MAXW, dest + tl.t_begin[m], cnt_d + m * PART_MAXW}, (tl.n[m] + 127) / 128, 128, sizeof(int) * PART_MAXW);
+    std::vector<int> hc(NSHAPE * PART_MAXW, 0);
+    be.d2h(hc.data(), cnt_d, sizeof(int) * NSHAPE * PART_MAXW);
+    std::vector<long long> mine((size_t)NSHAPE * W, 0);
+    for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = hc[m * PART_MAXW + h];
+    const std::vector<long long> cm = allgather_ll(mine);                 // cm[(src * NSHAPE + m) * W + dst]
+    auto C = [&](int src, int m, int dst) { return cm[((size_t)src * NSHAPE + m) * W + dst]; };
+    PTRACE("3. pack, exchange");
+    // 3. pack, exchange
+    std::vector<long long> sbase(NSHAPE + 1, 0), rbase(NSHAPE + 1, 0), nrecv(NSHAPE, 0), run_off((size_t)NSHAPE * PART_MAXW, 0);
+    for (int m = 0; m < NSHAPE; m++) {
+      long long o = 0;
+      for (int h = 0; h < W; h++) { run_off[(size_t)m * PART_MAXW + h] = o; o += C(R, m, h); nrecv[m] += C(h, m, R); }
+      const long long RW = m >= 1 ? part_rec_words(m, d) : 0;
+      sbase[m + 1] = sbase[m] + (long long)tl.n[m] * RW; rbase[m + 1] = rbase[m] + nrecv[m] * RW;
+    }
+    unsigned long long* sendb = (unsigned long long*)ptSend.ensure(sizeof(unsigned long long) * (size_t)(sbase[NSHAPE] + 4));
+    unsigned long long* recvb = (unsigned long long*)ptRecv.ensure(sizeof(unsigned long long) * (size_t)(rbase[NSHAPE] + 4));
+    long long* run_d = (long long*)ptRunOff.ensure(sizeof(long long) * NSHAPE * PART_MAXW);
+    be.h2d(run_d, run_off.data(), sizeof(long long) * NSHAPE * PART_MAXW);
+    for (int m = 1; m < NSHAPE; m++) if (tl.n[m] > 0) {
+      KPartPack k{sp, pg.v, sl, tl, m, R, pg.gpos.template as<int>(), sot, dest + tl.t_begin[m], run_d + m * PART_MAXW, cur_d + m * PART_MAXW, sendb + sbase[m]};
+      be.launch(k, (tl.n[m] + PART_TB - 1) / PART_TB, 128, KPartPack::smem_bytes());
+    }
+    be.xchg_begin();
+    for (int m = 1; m < NSHAPE; m++) if (gN[m] > 0) {
+      const long long RB = 8LL * part_rec_words(m, d);
+      std::vector<long long> soff(W), scnt(W), roff(W), rcnt(W); long long o = 0;
+      for (int h = 0; h < W; h++) { soff[h] = run_off[(size_t)m * PART_MAXW + h] * RB; scnt[h] = C(R, m, h) * RB; roff[h] = o * RB; rcnt[h] = C(h, m, R) * RB; o += C(h, m, R); }
+      be.xchg_alltoallv(sendb + sbase[m], soff.data(), scnt.data(), recvb + rbase[m], roff.data(), rcnt.data());
+      pstats.bytes_terms += (nrecv[m] - C(R, m, R)) * RB;
+    }
+    be.xchg_end();
+    PTRACE("4. owned terms in");
+    // 4. owned terms in canonical order
+    TermView tv; memset(&tv, 0, sizeof(tv));
+    long long nt = 0, tA = 0, tpq = 0;
+    for (int m = 0; m < NSHAPE; m++) {
+      tv.n[m] = (int)nrecv[m]; tv.t_begin[m] = nt; tv.A_base[m] = tA; tv.pq_base[m] = tpq;
+      nt += nrecv[m]; tA += nrecv[m] * m * d; tpq += nrecv[m] * m;
+    }
+    tv.t_begin[NSHAPE] = nt;
+    tv.A = (double*)txA.ensure(sizeof(double) * (size_t)(tA + 8)); tv.p = (double*)txp.ensure(sizeof(double) * (size_t)(tpq + 8));
+    tv.q = (double*)txq.ensure(sizeof(double) * (size_t)(tpq + 8)); tv.b = (double*)txb.ensure(sizeof(double) * (size_t)(nt + 1) * d);
+    tv.meta = (SlotMeta*)txmeta.ensure(sizeof(SlotMeta) * (size_t)(nt + 1)); tv.cmap = (unsigned char*)txcmap.ensure((size_t)(nt + 1) * MAXM);
+    unsigned long long* gk = (unsigned long long*)ptGk.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    unsigned long long* gks = (unsigned long long*)ptGkS.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    int* oi = (int*)ptIdx0.ensure(sizeof(int) * (size_t)((nt > gtot ? nt : gtot) + 4)); int* ord = (int*)ptOrd.ensure(sizeof(int) * (size_t)(nt + 4));
+    unsigned long long* gidx = (unsigned long long*)ptGidx.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    int* nold_d = (int*)ptNold.ensure(sizeof(int) * NSHAPE);
+    be.memset(nold_d, 0, sizeof(int) * NSHAPE);
+    for (int m = 1; m < NSHAPE; m++) if (tv.n[m] > 0) {
+      const int n = tv.n[m], RW = part_rec_words(m, d); const long long tb = tv.t_begin[m];
+      be.launch(KPartRecKeys{recvb + rbase[m], n, RW, gk + tb, oi + tb}, (n + 127) / 128, 128, 0);
+      be.sort_pairs(gk + tb, gks + tb, oi + tb, ord + tb, n);
+      be.launch(KPartCountOld{gks + tb, n, nold_d + m}, 1, 32, 0);
+      be.launch(KPartUnpack{d, m, tv, recvb + rbase[m], ord + tb, gidx}, (n + PART_TB - 1) / PART_TB, 128, 0);
+    }
+    PTRACE("5. import list");
+    if (getenv("MCE_TRACE") && nt > 0) { std::vector<SlotMeta> hm(nt); be.d2h(hm.data(), tv.meta, sizeof(SlotMeta) * nt); std::vector<unsigned long long> hg(nt); be.d2h(hg.data(), gidx, 8 * nt);
+      for (int i = 0; i < nt && i < 12; i++) fprintf(stderr, "[r%d] term %d newm=%d pbc=%d parent=%d pad=%x gidx=%llx c=%g\n", R, i, hm[i].newm, hm[i].pbc, hm[i].parent, hm[i].pad_, hg[i], hm[i].c_val); }
+    // 5. import list: distinct (parent shape, home rank, alive rank) of the owned terms; every term learns its import index
+    unsigned long long* ik = (unsigned long long*)ptIKey.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    unsigned long long* iks = (unsigned long long*)ptIKeyS.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    int* ii = (int*)ptIIdx.ensure(sizeof(int) * (size_t)(nt + 4)); int* iis = (int*)ptIIdxS.ensure(sizeof(int) * (size_t)(nt + 4));
+    int* flag = (int*)ptFlag.ensure(sizeof(int) * (size_t)(nt + 4)); int* pos = (int*)ptPos.ensure(sizeof(int) * (size_t)(nt + 4));
+    unsigned long long* ilist = (unsigned long long*)ptIList.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
+    int* rlist = (int*)ptRList.ensure(sizeof(int) * (size_t)(nt + 4));
+    int* seg_d = (int*)ptSeg.ensure(sizeof(int) * (NSHAPE * PART_MAXW + 4)); int* nimp_d = (int*)ptNImp.ensure(sizeof(int) * 4);
+    be.memset(nimp_d, 0, sizeof(int) * 4);
+    if (nt > 0) {
+      const int nb = (int)((nt + 127) / 128);
+      be.launch(KImportKeys{tv.meta, nt, ik, ii}, nb, 128, 0);
+      be.sort_pairs(ik, iks, ii, iis, (int)nt);
+      be.launch(KUniqFlags{iks, nt, flag}, nb, 128, 0);
+      be.exclusive_scan(flag, pos, (int)nt);
+      be.launch(KImportAssign{iks, iis, flag, pos, nt, tv.meta, ilist, rlist, nimp_d}, nb, 128, 0);
+    }
+    be.launch(KImportSegs{ilist, nimp_d, W, seg_d}, (NSHAPE * W + 1 + 127) / 128, 128, 0);
+    std::vector<int> seg(NSHAPE * W + 1, 0), nold(NSHAPE, 0);
+    be.d2h(seg.data(), seg_d, sizeof(int) * (NSHAPE * W + 1));
+    be.d2h(nold.data(), nold_d, sizeof(int) * NSHAPE);
+    for (int m = 0; m < NSHAPE; m++) tv.n_old[m] = nold[m];
+    const int n_import = seg[NSHAPE * W];
+    PTRACE("6. requests to th");
+    // 6. requests to the home ranks, parent records back
+    for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = seg[m * W + h + 1] - seg[m * W + h];
+    const std::vector<long long> rq = allgather_ll(mine);                 // rq[(requester * NSHAPE + m) * W + home]
+    auto Q = [&](int req, int m, int home) { return rq[((size_t)req * NSHAPE + m) * W + home]; };
+    std::vector<long long> nreq(NSHAPE, 0), rqb(NSHAPE + 1, 0), gimp(NSHAPE, 0);
+    for (int m = 0; m < NSHAPE; m++) { for (int q = 0; q < W; q++) { nreq[m] += Q(q, m, R); for (int h = 0; h < W; h++) gimp[m] += Q(q, m, h); } rqb[m + 1] = rqb[m] + nreq[m]; }
+    PTRACE("6a");
+    int* reqb = (int*)ptReq.ensure(sizeof(int) * (size_t)(rqb[NSHAPE] + 4));
+    be.xchg_begin();
+    for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) {
+      std::vector<long long> soff(W), scnt(W), roff(W), rcnt(W); long long o = 0;
+      for (int h = 0; h < W; h++) { soff[h] = 4LL * seg[m * W + h]; scnt[h] = 4 * Q(R, m, h); roff[h] = 4 * o; rcnt[h] = 4 * Q(h, m, R); o += Q(h, m, R); }
+      be.xchg_alltoallv(rlist, soff.data(), scnt.data(), reqb + rqb[m], roff.data(), rcnt.data());
+    }
+    be.xchg_end();
+    PTRACE("6b");
+    const int Hcap = cell_count_central_half(max_shape, d);
+    std::vector<ParentRecLayout> lay(NSHAPE);
+    std::vector<long long> psb(NSHAPE + 1, 0), prb(NSHAPE + 1, 0), nimp(NSHAPE, 0);
+    for (int m = 0; m < NSHAPE; m++) {
+      if (m >= 1) { int mt = m + sp.npn; if (mt > max_shape) mt = max_shape; lay[m] = parent_rec_layout(m, d, with_tp ? cell_count_central_half(mt, d) : 0); } else memset(&lay[m], 0, sizeof(lay[m]));
+      nimp[m] = seg[(m + 1) * W > NSHAPE * W ? NSHAPE * W : (m + 1) * W] - seg[m * W];
+      psb[m + 1] = psb[m] + nreq[m] * lay[m].bytes; prb[m + 1] = prb[m] + nimp[m] * lay[m].bytes;
+    }
+    PTRACE("6c");
+    if (getenv("MCE_TRACE")) { for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) { fprintf(stderr, "[r%d] m=%d nreq=%lld nimp=%lld n_alive=%d nt=%lld n_import=%d seg:", R, m, nreq[m], nimp[m], pg.v.n_alive, nt, n_import); for (int h = 0; h <= W; h++) fprintf(stderr, " %d", seg[m * W + h]); fprintf(stderr, "\n"); } }
+    unsigned char* prs = (unsigned char*)ptPRecS.ensure((size_t)psb[NSHAPE] + 64);
+    unsigned char* prr = (unsigned char*)ptPRecR.ensure((size_t)prb[NSHAPE] + 64);
+    for (int m = 1; m < NSHAPE; m++) if (nreq[m] > 0)
+      be.launch(KImportPack{pg.v, ws, with_tp ? 1 : 0, m, d, lay[m], reqb + rqb[m], pg.gpos.template as<int>(), prs + psb[m]}, (int)nreq[m], 64, 0);
+    PTRACE("6d");
+    be.xchg_begin();
+    for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) {
+      const long long B = lay[m].bytes;
+      std::vector<long long> soff(W), scnt(W), roff(W), rcnt(W); long long o = 0;
+      for (int h = 0; h < W; h++) { soff[h] = o * B; scnt[h] = Q(h, m, R) * B; o += Q(h, m, R); roff[h] = (long long)(seg[m * W + h] - seg[m * W]) * B; rcnt[h] = Q(R, m, h) * B; }
+      be.xchg_alltoallv(prs + psb[m], soff.data(), scnt.data(), prr + prb[m], roff.data(), rcnt.data());
+      pstats.bytes_parents += (nimp[m] - Q(R, m, R)) * B;
+    }
+    be.xchg_end();
+    PTRACE("7. the import sto");
+    // 7. the import store: a generation store of its own, addressed like the local one
+    std::vector<int> per(NSHAPE, 0);
+    for (int m = 0; m < NSHAPE; m++) per[m] = (int)nimp[m];
+    fill_gen_layout(imp, per);
+    imp.v.alive = (int*)imp.alive.ensure(sizeof(int) * ((size_t)n_import + 4));
+    imp.v.n_alive = n_import; imp.alive_per_shape = per;
+    memset(iws, 0, sizeof(*iws));
+    iws->sgnmask = (unsigned*)iwsSgn.ensure(sizeof(unsigned) * ((size_t)n_import + 4));
+    iws->bxor = (unsigned*)iwsXor.ensure(sizeof(unsigned) * ((size_t)n_import + 4));
+    iws->tpB_stride = Hcap;
+    if (with_tp) {
+      iws->tpB = (unsigned*)iwsTpB.ensure(sizeof(unsigned) * (size_t)n_import * Hcap + 16);
+      iws->tpB_cells = (int*)iwsTpBc.ensure(sizeof(int) * ((size_t)n_import + 4));
+    }
+    int* igpos = (int*)ptIgpos.ensure(sizeof(int) * ((size_t)n_import + 4));
+    for (int m = 1; m < NSHAPE; m++) if (nimp[m] > 0)
+      be.launch(KImportUnpack{imp.v, *iws, with_tp ? 1 : 0, m, d, lay[m], prr + prb[m], seg[m * W], igpos}, (int)nimp[m], 64, 0);
+    pstats.imports = n_import; pstats.owned = (int)nt;
+    *tvx = tv;
+  }
+
+  // in-place re-orientation masks of the imported parents, combined over the ranks between the two G-table phases
+  void part_bxor_sync(ParentWs& iws) {
+    int gn = 0; for (int m = 0; m < NSHAPE; m++) gn += g_alive_per_shape[m];
+    const int n = imp.v.n_alive;
+    unsigned* glob = (unsigned*)ptBxG.ensure(sizeof(unsigned) * ((size_t)gn + 4));
+    const int* igpos = ptIgpos.template as<int>();
+    be.memset(glob, 0, sizeof(unsigned) * (size_t)gn);
+    if (n > 0) be.launch(KBxorScatter{n, iws.bxor, igpos, glob}, (n + 127) / 128, 128, 0);
+    be.xchg_begin(); be.xchg_allreduce_u32(glob, (size_t)gn); be.xchg_end();
+    if (n > 0) be.launch(KBxorGather{n, iws.bxor, igpos, glob}, (n + 127) / 128, 128, 0);
+  }
+
+  // global alive ranks of the new generation's local survivors + the survivor counts over all ranks
+  void part_assign_gpos(GenStore& ng, const TermView& tv, const int* order_all, const int* gstart_all, const std::vector<int>& gstart_off) {
+    const int W = be.shard.world, n_surv = ng.v.n_alive;
+    unsigned long long* skey = (unsigned long long*)ptSKey.ensure(sizeof(unsigned long long) * ((size_t)n_surv + 4));
+    if (n_surv > 0) {
+      KSurvKeys k; memset(&k, 0, sizeof(k));
+      k.next = ng.v; k.tv = tv; k.n_surv = n_surv; k.order_all = order_all; k.gstart_all = gstart_all; k.gidx = ptGidx.template as<unsigned long long>(); k.skey = skey;
+      for (int m = 0; m < NSHAPE; m++) k.gstart_off[m] = gstart_off[m];
+      be.launch(k, (n_surv + 127) / 128, 128, 0);
+    }
+    std::vector<long long> mine(NSHAPE, 0);
+    for (int m = 0; m < NSHAPE; m++) mine[m] = ng.alive_per_shape[m];
+    const std::vector<long long> cs = allgather_ll(mine);                 // cs[h * NSHAPE + m]
+    KSurvRank k; memset(&k, 0, sizeof(k));
+    std::vector<long long> roff(W), rcnt(W); long long tot = 0;
+    for (int h = 0; h < W; h++) {
+      long long nh = 0;
+      for (int m = 0; m < NSHAPE; m++) { k.L.off[h][m] = tot + nh; k.L.cnt[h][m] = (int)cs[(size_t)h * NSHAPE + m]; nh += cs[(size_t)h * NSHAPE + m]; }
+      roff[h] = 8 * tot; rcnt[h] = 8 * nh; tot += nh;
+    }
+    int base = 0;
+    for (int m = 0; m < NSHAPE; m++) { int g = 0; for (int h = 0; h < W; h++) g += (int)cs[(size_t)h * NSHAPE + m]; k.L.shape_base[m] = base; g_alive_per_shape[m] = g; base += g; }
+    unsigned long long* all = (unsigned long long*)ptSAll.ensure(sizeof(unsigned long long) * ((size_t)tot + 4));
+    be.xchg_begin(); allgatherv(skey, 8LL * n_surv, all, roff, rcnt); be.xchg_end();
+    int* gp = (int*)ng.gpos.ensure(sizeof(int) * ((size_t)n_surv + 4));
+    if (n_surv > 0) {
+      k.next = ng.v; k.n_surv = n_surv; k.W = W; k.skey = skey; k.all = all; k.gpos = gp;
+      be.launch(k, (n_surv + 127) / 128, 128, 0);
+    }
+  }
+  // host copy of the global alive ranks of the local survivors (tests, exporters: canonical order = ascending rank)
+  int export_gpos(int* out, int cap) {
+    const GenStore& g = gen[cur];
+    const int n = g.v.n_alive;
+    if (be.shard.world <= 1) { for (int i = 0; i < n && i < cap; i++) out[i] = i; return n; }
+    if (n > 0 && out) be.d2h(out, g.gpos.p, sizeof(int) * (size_t)(n < cap ? n : cap));
+    return n;
   }
 
   int step_general(double msmt, const double* Phi, const double* Gamma, const double* beta, const double* H, double gamma,
@@ -343,6 +643,8 @@ class Engine {
     StepParams sp = make_params(msmt, Phi, Gamma, beta, H, gamma, B, u, with_tp);
     GenStore& pg = gen[cur]; GenStore& ng = gen[1 - cur];
     const int n_alive = pg.v.n_alive;
+    const int W = be.shard.world, R = be.shard.rank; (void)R;
+    const bool part = W > 1;                 // partitioned estimator: this rank holds n_alive of the parents (possibly none)
     // A caller that rewinds master_step (cauchy_windows.hpp:538, 659 write the field) can drive a window deeper than declared:
     // the per-parent buffers hold max_shape rows, so a time propagation that would append beyond that is refused, not clamped.
     if (with_tp)
@@ -350,6 +652,7 @@ class Engine {
         if (pg.alive_per_shape[m] > 0 && m + sp.npn > max_shape) { error = "time propagation would give a term more than max_shape = " + std::to_string(max_shape) + " hyperplanes (window stepped past its declared depth)"; return -5; }
     const int nq = 1 + d + d * d;
     stats.parents = n_alive;
+    if (part) { long long gn = 0; for (int m = 0; m < NSHAPE; m++) gn += g_alive_per_shape[m]; stats.parents = gn; }
     int* diag = (int*)diagBuf.ensure(sizeof(int) * (16 + NSHAPE + 8)); be.memset(diag, 0, sizeof(int) * (16 + NSHAPE + 8));   // [16] diagnostics, then the survivor bounds per shape
     if (max_shape <= 16 && n_alive > 0) {        // rank structures of the parents' tables (lookups without binary search)
       int mmax = 1; for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) mmax = m;
@@ -372,12 +675,10 @@ class Engine {
       ws.m_tp = (unsigned char*)wsm.ensure((size_t)n_alive + 16);
       be.launch(KTimeProp{sp, pg.v, ws}, (n_alive + 127) / 128, 128, 0);
       if (!skip_post_mu) {
-        const int W = be.shard.world, pch = shard_chunk(n_alive, W);        // term-level sharding: a chunk of parents per rank
-        int tp0 = 0, tp1 = n_alive;
-        if (W > 1) shard_range(n_alive, be.shard.rank, W, &tp0, &tp1);
+        const int tp0 = 0, tp1 = n_alive;
         ws.tpB_stride = Hcap;
-        ws.tpB = (unsigned*)wsTpB.ensure(sizeof(unsigned) * (size_t)pch * W * Hcap);
-        ws.tpB_cells = (int*)wsTpBc.ensure(sizeof(int) * ((size_t)pch * W + 4));
+        ws.tpB = (unsigned*)wsTpB.ensure(sizeof(unsigned) * (size_t)n_alive * Hcap + 16);
+        ws.tpB_cells = (int*)wsTpBc.ensure(sizeof(int) * ((size_t)n_alive + 4));
         int max_mtp = 0;
         for (int m = 1; m < NSHAPE; m++) if (pg.alive_per_shape[m] > 0) max_mtp = m + sp.npn;
         if (max_mtp > max_shape) max_mtp = max_shape;
@@ -389,12 +690,6 @@ class Engine {
           be.launch(KTpDce2{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2::smem_bytes(NWt, nth, d));
         } else {
           be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag, tp0}, tp1 - tp0, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
-        }
-        if (W > 1) {           // every rank receives the B-tables of the other ranks' parents
-          be.xchg_begin();
-          be.xchg_allgather(ws.tpB, sizeof(unsigned) * (size_t)pch * Hcap);
-          be.xchg_allgather(ws.tpB_cells, sizeof(int) * (size_t)pch);
-          be.xchg_end();
         }
       }
     }
@@ -437,18 +732,23 @@ class Engine {
     double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
     // The moment kernel isolates its accumulator warp on one scheduler partition (warp id % 4); that mapping only holds when
     // its CTAs are placed on idle SMs, so the main stream is drained first (measured: 8.4 ms instead of 11.6 ms at 1.1 M slots).
+    // partitioned estimator, ordered moments: the sums run over ALL ranks' slots in the reference's order (bit-exact)
+    const cplx* mom_g = sl.g; const double* mom_y = sl.y; long long mom_n = nslots;
+    if (part) {
+      if (moments_mode == 0) { cplx* gg; double* gy; mom_n = part_gather_slots(sl, pg, &gg, &gy); mom_g = gg; mom_y = gy; stats.slots = mom_n; }
+    }
     be.ev_record(6);
     be.sync();
     be.side_begin();
     be.ev_record_side(4);
-    if (fast_moments) {
+    if (fast_moments && !part) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
       be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
       be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
       be.launch_side(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
     } else {
-      be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
+      be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
     be.ev_record_side(5);
     auto finish_moments = [&]() {
@@ -456,6 +756,16 @@ class Engine {
       be.side_join();
       stats.ev_moments_ms = be.ev_elapsed(4, 5); stats.ev_mu_ms = be.ev_elapsed(0, 6);
       be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
+      if (part && moments_mode != 0) {        // per-rank serial sums, added in rank order: the same result on every rank for a given world size
+        std::vector<long long> mine(2 * nq);
+        memcpy(mine.data(), raw.data(), sizeof(double) * 2 * nq);
+        const std::vector<long long> all = allgather_ll(mine);
+        for (int i = 0; i < 2 * nq; i++) {
+          double acc = 0;
+          for (int h = 0; h < W; h++) { double v; memcpy(&v, &all[(size_t)h * 2 * nq + i], sizeof(double)); acc += v; }
+          raw[i] = acc;
+        }
+      }
       finalize_moments(raw.data(), true);
       sp.gscale = G_SCALE_FACTOR;
     };
@@ -469,6 +779,8 @@ class Engine {
     std::vector<int> tot(2 * NSHAPE);
     be.d2h(tot.data(), totals, sizeof(int) * 2 * NSHAPE);
     stats.ms_moments = toc(tph); tph = tic();
+    std::vector<long long> all_tot;          // partitioned estimator: every rank's (old, child) counts per new shape
+    if (part) { std::vector<long long> mine(tot.begin(), tot.end()); all_tot = allgather_ll(mine); }
 
     TermView tv; memset(&tv, 0, sizeof(tv));
     long long nterms = 0, tA = 0, tpq = 0;
@@ -480,10 +792,19 @@ class Engine {
       if (m < shape_range) muc_per_shape[m] = tv.n[m];
     }
     tv.t_begin[NSHAPE] = nterms;
-    Nt_muc = (int)nterms; stats.terms_after_muc = nterms;
+    long long g_nterms = nterms;
+    if (part) {
+      g_nterms = 0;
+      for (int m = 0; m < NSHAPE; m++) {
+        long long g = 0; for (int h = 0; h < W; h++) g += all_tot[(size_t)h * 2 * NSHAPE + m] + all_tot[(size_t)h * 2 * NSHAPE + NSHAPE + m];
+        if (m < shape_range) muc_per_shape[m] = (int)g;
+        g_nterms += g;
+      }
+    }
+    Nt_muc = (int)g_nterms; stats.terms_after_muc = g_nterms;
     if (skip_post_mu) {          // est:732-733, 806-828: only the counts change on the window's last step
       finish_moments();
-      terms_per_shape = muc_per_shape; Nt = (int)nterms; finished = true;
+      terms_per_shape = muc_per_shape; Nt = (int)g_nterms; finished = true;
       return 0;
     }
 
@@ -495,6 +816,14 @@ class Engine {
     tv.cmap = (unsigned char*)tvcmap.ensure((size_t)(nterms + 1) * MAXM);
     long long* sot = (long long*)slotOfTerm.ensure(sizeof(long long) * (size_t)(nterms + 1));
     be.launch(KRegroup{sp, sl, tv, nchunks, counts, sot}, nchunks, RANK_CHUNK, KRegroup::smem_bytes());
+    ParentWs gws = ws;                       // the parents the G-table kernel reads: the local ones, or the imported ones
+    if (part) {                              // the terms move to the owners of their reduction keys; from here on `tv` holds the owned terms
+      TermView tvx;
+      part_exchange(sp, sl, tv, sot, all_tot, with_tp, pg, ws, &tvx, &gws);
+      tv = tvx; nterms = tv.t_begin[NSHAPE];
+    }
+    PTRACE("exchange done");
+    const GenView& pv = part ? imp.v : pg.v;
     stats.ms_regroup = toc(tph); tph = tic();
 
     be.ev_record(7);
@@ -576,7 +905,7 @@ class Engine {
       if (rounds > (int)nterms + 4) { be.side_join(); error = "FTR resolution did not converge"; return -6; }
     }
     stats.ftr_rounds_max = rounds;
-    if (capture) for (int m : shapes) capture_shape(tv, m, F_all + tv.t_begin[m], ws, with_tp);
+    if (capture) for (int m : shapes) capture_shape(tv, m, F_all + tv.t_begin[m], gws, with_tp, part ? imp : pg);
     for (int m : shapes) {
       const int n = tv.n[m], nb = (n + 127) / 128; const long long tb = tv.t_begin[m];
       int* gstart = gstart_all + tb + m;                       // at most n + 1 entries per shape
@@ -593,7 +922,7 @@ class Engine {
         const int Hm = cell_count_central_half(m, d);
         for (int ph = 0; ph < 2; ph++) {
           const int ix = ph * NSHAPE + m;
-          be.launch(KBigGroups{gstart, cr_d + 2 * m, ph, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix, be.shard.rank, be.shard.world}, nb, 128, 0);
+          be.launch(KBigGroups{gstart, cr_d + 2 * m, ph, big_T, Hm, bgroups + big_slot_base[ix], bparts + big_part_base[ix], bcnt + 2 * ix, bcnt64 + 3 * ix, 0, 1}, nb, 128, 0);
         }
       }
     }
@@ -616,18 +945,8 @@ class Engine {
       n_groups[m] = cr[2 * m];
       n_phase1[m] = cr[2 * m + 1];      // groups rooted at an old term come first (roots ascend, old terms precede children)
     }
-    // Term-level sharding (mce_shard.h): every (phase, shape) block of group slots is padded to a multiple of the world size,
-    // so that the ranks' equal chunks of every output array can be all-gathered in place; padding slots stay dead.
-    const int W = be.shard.world, R = be.shard.rank;
-    std::vector<int> n_layout(n_groups), shift1(NSHAPE, 0);
-    if (W > 1)
-      for (int m : shapes) {
-        const int pad0 = round_up(n_phase1[m], W), pad1 = round_up(n_groups[m] - n_phase1[m], W);
-        n_layout[m] = pad0 + pad1; shift1[m] = pad0 - n_phase1[m];
-      }
-    fill_gen_layout(ng, n_layout);
+    fill_gen_layout(ng, n_groups);
     unsigned char* aflag = (unsigned char*)aliveFlag.ensure((size_t)ng.v.n_groups + 16);
-    if (W > 1) be.memset(aflag, 0, (size_t)ng.v.n_groups);
     const int HC2 = next_pow2(Hcap < 4 ? 4 : Hcap);
     const size_t gsm = KGTable::smem_bytes(HC2);
     long long total_groups = 0;
@@ -650,6 +969,7 @@ class Engine {
         be.memset(bflags, 0, sizeof(int) * (size_t)tf);
       }
     }
+    PTRACE("gtable");
     be.ev_record(2);
     for (int phase = 0; phase < 2; phase++) {
       for (int m = 1; m < NSHAPE; m++) {
@@ -657,9 +977,7 @@ class Engine {
         const int g0 = phase == 0 ? 0 : n_phase1[m], g1 = phase == 0 ? n_phase1[m] : n_groups[m];
         if (g1 <= g0) continue;
         total_groups += g1 - g0;
-        int lo = g0, hi = g1;                                   // this rank's groups of the block
-        if (W > 1) { shard_range(g1 - g0, R, W, &lo, &hi); lo += g0; hi += g0; }
-        const int gshift = phase == 0 ? 0 : shift1[m];
+        const int lo = g0, hi = g1, gshift = 0;
         const int Hm = cell_count_central_half(m, d);
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
         if (max_shape <= 16) {
@@ -673,39 +991,20 @@ class Engine {
           }
           const int* ord = order_all + tv.t_begin[m]; const int* gst = gstart_all + gstart_off[m];
           const size_t smb = KGTable2::smem_bytes(Hcap, NW);
-          KGTable2 k{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
+          KGTable2 k{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
           be.launch(k, hi - lo, nth, smb);
           if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
-            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
-            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
-            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pg.v, ng.v, ws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
+            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
           }
         } else {
-          KGTable k{sp, pg.v, ng.v, ws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
+          KGTable k{sp, pv, ng.v, gws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
           be.launch(k, g1 - g0, nth, gsm);
         }
         stats.gtable_launches++;
       }
-      if (W > 1) {             // all-gather the new terms and tables of this phase; after phase 0 also the re-orientation masks
-        be.xchg_begin();
-        for (int m : shapes) {
-          const int g0 = phase == 0 ? 0 : n_phase1[m], g1 = phase == 0 ? n_phase1[m] : n_groups[m];
-          if (g1 <= g0) continue;
-          const size_t ch = (size_t)shard_chunk(g1 - g0, W);
-          const int gidA = ng.v.gid_begin[m] + (phase == 0 ? 0 : round_up(n_phase1[m], W));
-          const size_t stride = (size_t)ng.v.tab_stride[m];
-          be.xchg_allgather(ng.v.g_m + gidA, ch);
-          be.xchg_allgather(ng.v.cells + gidA, ch * sizeof(int));
-          be.xchg_allgather(aflag + gidA, ch);
-          be.xchg_allgather(gen_A(ng.v, gidA, m, d), ch * m * d * sizeof(double));
-          be.xchg_allgather(gen_p(ng.v, gidA, m), ch * m * sizeof(double));
-          be.xchg_allgather(gen_b(ng.v, gidA, d), ch * d * sizeof(double));
-          be.xchg_allgather(gen_keys(ng.v, gidA, m), ch * stride * sizeof(unsigned));
-          be.xchg_allgather(gen_G(ng.v, gidA, m), ch * stride * sizeof(cplx));
-        }
-        if (phase == 0) be.xchg_allreduce_u32(ws.bxor, (size_t)n_alive);
-        be.xchg_end();
-      }
+      if (part && phase == 0) part_bxor_sync(gws);      // phase 1 reads the re-orientation masks phase 0 wrote, on whichever rank
     }
     be.ev_record(3);
     stats.ev_gtable_ms = be.ev_elapsed(2, 3); stats.ev_ftr_ms = be.ev_elapsed(7, 8);
@@ -732,14 +1031,17 @@ class Engine {
       n_surv = bounds[NSHAPE];
     }
     ng.v.n_alive = n_surv;
+    PTRACE("assign gpos");
+    if (part) part_assign_gpos(ng, tv, order_all, gstart_all, gstart_off);
     stats.diag_alias = hd[0]; stats.diag_hash = hd[1];
     stats.cells_parents = pg.sum_cells; ng.sum_cells = (long long)(unsigned)hd[2] | ((long long)hd[3] << 32); stats.cells_survivors = ng.sum_cells;
     stats.survivors = n_surv;
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0);
-    for (int m = 1; m < shape_range; m++) terms_per_shape[m] = ng.alive_per_shape[m];
+    for (int m = 1; m < shape_range; m++) terms_per_shape[m] = part ? g_alive_per_shape[m] : ng.alive_per_shape[m];
     Nt = n_surv;
+    if (part) { Nt = 0; for (int m = 0; m < NSHAPE; m++) Nt += g_alive_per_shape[m]; stats.survivors = Nt; }
     cur = 1 - cur;
-    if (print_basic_info) post_ftr_moments(sp); else fz = make_cplx(1, 0);           // est:1166-1176 (quirk A.9 iii)
+    if (print_basic_info && !part) post_ftr_moments(sp); else fz = make_cplx(1, 0);           // est:1166-1176 (quirk A.9 iii)
     stats.ms_compact = toc(tph);
     // algorithmic bytes with the ACTUAL table sizes: every compulsory input read once, every output
     // written once, the post-MUC term payload written + read once (FTR is a global barrier). A table cell is
@@ -765,7 +1067,7 @@ class Engine {
     }
   };
 
-  void capture_shape(const TermView& tv, int m, const int* F, const ParentWs& ws, bool with_tp) {
+  void capture_shape(const TermView& tv, int m, const int* F, const ParentWs& ws, bool with_tp, GenStore& pg) {
     CapShape cs; cs.m = m; cs.n = tv.n[m];
     const int n = cs.n;
     cs.A.resize((size_t)n * m * d); cs.p.resize((size_t)n * m); cs.q.resize((size_t)n * m); cs.b.resize((size_t)n * d); cs.cd.resize((size_t)n * 2);
@@ -778,7 +1080,6 @@ class Engine {
     be.d2h(me.data(), tv.meta + tv.t_begin[m], sizeof(SlotMeta) * n);
     be.d2h(cs.cmap.data(), tv.cmap + tv.t_begin[m] * MAXM, (size_t)n * MAXM);
     be.d2h(cs.F.data(), F, sizeof(int) * n);
-    GenStore& pg = gen[cur];
     std::vector<int> alive(pg.v.n_alive), cells(pg.v.n_groups); std::vector<unsigned char> gm(pg.v.n_groups);
     be.d2h(alive.data(), pg.v.alive, sizeof(int) * alive.size());
     be.d2h(cells.data(), pg.v.cells, sizeof(int) * cells.size());
@@ -854,6 +1155,7 @@ class Engine {
     master_step = 0; Nt = 1; numeric_moment_errors = 0; finished = false; skip_post_mu = 0;
     std::fill(terms_per_shape.begin(), terms_per_shape.end(), 0); terms_per_shape[d] = 1;
     gen[0].v.n_alive = 0; gen[1].v.n_alive = 0;
+    std::fill(g_alive_per_shape.begin(), g_alive_per_shape.end(), 0);
     A1 = A0; p1 = p0; b1 = b0;                   // setup_first_term(A0_init, p0_init, b0_init), est:1280
     cur = 0;          // same buffer parity on every pass of a window: the grow-only buffers settle after the first pass
   }

@@ -16,9 +16,12 @@
 
 namespace mce {
 
-enum { MCE_XCHG_ALLGATHER = 0, MCE_XCHG_ALLREDUCE_SUM_U32 = 1 };
+enum { MCE_XCHG_ALLGATHER = 0, MCE_XCHG_ALLREDUCE_SUM_U32 = 1, MCE_XCHG_ALLTOALLV = 2 };
 // op ALLGATHER: `base` holds world chunks of n bytes, chunk `rank` is valid on entry, all are valid on return.
 // op ALLREDUCE_SUM_U32: n 32-bit unsigned values at `base`, summed over the ranks in place.  Returns 0 on success.
+// op ALLTOALLV: `base` points to a mce_alltoallv_args, n = world: scnt[h] bytes at send + soff[h] go to rank h, rcnt[h] bytes
+// from rank h land at recv + roff[h] (the rank's own chunk included).
+struct mce_alltoallv_args { const void* send; void* recv; const long long* soff; const long long* scnt; const long long* roff; const long long* rcnt; };
 typedef int (*mce_exchange_fn)(void* ctx, int op, void* base, long long n);
 
 struct ShardInfo {

@@ -1,12 +1,13 @@
-"""Term-level sharding of one estimator over torch.distributed ranks (one process per GPU) -- host glue for the
-mce_shard_* entry points of include/mce_b200.h (design: csrc/mce_shard.h).
+"""ONE estimator partitioned over torch.distributed ranks (one process per GPU) -- host glue for the mce_shard_* entry
+points of include/mce_b200.h (design: csrc/mce_kern_part.h).
 
 Every rank creates the estimator with identical arguments, calls `init_term_sharding` once before the first step, and then
-makes identical step calls; all ranks end up with bit-identical state and moments.
+makes identical step calls.  Every term lives on one rank; moments and counts come back global on every rank.
 
-transport="nccl": the library opens libnccl.so.2 itself and issues grouped all-gathers on its own CUDA stream; torch.distributed
-is only used to ship the 128-byte NCCL id from rank 0.  transport="callback": the library hands every exchange to Python,
-which runs it over `dist` (used by the CPU tests with the gloo backend and host memory)."""
+transport="nccl": the library opens libnccl.so.2 itself and issues grouped send/recv, all-gathers and all-reduces on its own
+CUDA stream; torch.distributed is only used to ship the 128-byte NCCL id from rank 0.  transport="callback": the library hands
+every exchange to Python, which runs it over `dist` (used by the CPU tests with the gloo backend and host memory).
+moments: "ordered" (bit-identical to one GPU) or "allreduce" (per-rank sums added in rank order; scales)."""
 import ctypes as ct
 
 import numpy as np
@@ -17,11 +18,13 @@ _KEEP = []          # callback objects must outlive the handles that use them
 EXCHANGES = [0, 0]   # callback transport: number of exchanges, bytes received per rank (diagnostics)
 
 
-def init_term_sharding(handle, dist, lib=None, transport="nccl", device=-1):
+def init_term_sharding(handle, dist, lib=None, transport="nccl", device=-1, moments="ordered"):
     lib = lib or _capi.load()
     rank, world = dist.get_rank(), dist.get_world_size()
     if world == 1:
         return
+    if lib.mce_shard_set_moments_mode(handle, {"ordered": 0, "allreduce": 1}[moments]) != 0:
+        raise RuntimeError("mce_shard_set_moments_mode failed")
     if transport == "nccl":
         buf = ct.create_string_buffer(128)
         if rank == 0 and lib.mce_shard_unique_id(device, buf) != 0:
@@ -38,7 +41,29 @@ def init_term_sharding(handle, dist, lib=None, transport="nccl", device=-1):
         try:
             EXCHANGES[0] += 1
             EXCHANGES[1] += n * (world - 1) if op == 0 else 4 * n
-            if op == 0:          # in-place all-gather of `world` chunks of n bytes
+            if op == 2:          # personalised exchange (mce_alltoallv_args); gloo has no all_to_all: pairwise isend / irecv
+                a = ct.cast(base, ct.POINTER(_capi.MceAllToAllV)).contents
+                def view(addr, nbytes):
+                    return torch.from_numpy(np.ctypeslib.as_array((ct.c_ubyte * nbytes).from_address(addr)))
+                reqs, outs = [], []
+                for h in range(world):
+                    sc, rc = a.scnt[h], a.rcnt[h]
+                    if h == rank:
+                        if sc:
+                            ct.memmove(a.recv + a.roff[h], a.send + a.soff[h], sc)
+                        continue
+                    if sc:
+                        reqs.append(dist.isend(view(a.send + a.soff[h], sc).clone(), dst=h))
+                    if rc:
+                        buf = torch.empty(rc, dtype=torch.uint8)
+                        reqs.append(dist.irecv(buf, src=h))
+                        outs.append((buf, a.recv + a.roff[h], rc))
+                    EXCHANGES[1] += rc
+                for r in reqs:
+                    r.wait()
+                for buf, addr, rc in outs:
+                    view(addr, rc)[:] = buf
+            elif op == 0:          # in-place all-gather of `world` chunks of n bytes
                 whole = torch.from_numpy(np.ctypeslib.as_array((ct.c_ubyte * (n * world)).from_address(base)))
                 chunks = [torch.empty(n, dtype=torch.uint8) for _ in range(world)]
                 dist.all_gather(chunks, whole[rank * n:(rank + 1) * n].clone())

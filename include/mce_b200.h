@@ -143,18 +143,33 @@ typedef struct mce_step_stats {
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 
-/* ---- Term-level sharding of ONE estimator over several ranks (one process per GPU; SURVEY.md 8e, csrc/mce_shard.h) ----
- * Every rank creates the estimator with identical arguments and makes identical calls; the DCE-TP and G-table kernels are
- * split over the ranks and their outputs all-gathered, so all ranks hold the same (bit-identical) state and moments.
- * Native transport: NCCL (libnccl.so.2 opened at run time).  Rank 0 calls mce_shard_unique_id, ships the 128 bytes to the
- * other ranks by any means (e.g. torch.distributed.broadcast), then every rank calls mce_shard_init.
+/* ---- ONE estimator partitioned over several ranks (one process per GPU; SURVEY.md 8e, csrc/mce_kern_part.h) ----
+ * Replaces the pthread split of the term list (cauchy_estimator.hpp:886-895, 1604).  Every rank creates the estimator with
+ * identical arguments and makes identical calls; every term lives on exactly ONE rank.  Per step a rank propagates its own
+ * parents, the new terms are routed to the rank that owns their reduction key (all-to-all; range splitters snapped to gaps wider
+ * than the reduction window, so term reduction stays global), the owner fetches the tables of the parents its terms descend
+ * from, builds the G-tables and keeps the survivors.  Moments: mode 0 (default) adds ALL ranks' slots in the reference's
+ * order on every rank (bit-identical to one GPU); mode 1 adds per-rank serial sums in rank order (scales; results depend
+ * on the world size in the last bits).  mce_get_moments / mce_get_terms_per_shape return GLOBAL values on every rank;
+ * mce_export_shape returns the rank's own terms, mce_shard_export_gpos their positions in the canonical (one-GPU) order.
+ * Native transport: NCCL (libnccl.so.2 opened at run time: grouped ncclSend/ncclRecv, ncclAllGather, ncclAllReduce on the
+ * estimator's stream).  Rank 0 calls mce_shard_unique_id, ships the 128 bytes to the other ranks by any means (e.g.
+ * torch.distributed.broadcast), then every rank calls mce_shard_init.
  * Callback transport: the library calls `fn` for every exchange (op 0: in-place all-gather of world chunks of n bytes at
- * base, chunk `rank` valid on entry; op 1: in-place sum of n uint32 over the ranks); the pointers are device pointers on
- * the CUDA build.  Requires at most 16 hyperplanes per term. */
+ * base, chunk `rank` valid on entry; op 1: in-place sum of n uint32 over the ranks; op 2: base points to a
+ * mce_alltoallv_args, n = world); the pointers are device pointers on the CUDA build.  Requires at most 16 hyperplanes per term. */
+typedef struct { const void* send; void* recv; const long long* soff; const long long* scnt; const long long* roff; const long long* rcnt; } mce_alltoallv_args;
+typedef struct {
+  int rank, world, owned_terms, imported_parents, local_parents, pad_;
+  long long bytes_terms, bytes_parents, bytes_moments, bytes_keys;   /* received from other ranks during the last step */
+} mce_shard_stats;
 typedef int (*mce_exchange_fn)(void* ctx, int op, void* base, long long n);
 int mce_shard_unique_id(int device, void* id128);
 int mce_shard_init(mce_handle* h, int rank, int world, const void* id128);
 int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn fn, void* ctx);
+int mce_shard_set_moments_mode(mce_handle* h, int mode);
+int mce_shard_export_gpos(mce_handle* h, int* out /*[cap]*/, int cap);     /* returns the number of local terms */
+int mce_shard_get_stats(mce_handle* h, mce_shard_stats* out);
 
 /* Test hook: keep a host copy of the post-MUC term list and FTR flag arrays of the last step. */
 /* Device self-test of the branch-free IEEE division used by the cpdf grid kernel (csrc/mce_math.h: div_nobranch) on n

@@ -75,6 +75,10 @@ struct EmuBackend {
   void xchg_end() {}
   void xchg_allgather(void* base, size_t bytes_per_rank) { if (bytes_per_rank && shard.fn(shard.fn_ctx, MCE_XCHG_ALLGATHER, base, (long long)bytes_per_rank) != 0) throw std::runtime_error("exchange callback failed"); }
   void xchg_allreduce_u32(void* base, size_t n) { if (n && shard.fn(shard.fn_ctx, MCE_XCHG_ALLREDUCE_SUM_U32, base, (long long)n) != 0) throw std::runtime_error("exchange callback failed"); }
+  void xchg_alltoallv(const void* send, const long long* soff, const long long* scnt, void* recv, const long long* roff, const long long* rcnt) {
+    mce_alltoallv_args a{send, recv, soff, scnt, roff, rcnt};
+    if (shard.fn(shard.fn_ctx, MCE_XCHG_ALLTOALLV, &a, (long long)shard.world) != 0) throw std::runtime_error("exchange callback failed");
+  }
   void make_current() {}
   void side_begin() {}
   template <class K> void launch_side(const K& k, int nblocks, int nthreads, size_t smem) { launch(k, nblocks, nthreads, smem); }

@@ -196,6 +196,86 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
     return out
 
 
+def run_scenario_partitioned(lib, sc, dist, full_upto=0, max_steps=None, transport="callback", moments="ordered", device=-1, on_step=None):
+    """ONE estimator partitioned over the ranks of `dist` (cauchyfriendly_b200/shard.py).  Returns the dump layout of
+    run_scenario with the ranks' term lists merged into the canonical (one-GPU) order through mce_shard_export_gpos, so the
+    result can be compared with the same golden dumps -- on every rank."""
+    from cauchyfriendly_b200.shard import init_term_sharding
+    s = Session(lib, sc, device=device)
+    init_term_sharding(s.h, dist, lib=lib, transport=transport, device=device, moments=moments)
+    out = {}
+    d = sc.d
+    world = dist.get_world_size()
+    try:
+        nrec = len(sc.rec) if max_steps is None else min(max_steps, len(sc.rec))
+        for k in range(nrec):
+            r = sc.rec[k]
+            sp = "s%d" % (k + 1)
+            first = k == 0
+            with_tp = (k % sc.p) == 0 and not first
+            err = s.step(r)
+            mo = s.moments()
+            out[sp + "/info"] = np.array([int(with_tp), mo.skip_post_mu, mo.Nt_after_muc, mo.Nt, err, int(first)], np.int32)
+            out[sp + "/muc/counts"] = s.counts(True)
+            mom = np.zeros(1 + d + d * d, np.complex128)
+            mom[0] = complex(mo.fz[0], mo.fz[1]) if first else complex(mo.fz_after_mu[0], mo.fz_after_mu[1])
+            mom[1 : 1 + d] = np.array(mo.mean[: 2 * d]).view(np.complex128)
+            mom[1 + d :] = np.array(mo.cov[: 2 * d * d]).view(np.complex128)
+            out[sp + "/moments"] = mom
+            out[sp + "/gscale"] = np.array([mo.g_scale_factor])
+            if not mo.skip_post_mu:
+                cnt = s.counts(False)
+                out[sp + "/ftr/counts"] = cnt
+                nloc = lib.mce_shard_export_gpos(s.h, None, 0)
+                gpos = np.zeros(max(nloc, 1), np.int32)
+                lib.mce_shard_export_gpos(s.h, gpos.ctypes.data_as(ct.POINTER(ct.c_int)), nloc)
+                gpos = gpos[:nloc]
+                mine, off = {}, 0
+                for m in range(1, s.shape_range):
+                    if cnt[m] <= 0:
+                        continue
+                    e = s.export_shape(m)
+                    n = e["A"].shape[0]
+                    e["gpos"] = gpos[off:off + n].copy()
+                    off += n
+                    mine[m] = e
+                assert off == nloc, (off, nloc)
+                everyone = [None] * world
+                dist.all_gather_object(everyone, mine)
+                base = 0
+                for m in range(1, s.shape_range):
+                    if cnt[m] <= 0:
+                        continue
+                    parts = [ev[m] for ev in everyone if m in ev and ev[m]["A"].shape[0] > 0]
+                    gp = np.concatenate([q["gpos"] for q in parts])
+                    order = np.argsort(gp, kind="stable")
+                    assert gp.size == cnt[m] and np.array_equal(gp[order], base + np.arange(cnt[m])), "global alive ranks of shape %d are not a permutation" % m
+                    base += cnt[m]
+                    cells = np.concatenate([q["cells"] for q in parts])
+                    starts = np.concatenate([[0], np.cumsum(cells)])[:-1]
+                    keys_l = np.concatenate([q["keys"] for q in parts]); G_l = np.concatenate([q["G"] for q in parts])
+                    e = dict(A=np.concatenate([q["A"] for q in parts])[order], p=np.concatenate([q["p"] for q in parts])[order],
+                             b=np.concatenate([q["b"] for q in parts])[order], cells=cells[order])
+                    e["keys"] = np.concatenate([keys_l[starts[i]:starts[i] + cells[i]] for i in order]) if order.size else keys_l
+                    e["G"] = np.concatenate([G_l[starts[i]:starts[i] + cells[i]] for i in order]) if order.size else G_l
+                    pre = "%s/ftr/m%d" % (sp, m)
+                    out[pre + "/digest"] = key_digest(e["cells"], e["keys"])
+                    out[pre + "/fdigest"] = np.array([_ssum(np.abs(e["G"])), _ssum(e["p"]), _ssum(np.abs(e["b"]))])
+                    if (k + 1) <= full_upto:
+                        for nm in ("A", "p", "b", "cells", "keys", "G"):
+                            out[pre + "/" + nm] = e[nm]
+                        out[pre + "/encB"] = e["keys"].astype(np.int32)
+            if on_step:
+                on_step(k + 1, s, out)
+            if r.shift_kind == SHIFT_EXPLICIT:
+                s.shift_b(r.delta, -1.0)
+            elif r.shift_kind == SHIFT_OWN_MEAN:
+                s.shift_b(np.array(mo.mean[: 2 * d])[0::2], -1.0)
+    finally:
+        s.close()
+    return out
+
+
 def oracle_dump(scenario_path, out_path, full_upto=0, max_steps=None, use_ref=False, print_basic_info=False):
     """Runs the C oracle (or the compiled reference) on a scenario file and reads its dump."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_run_cpu1") if use_ref else os.path.join(ROOT, "oracle", "_build", "mce_oracle_run")

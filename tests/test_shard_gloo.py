@@ -1,7 +1,9 @@
-"""N > 1 path on CPU: term-level sharding of ONE estimator over two torch.distributed ranks (gloo).  Each rank runs the
-sequential emulation of the kernels (test infrastructure) on its share of the DCE-TP parents and of the reduction groups
-and exchanges the results through the library's callback transport; both ranks must reproduce the reference's golden
-dumps bit for bit, exactly like the unsharded run."""
+"""N > 1 path on CPU: ONE estimator partitioned over torch.distributed ranks (gloo).  Every rank runs the sequential emulation
+of the kernels (test infrastructure) on the terms it owns: parents are propagated where they live, the new terms are routed
+to the owners of their reduction keys, parent tables are fetched, survivors stay (csrc/mce_kern_part.h).  The exchanges go
+through the library's callback transport.  With ordered moments the merged term lists, counts and moments of every rank must
+reproduce the reference's golden dumps bit for bit, exactly like the unsharded run; with rank-ordered partial sums the counts
+and key digests stay exact and the moments agree to 1e-9."""
 import os
 import subprocess
 import sys
@@ -15,37 +17,63 @@ import os, sys
 sys.path.insert(0, os.environ["MCE_ROOT"]); sys.path.insert(0, os.path.join(os.environ["MCE_ROOT"], "tests"))
 import torch.distributed as dist
 from compare import compare_dumps
-from harness import load_emu, run_scenario
+from harness import load_emu, run_scenario_partitioned
 from mceio import read_dump, read_scenario
-from cauchyfriendly_b200.shard import init_term_sharding
 dist.init_process_group("gloo")
 lib = load_emu()
 name, steps, full = os.environ["MCE_CASE"].split(":")
 steps, full = int(steps), int(full)
+mode = os.environ.get("MCE_MOMENTS", "ordered")
 gold_dir = os.path.join(os.environ["MCE_ROOT"], "tests", "golden")
 sc = read_scenario(os.path.join(gold_dir, name + ".mces"))
 gold = {n: v for n, v in read_dump(os.path.join(gold_dir, name + ".ref.mced")).items() if n == "header" or int(n.split("/")[0][1:]) <= steps}
-got = run_scenario(lib, sc, full_upto=full, max_steps=steps, capture=True, split=int(os.environ.get("MCE_SPLIT", "0")),
-                   on_create=lambda s: init_term_sharding(s.h, dist, lib=lib, transport="callback"))
+owned = []
+def on_step(k, s, out):
+    from cauchyfriendly_b200._capi import MceShardStats
+    import ctypes as ct
+    st = MceShardStats(); lib.mce_shard_get_stats(s.h, ct.byref(st)); owned.append(st.local_parents)
+got = run_scenario_partitioned(lib, sc, dist, full_upto=full, max_steps=steps, moments=mode, on_step=on_step)
 got = {n: v for n, v in got.items() if n in gold}
-probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
+def skip(n):       # the post-coalignment term lists are a debug capture of the one-GPU path; full term lists only up to step `full`
+    return "/muc/m" in n or ("/ftr/m" in n and n.split("/")[-1] in ("A", "p", "b", "cells", "keys", "G", "encB") and int(n.split("/")[0][1:]) > full)
+if mode == "ordered":
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=skip)
+else:
+    # rank-ordered partial sums: fz (hence every G) moves in the last bits, cells that cancel move more; the discrete results
+    # (counts, keys, hyperplanes) are compared exactly, fz and the mean to 1e-9, G through its digest to 1e-6
+    import numpy as np
+    d = sc.d
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-6, r"/gscale$": 1e-12}, skip=lambda n: skip(n) or n.endswith("/G") or n.endswith("/moments"))
+    for n in gold:
+        if n.endswith("/moments"):
+            a, b = gold[n], got[n]
+            if abs(a[0] - b[0]) > 1e-12 * abs(a[0]) or np.max(np.abs(a[1:1 + d] - b[1:1 + d])) > 1e-9 * np.max(np.abs(a[1:1 + d])):
+                probs.append("%s: fz / mean differ beyond 1e-9" % n)
+missing = [n for n in gold if n not in got and ("/ftr/" in n or n.endswith("/moments") or n.endswith("/info") or n.endswith("counts")) and not skip(n)]
+if missing:
+    probs.append("arrays of the golden dump that the partitioned run did not produce: %s" % missing[:5])
 from cauchyfriendly_b200 import shard
 if shard.EXCHANGES[0] < 10:
     probs.append("the exchange layer was not used (%d calls)" % shard.EXCHANGES[0])
+everyone = [None] * dist.get_world_size()
+dist.all_gather_object(everyone, owned)
+if not all(max(o) > 0 for o in everyone):
+    probs.append("a rank never owned a term: %s" % everyone)
 open(os.environ["MCE_OUT"] + ".%d" % dist.get_rank(), "w").write("\n".join(probs[:20]) if probs else "OK")
 dist.barrier(); dist.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("case,split", [("lti3:8:5", 0), ("lti4_2msmts:8:5", 0), ("leo7:6:3", 0), ("lti3:8:5", 3)])
-def test_term_sharded_estimator_matches_golden_on_every_rank(case, split, tmp_path):
+@pytest.mark.parametrize("case,world,moments", [("lti3:8:5", 2, "ordered"), ("lti4_2msmts:8:5", 2, "ordered"), ("leo7:6:4", 2, "ordered"),
+                                                ("lti3:8:5", 3, "ordered"), ("lti3:5:5", 3, "allreduce"), ("homing3:7:4", 2, "ordered")])
+def test_partitioned_estimator_matches_golden_on_every_rank(case, world, moments, tmp_path):
     from harness import load_emu
     load_emu(rebuild=True)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     out = str(tmp_path / "res")
-    env = dict(os.environ, MCE_ROOT=ROOT, MCE_OUT=out, MCE_CASE=case, MCE_SPLIT=str(split))
-    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+    env = dict(os.environ, MCE_ROOT=ROOT, MCE_OUT=out, MCE_CASE=case, MCE_MOMENTS=moments)
+    subprocess.check_call([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
                            "--master-port", "29519", str(script)], env=env, timeout=900)
-    for r in range(2):
+    for r in range(world):
         assert open(out + ".%d" % r).read() == "OK", "rank %d: %s" % (r, open(out + ".%d" % r).read())
