@@ -180,6 +180,11 @@ int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, 
   h->e->be.make_current();
   try { return h->e->div_selftest(n, seed, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
+int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, const double* y, double* out) {
+  if (!h || n < 0 || d < 0 || d > mce::MAXD || !out || (n > 0 && !g) || (n > 0 && d > 0 && !y)) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
+  try { return h->e->debug_moment_sums(n, d, g, y, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
 int mce_debug_capture(mce_handle* h, int enable) { if (!h) return MCE_ERR_BAD_ARG; h->e->capture = enable != 0; return 0; }
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd, int* meta, uint8_t* cmap, int8_t* csmap, int* F) {
   if (!h || !n_terms) return MCE_ERR_BAD_ARG;

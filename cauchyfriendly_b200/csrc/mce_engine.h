@@ -20,7 +20,6 @@
 #include "mce_kern_part.h"
 
 namespace mce {
-#define PTRACE(x) do { if (getenv("MCE_TRACE")) { fprintf(stderr, "[r%d s%d] %s\n", be.shard.rank, master_step, x); fflush(stderr); } } while (0)
 
 // reference error bits, cauchy_constants.hpp:104-116
 enum { ERROR_COVARIANCE_UNSTABLE_ANY_STEP = 0, ERROR_COVARIANCE_UNSTABLE_CURRENT_STEP_FINAL_MSMT = 1,
@@ -337,7 +336,7 @@ class Engine {
       be.h2d(init, A1.data(), sizeof(double) * d * d);
       be.h2d(init + d * d, p1.data(), sizeof(double) * d);
       be.h2d(init + d * d + d, b1.data(), sizeof(double) * d);
-      double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+      double* mom = (double*)momOut.ensure(sizeof(double) * 4 * nq + 16);
       int* cnt = (int*)unkBuf.ensure(64);
       KFirstStep k{sp, init, init + d * d, init + d * d + d, ng.v, mom, cnt};
       size_t smem = sizeof(double) * ((d + 1) * (2 + 2 * d) + 4) + sizeof(int) * (d + 4);
@@ -412,7 +411,6 @@ class Engine {
     for (int m = 0; m < NSHAPE; m++) gtb[m + 1] = gtb[m] + gN[m];
     const long long nl = tl.t_begin[NSHAPE], gtot = gtb[NSHAPE];
     pstats = PartStats();
-    PTRACE("1. reduction keys");
     // 1. reduction keys of the local terms, all ranks' keys per shape, splitters
     unsigned long long* kloc = (unsigned long long*)ptKeys.ensure(sizeof(unsigned long long) * (size_t)(nl + 4));
     unsigned long long* kall = (unsigned long long*)ptAllKeys.ensure(sizeof(unsigned long long) * (size_t)(gtot + 4));
@@ -433,7 +431,6 @@ class Engine {
       be.sort_pairs(kall + gtb[m], ksrt + gtb[m], dmy0 + gtb[m], dmy1 + gtb[m], (int)gN[m]);
       be.launch(KPartSplit{ksrt + gtb[m], (int)gN[m], W, split_d + m * PART_MAXW}, W - 1, 128, sizeof(int) * 130);
     }
-    PTRACE("2. destination of");
     // 2. destination of every local term, send counts
     unsigned char* dest = (unsigned char*)ptDest.ensure((size_t)nl + 16);
     int* cnt_d = (int*)ptCnt.ensure(sizeof(int) * 2 * NSHAPE * PART_MAXW); int* cur_d = cnt_d + NSHAPE * PART_MAXW;
@@ -446,7 +443,6 @@ class Engine {
     for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = hc[m * PART_MAXW + h];
     const std::vector<long long> cm = allgather_ll(mine);                 // cm[(src * NSHAPE + m) * W + dst]
     auto C = [&](int src, int m, int dst) { return cm[((size_t)src * NSHAPE + m) * W + dst]; };
-    PTRACE("3. pack, exchange");
     // 3. pack, exchange
     std::vector<long long> sbase(NSHAPE + 1, 0), rbase(NSHAPE + 1, 0), nrecv(NSHAPE, 0), run_off((size_t)NSHAPE * PART_MAXW, 0);
     for (int m = 0; m < NSHAPE; m++) {
@@ -472,7 +468,6 @@ class Engine {
       pstats.bytes_terms += (nrecv[m] - C(R, m, R)) * RB;
     }
     be.xchg_end();
-    PTRACE("4. owned terms in");
     // 4. owned terms in canonical order
     TermView tv; memset(&tv, 0, sizeof(tv));
     long long nt = 0, tA = 0, tpq = 0;
@@ -497,9 +492,6 @@ class Engine {
       be.launch(KPartCountOld{gks + tb, n, nold_d + m}, 1, 32, 0);
       be.launch(KPartUnpack{d, m, tv, recvb + rbase[m], ord + tb, gidx}, (n + PART_TB - 1) / PART_TB, 128, 0);
     }
-    PTRACE("5. import list");
-    if (getenv("MCE_TRACE") && nt > 0) { std::vector<SlotMeta> hm(nt); be.d2h(hm.data(), tv.meta, sizeof(SlotMeta) * nt); std::vector<unsigned long long> hg(nt); be.d2h(hg.data(), gidx, 8 * nt);
-      for (int i = 0; i < nt && i < 12; i++) fprintf(stderr, "[r%d] term %d newm=%d pbc=%d parent=%d pad=%x gidx=%llx c=%g\n", R, i, hm[i].newm, hm[i].pbc, hm[i].parent, hm[i].pad_, hg[i], hm[i].c_val); }
     // 5. import list: distinct (parent shape, home rank, alive rank) of the owned terms; every term learns its import index
     unsigned long long* ik = (unsigned long long*)ptIKey.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
     unsigned long long* iks = (unsigned long long*)ptIKeyS.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
@@ -523,14 +515,12 @@ class Engine {
     be.d2h(nold.data(), nold_d, sizeof(int) * NSHAPE);
     for (int m = 0; m < NSHAPE; m++) tv.n_old[m] = nold[m];
     const int n_import = seg[NSHAPE * W];
-    PTRACE("6. requests to th");
     // 6. requests to the home ranks, parent records back
     for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = seg[m * W + h + 1] - seg[m * W + h];
     const std::vector<long long> rq = allgather_ll(mine);                 // rq[(requester * NSHAPE + m) * W + home]
     auto Q = [&](int req, int m, int home) { return rq[((size_t)req * NSHAPE + m) * W + home]; };
     std::vector<long long> nreq(NSHAPE, 0), rqb(NSHAPE + 1, 0), gimp(NSHAPE, 0);
     for (int m = 0; m < NSHAPE; m++) { for (int q = 0; q < W; q++) { nreq[m] += Q(q, m, R); for (int h = 0; h < W; h++) gimp[m] += Q(q, m, h); } rqb[m + 1] = rqb[m] + nreq[m]; }
-    PTRACE("6a");
     int* reqb = (int*)ptReq.ensure(sizeof(int) * (size_t)(rqb[NSHAPE] + 4));
     be.xchg_begin();
     for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) {
@@ -539,7 +529,6 @@ class Engine {
       be.xchg_alltoallv(rlist, soff.data(), scnt.data(), reqb + rqb[m], roff.data(), rcnt.data());
     }
     be.xchg_end();
-    PTRACE("6b");
     const int Hcap = cell_count_central_half(max_shape, d);
     std::vector<ParentRecLayout> lay(NSHAPE);
     std::vector<long long> psb(NSHAPE + 1, 0), prb(NSHAPE + 1, 0), nimp(NSHAPE, 0);
@@ -548,13 +537,10 @@ class Engine {
       nimp[m] = seg[(m + 1) * W > NSHAPE * W ? NSHAPE * W : (m + 1) * W] - seg[m * W];
       psb[m + 1] = psb[m] + nreq[m] * lay[m].bytes; prb[m + 1] = prb[m] + nimp[m] * lay[m].bytes;
     }
-    PTRACE("6c");
-    if (getenv("MCE_TRACE")) { for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) { fprintf(stderr, "[r%d] m=%d nreq=%lld nimp=%lld n_alive=%d nt=%lld n_import=%d seg:", R, m, nreq[m], nimp[m], pg.v.n_alive, nt, n_import); for (int h = 0; h <= W; h++) fprintf(stderr, " %d", seg[m * W + h]); fprintf(stderr, "\n"); } }
     unsigned char* prs = (unsigned char*)ptPRecS.ensure((size_t)psb[NSHAPE] + 64);
     unsigned char* prr = (unsigned char*)ptPRecR.ensure((size_t)prb[NSHAPE] + 64);
     for (int m = 1; m < NSHAPE; m++) if (nreq[m] > 0)
       be.launch(KImportPack{pg.v, ws, with_tp ? 1 : 0, m, d, lay[m], reqb + rqb[m], pg.gpos.template as<int>(), prs + psb[m]}, (int)nreq[m], 64, 0);
-    PTRACE("6d");
     be.xchg_begin();
     for (int m = 1; m < NSHAPE; m++) if (gimp[m] > 0) {
       const long long B = lay[m].bytes;
@@ -564,7 +550,6 @@ class Engine {
       pstats.bytes_parents += (nimp[m] - Q(R, m, R)) * B;
     }
     be.xchg_end();
-    PTRACE("7. the import sto");
     // 7. the import store: a generation store of its own, addressed like the local one
     std::vector<int> per(NSHAPE, 0);
     for (int m = 0; m < NSHAPE; m++) per[m] = (int)nimp[m];
@@ -729,7 +714,7 @@ class Engine {
 
     // ---- moments (K3 tail): serial-order fz, two-level mean/covariance sums ----
     // The sums run on the side stream: nothing before the G-table build needs them, so they overlap regroup + FTR.
-    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    double* mom = (double*)momOut.ensure(sizeof(double) * 4 * nq + 16);
     // The moment kernel isolates its accumulator warp on one scheduler partition (warp id % 4); that mapping only holds when
     // its CTAs are placed on idle SMs, so the main stream is drained first (measured: 8.4 ms instead of 11.6 ms at 1.1 M slots).
     // partitioned estimator, ordered moments: the sums run over ALL ranks' slots in the reference's order (bit-exact)
@@ -822,7 +807,6 @@ class Engine {
       part_exchange(sp, sl, tv, sot, all_tot, with_tp, pg, ws, &tvx, &gws);
       tv = tvx; nterms = tv.t_begin[NSHAPE];
     }
-    PTRACE("exchange done");
     const GenView& pv = part ? imp.v : pg.v;
     stats.ms_regroup = toc(tph); tph = tic();
 
@@ -969,7 +953,6 @@ class Engine {
         be.memset(bflags, 0, sizeof(int) * (size_t)tf);
       }
     }
-    PTRACE("gtable");
     be.ev_record(2);
     for (int phase = 0; phase < 2; phase++) {
       for (int m = 1; m < NSHAPE; m++) {
@@ -1031,7 +1014,6 @@ class Engine {
       n_surv = bounds[NSHAPE];
     }
     ng.v.n_alive = n_surv;
-    PTRACE("assign gpos");
     if (part) part_assign_gpos(ng, tv, order_all, gstart_all, gstart_off);
     stats.diag_alias = hd[0]; stats.diag_hash = hd[1];
     stats.cells_parents = pg.sum_cells; ng.sum_cells = (long long)(unsigned)hd[2] | ((long long)hd[3] << 32); stats.cells_survivors = ng.sum_cells;
@@ -1107,7 +1089,7 @@ class Engine {
     if (n == 0) return;
     cplx* gg = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(n + 8));
     double* yy = (double*)sly.ensure(sizeof(double) * (size_t)(n + 1) * 2 * d);
-    double* mom = (double*)momOut.ensure(sizeof(double) * 2 * nq + 16);
+    double* mom = (double*)momOut.ensure(sizeof(double) * 4 * nq + 16);
     be.launch(KPostFtrMoments{sp, g.v, gg, yy}, (n + 127) / 128, 128, 0);
     be.launch(KMomentsSerial{gg, yy, (long long)n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     std::vector<double> raw(2 * nq);
@@ -1241,6 +1223,20 @@ class Engine {
     const double norm_factor = fz.re, RECIPRICAL_TWO_PI = 1.0 / (2.0 * M_PI);
     for (int k = 0; k < n; k++) zs[k] = 2 * zs[k] * RECIPRICAL_TWO_PI * RECIPRICAL_TWO_PI / norm_factor;   // cpdf_ndim.hpp:1446
     return n;
+  }
+
+  // Test hook: the serial-order moment sums (KMomentsSerial) of caller-supplied per-slot values g[n] (complex) and y[n][dd] (complex);
+  // out[2 * (1 + dd + dd * dd)] receives the sums.
+  int debug_moment_sums(long long n, int dd, const double* g, const double* y, double* out) {
+    const int nq = 1 + dd + dd * dd;
+    cplx* gg = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(n + 8));
+    double* yy = (double*)sly.ensure(sizeof(double) * ((size_t)(n + 1) * 2 * (dd > 0 ? dd : 1)));
+    double* mom = (double*)momOut.ensure(sizeof(double) * 4 * nq + 16);
+    if (n > 0) be.h2d(gg, g, sizeof(cplx) * (size_t)n);
+    if (n > 0 && dd > 0) be.h2d(yy, y, sizeof(double) * (size_t)n * 2 * dd);
+    be.launch(KMomentsSerial{gg, yy, n, dd, mom}, nq, 512, KMomentsSerial::smem_bytes(dd));
+    be.d2h(out, mom, sizeof(double) * 2 * nq);
+    return 0;
   }
 
   // device self-test of div_nobranch (mce_math.h): out[0] = flagged-ok pairs that differ from a / b, out[1] = ok pairs

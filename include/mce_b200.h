@@ -175,6 +175,10 @@ int mce_shard_get_stats(mce_handle* h, mce_shard_stats* out);
 /* Device self-test of the branch-free IEEE division used by the cpdf grid kernel (csrc/mce_math.h: div_nobranch) on n
  * pseudo-random operand pairs: out[0] = pairs flagged valid whose value differs from a / b (must be 0), out[1] = valid pairs. */
 int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, unsigned long long* out /*[2]*/);
+/* Test hook for the moment sums (csrc/mce_kern_prop.h: KMomentsSerial): fz = sum g, mean_j = sum g y_j, cov_jk = -sum (g y_j) y_k over
+ * n caller-supplied slots, every real accumulator in slot order exactly like the dependent chain of cauchy_estimator.hpp:307-338.
+ * g: n complex values, y: n x d complex values (d may be 0: only fz), out: 2 * (1 + d + d*d) doubles. */
+int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, const double* y, double* out);
 int mce_debug_capture(mce_handle* h, int enable);
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,
                         int* meta /*[n][8]*/, uint8_t* cmap /*[n][32]*/, int8_t* csmap /*[n][32]*/, int* F /*[n]*/);
