@@ -10,8 +10,13 @@ One bench *step* = one full pass of that 12-MU window through CauchyEstimator::s
   value  : child terms / s, device time (CUDA events on the engine's stream, summed over the 12 step() calls)
   e2e    : same metric, wall clock around the reference-facing C-ABI calls with HOST buffers (every step() call
            uploads Phi/Gamma/H/... and downloads the moment sums; nothing is cached between passes)
-  N > 1  : one independent window per GPU (the reference's SlidingWindowManager runs one estimator process per
-           window, cauchy_windows.hpp:353-376), aggregate child terms/s, max-over-ranks time.  scaling = "weak".
+  N > 1  : ONE window partitioned over the GPUs (every term lives on one rank: terms are routed to the owners of their
+           reduction keys over NCCL send/recv, parent tables are fetched from their home ranks, the moment sums run in the
+           reference's order on every rank -- csrc/mce_kern_part.h), scaling = "strong".  The window is the example's
+           sliding-window depth (num_windows = 5, leo_satellite_7state_gps.cpp:585: 15 MUs, 17 M child terms) so that there is
+           something to partition; the line also carries the same window on ONE GPU measured in the same run
+           (`one_gpu_same_window`) and the round-1 figure of N independent 12-MU windows (`replicas`).
+           --shard windows restores the replica run as the main line (scaling = "weak").
 --impl reference times the reference's own CPU implementation (oracle/_ref/ref_run_cpu8, the unmodified
 reference compiled with its default NUM_CPUS = 8) on the SAME full window (one pass; `config` is identical in both
 arms) and, for repeatability, on the prefix MUs 1..9, which both arms report as `matched`.
@@ -30,7 +35,15 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 SCEN = os.path.join(ROOT, "tests", "golden", "leo7.mces")
 WORKLOAD = "leo7_gps_d7_p3_window4 (12 MUs, tests/golden/leo7.mces)"
+SCEN_DEEP = os.path.join(ROOT, "tests", "golden", "leo7_w5.mces")
+WORKLOAD_DEEP = "leo7_gps_d7_p3_window5 (15 MUs, tests/golden/leo7_w5.mces)"
 METRIC = "child_terms_per_sec"
+
+
+def _workload(args):
+    """N = 1: the 12-MU window of the reference's own example run; N > 1 (one window partitioned): its 15-MU sliding-window depth."""
+    deep = args.window == 5 or (args.window == 0 and args.gpus > 1 and args.shard == "terms")
+    return (SCEN_DEEP, WORKLOAD_DEEP) if deep else (SCEN, WORKLOAD)
 
 
 def _peaks():
@@ -86,7 +99,8 @@ def _child_terms(rows):
     return tot
 
 
-def run_reference_sample(n_mu):
+def run_reference_sample(n_mu, scen=None):
+    scen = scen or SCEN
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_run_cpu8")
     kind = "reference"
     if not os.path.exists(exe):
@@ -95,7 +109,7 @@ def run_reference_sample(n_mu):
         if not os.path.exists(exe):
             subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
     t0 = time.time()
-    out = subprocess.check_output([exe, SCEN, "--time-only", "--max-steps", str(n_mu)], stderr=subprocess.DEVNULL).decode()
+    out = subprocess.check_output([exe, scen, "--time-only", "--max-steps", str(n_mu)], stderr=subprocess.DEVNULL).decode()
     wall = time.time() - t0
     rows = _parse_ref_lines(out)
     step_ms = sum(r[3] for r in rows)
@@ -105,12 +119,12 @@ def run_reference_sample(n_mu):
 MATCHED_MUS = 9          # prefix of the window both arms also report on its own (cheap enough to repeat on the CPU)
 
 
-def _config(n_mus):
+def _config(n_mus, workload=WORKLOAD):
     """Identical in both arms: the workload (inputs) both time.  Everything arm-specific lives in other keys of the line --
     including the child-term count: the reference's 8-thread build walks the terms in another order than its 1-thread build
     (the canonical order this repository reproduces bit for bit), elects other reduction-group roots and from MU 10 on carries
     ~13 % more terms through the same window (2 402 755 child terms against 2 115 431)."""
-    return {"workload": WORKLOAD, "mus_per_step": n_mus}
+    return {"workload": workload, "mus_per_step": n_mus}
 
 
 def reference_arm(args):
@@ -121,6 +135,9 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    scen, workload = _workload(args)
+    if scen == SCEN_DEEP:
+        return reference_arm_deep(args, scen, workload)
     for _ in range(min(1, args.warmup)):
         run_reference_sample(MATCHED_MUS)
     full = []
@@ -159,6 +176,32 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def reference_arm_deep(args, scen, workload):
+    """N > 1: the GPU arm partitions the 15-MU window.  One pass of that window takes the reference ~7 minutes on 8 threads (its
+    throughput falls with depth), so each step is the bounded sample MUs 1..12 of the same window (about 20 s); `value` is the
+    reference's child terms/s on that sample -- an UPPER bound of its throughput on the whole window."""
+    n_mu = 12
+    passes = []
+    t0 = time.time()
+    for _ in range(max(1, args.steps)):
+        kind, rows, ms, _ = run_reference_sample(n_mu, scen)
+        passes.append((rows, ms))
+        if time.time() - t0 > 150.0:
+            break
+    tot_ms = sum(ms for _, ms in passes); tot_child = sum(_child_terms(rows) for rows, _ in passes)
+    value = tot_child / (tot_ms / 1e3)
+    cores = 8 if kind == "reference" else 1
+    sample = "MUs 1..%d of the 15-MU window, %d pass(es) (%d child terms, %.1f s of step() time each); %s" % (
+        n_mu, len(passes), tot_child // len(passes), tot_ms / 1e3 / len(passes), "unmodified reference, NUM_CPUS=8 pthreads" if kind == "reference" else "plain-C oracle port, 1 thread")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "child terms/s", "n_gpus": args.gpus, "steps": len(passes),
+            "warmup": 0, "ms_per_step": tot_ms / len(passes), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": _config(15, workload), "child_terms_per_step": tot_child // len(passes),
+            "detail": {"ms_per_mu": [r[3] for r in passes[0][0]], "sampled_mus": n_mu},
+            "cpu_baseline": {"value": value, "unit": "child terms/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "child terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -175,12 +218,13 @@ def gpu_arm(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = load_product()
-    sc = read_scenario(SCEN)
+    scen, workload = _workload(args)
+    sc = read_scenario(scen)
     s = Session(lib, sc, device=local_rank)
     term_sharded = dist is not None and args.shard == "terms"
     if term_sharded:
         from cauchyfriendly_b200.shard import init_term_sharding
-        init_term_sharding(s.h, dist, lib=lib, transport="nccl", device=local_rank)
+        init_term_sharding(s.h, dist, lib=lib, transport="nccl", device=local_rank, moments=args.moments)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     def one_pass(collect):
@@ -210,9 +254,15 @@ def gpu_arm(args):
                 s.shift_b(r.delta, -1.0)
         mo = s.moments()
         wall = time.perf_counter() - wall0
+        if term_sharded and collect:
+            from cauchyfriendly_b200._capi import MceShardStats
+            import ctypes as ct
+            ss = MceShardStats(); lib.mce_shard_get_stats(s.h, ct.byref(ss))
+            phases = dict(owned_terms=ss.owned_terms, imported_parents=ss.imported_parents, local_parents=ss.local_parents,
+                          mb_terms=ss.bytes_terms / 1e6, mb_parent_tables=ss.bytes_parents / 1e6, mb_keys=ss.bytes_keys / 1e6)
         lib.mce_reset(s.h)
         return dict(ev_ms=ev_ms, wall_s=wall, child=child, gt_ms=gt_ms, gt_bytes=gt_bytes, gt_launch=gt_launch, h2d=h2d, d2h=d2h,
-                    launches=launches, heaviest=heaviest, Nt=mo.Nt, pre_ev=pre_ev, pre_child=pre_child, pre_wall=pre_wall)
+                    launches=launches, heaviest=heaviest, Nt=mo.Nt, pre_ev=pre_ev, pre_child=pre_child, pre_wall=pre_wall, shard=phases)
 
     for _ in range(max(3, args.warmup)):
         one_pass(False)
@@ -245,6 +295,37 @@ def gpu_arm(args):
             c = torch.tensor([child], dtype=torch.int64, device="cuda")
             dist.all_reduce(c, op=dist.ReduceOp.SUM)
             child = int(c[0])
+    # N > 1, one window partitioned: the same window on ONE GPU (rank 0 alone) and the replica figure (one 12-MU window per GPU)
+    secondary = {}
+    if term_sharded:
+        def solo(scn, passes):
+            sc1 = read_scenario(scn)
+            s1 = Session(lib, sc1, device=local_rank)
+            ev, ch = 0.0, 0
+            for it in range(passes + 1):
+                prev = 1
+                for k, r in enumerate(sc1.rec):
+                    s1.step(r)
+                    st = s1.stats()
+                    if it > 0:
+                        ev += st.ev_step_ms; ch += st.terms_after_muc - prev
+                    prev = st.survivors if k + 1 < len(sc1.rec) else st.terms_after_muc
+                    if r.shift_kind == SHIFT_EXPLICIT:
+                        s1.shift_b(r.delta, -1.0)
+                lib.mce_reset(s1.h)
+            s1.close()
+            return ev / 1e3, ch
+        if rank == 0:
+            ev1, ch1 = solo(scen, 2)
+            secondary["one_gpu_same_window"] = {"value": ch1 / ev1, "ms_per_step": 1e3 * ev1 / 2, "passes": 2}
+        dist.barrier()
+        evr, chr_ = solo(SCEN, 3)
+        t = torch.tensor([evr], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        c = torch.tensor([chr_], dtype=torch.int64, device="cuda"); dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        secondary["replicas"] = {"value": int(c[0]) / float(t[0]), "ms_per_step": 1e3 * float(t[0]) / 3, "workload": WORKLOAD, "scaling": "weak", "passes": 3}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, acc[-1]["shard"])
+        secondary["partition_last_mu"] = gathered
     if rank == 0:
         peaks, which = _peaks()
         a0 = acc[-1]
@@ -261,13 +342,13 @@ def gpu_arm(args):
         line = {"metric": METRIC, "value": child / ev_s, "unit": "child terms/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": 1e3 * ev_s / args.steps, "higher_is_better": True, "scaling": "strong" if term_sharded else "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": _config(len(sc.rec)), "child_terms_per_step": child // (args.steps * (1 if term_sharded else world)),
+                "config": _config(len(sc.rec), workload), "child_terms_per_step": child // (args.steps * (1 if term_sharded else world)),
                 "matched": {"mus": MATCHED_MUS, "child_terms": a0["pre_child"], "value": sum(a["pre_child"] for a in acc) / (sum(a["pre_ev"] for a in acc) / 1e3),
                             "e2e_value": sum(a["pre_child"] for a in acc) / sum(a["pre_wall"] for a in acc), "ms": sum(a["pre_ev"] for a in acc) / len(acc), "passes": len(acc)},
                 "detail": {"ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
                            "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
-                           "parallelism": ("one window, terms sharded over %d gpus (NCCL all-gather of DCE-TP and G-table outputs)" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "moments": "reference serial order (bit-exact)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
+                           "parallelism": ("one window partitioned over %d gpus: terms routed to the owners of their reduction keys (NCCL send/recv), parent tables fetched from their home ranks" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
+                           "moments": "reference serial order (bit-exact)" if not term_sharded or args.moments == "ordered" else "per-rank serial sums added in rank order (last bits depend on N)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
                 "e2e": {"value": child / wall_s, "unit": "child terms/s", "h2d_bytes_per_step": a0["h2d"], "d2h_bytes_per_step": a0["d2h"]},
                 "gpu_launches": int(sum(a["launches"] for a in acc)),
                 "clocks": sampler.summary(),
@@ -275,6 +356,9 @@ def gpu_arm(args):
                              "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                              "traffic": traffic, "bytes_per_launch_algorithmic": gt_bytes_per_launch, "ms_per_launch": gt_ms_per_launch},
                 "timed_region_wall_s": region_s}
+        line.update(secondary)
+        if "one_gpu_same_window" in secondary:
+            line["strong_scaling_speedup"] = secondary["one_gpu_same_window"]["ms_per_step"] / line["ms_per_step"]
         # CPU baseline: the reference itself on this box's host cores, bounded sample (MUs 1..9 of the same window)
         if world == 1 and not args.no_cpu_baseline:
             kind, rows, ms, _ = run_reference_sample(12 if not args.short_cpu_baseline else MATCHED_MUS)
@@ -298,8 +382,10 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--short-cpu-baseline", action="store_true", help="cpu_baseline leg on MUs 1..9 only (2 s instead of ~30 s)")
     ap.add_argument("--ref-full-passes", type=int, default=1, help="--impl reference: passes of the FULL window `value` is measured on")
-    ap.add_argument("--shard", default="windows", choices=["windows", "terms"],
-                    help="N > 1: one window per GPU (default, weak scaling) or ONE window with its terms sharded over the GPUs (strong scaling)")
+    ap.add_argument("--shard", default="terms", choices=["windows", "terms"],
+                    help="N > 1: ONE window partitioned over the GPUs (default, strong scaling) or one independent window per GPU (weak scaling)")
+    ap.add_argument("--window", type=int, default=0, choices=[0, 4, 5], help="time steps of the window: 4 (12 MUs) or 5 (15 MUs); 0 = 4 at N = 1, 5 for a partitioned window")
+    ap.add_argument("--moments", default="ordered", choices=["ordered", "allreduce"], help="partitioned window: moment sums in the reference's order (bit-exact) or per-rank sums added in rank order")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)
