@@ -35,7 +35,7 @@ class MceAllToAllV(ct.Structure):      # mce_alltoallv_args
 
 class MceShardStats(ct.Structure):     # mce_shard_stats
     _fields_ = [("rank", ct.c_int), ("world", ct.c_int), ("owned_terms", ct.c_int), ("imported_parents", ct.c_int), ("local_parents", ct.c_int), ("pad_", ct.c_int),
-                ("bytes_terms", ct.c_longlong), ("bytes_parents", ct.c_longlong), ("bytes_moments", ct.c_longlong), ("bytes_keys", ct.c_longlong)]
+                ("bytes_terms", ct.c_longlong), ("bytes_parents", ct.c_longlong), ("bytes_moments", ct.c_longlong), ("bytes_keys", ct.c_longlong), ("ms_stage", ct.c_double * 8)]
 
 
 EXCHANGE_FN = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_longlong)

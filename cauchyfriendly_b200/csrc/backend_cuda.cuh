@@ -157,7 +157,7 @@ struct CudaBackend {
     if (nccl.comm && nccl.CommDestroy) { nccl.CommDestroy(nccl.comm); nccl.comm = nullptr; }
     if (cub_tmp) cudaFree(cub_tmp);
     cub_tmp = nullptr; cub_tmp_bytes = 0;
-    for (int i = 0; i < 12; i++) if (evs[i]) { cudaEventDestroy(evs[i]); evs[i] = nullptr; }
+    for (int i = 0; i < 24; i++) if (evs[i]) { cudaEventDestroy(evs[i]); evs[i] = nullptr; }
     if (side_ev) cudaEventDestroy(side_ev);
     if (side) cudaStreamDestroy(side);
     side = nullptr; side_ev = nullptr;
@@ -187,7 +187,7 @@ struct CudaBackend {
   }
   double toc(double t0) { return tic() - t0; }
   // device-side timing with CUDA events on the launching stream (no host synchronisation until ev_elapsed)
-  cudaEvent_t evs[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evs[24] = {};
   void ev_record(int i) {
     if (!evs[i]) MCE_CUDA_CHECK(cudaEventCreate(&evs[i]));
     MCE_CUDA_CHECK(cudaEventRecord(evs[i], stream));

@@ -247,6 +247,7 @@ int mce_shard_get_stats(mce_handle* h, mce_shard_stats* out) {
   out->rank = h->e->be.shard.rank; out->world = h->e->be.shard.world;
   out->owned_terms = h->e->pstats.owned; out->imported_parents = h->e->pstats.imports; out->local_parents = h->e->gen[h->e->cur].v.n_alive;
   out->bytes_terms = h->e->pstats.bytes_terms; out->bytes_parents = h->e->pstats.bytes_parents; out->bytes_moments = h->e->pstats.bytes_moments; out->bytes_keys = h->e->pstats.bytes_keys;
+  for (int i = 0; i < 8; i++) out->ms_stage[i] = h->e->pstats.ms[i];
   return 0;
 }
 

@@ -126,7 +126,7 @@ class Engine {
   DevBuf<BE> iwsSgn, iwsXor, iwsTpB, iwsTpBc, txA, txp, txq, txb, txmeta, txcmap;
   std::vector<int> g_alive_per_shape;           // survivors per shape over all ranks
   int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order
-  struct PartStats { long long bytes_terms = 0, bytes_parents = 0, bytes_moments = 0, bytes_keys = 0; int imports = 0, owned = 0; double ev_xchg_ms = 0; } pstats;
+  struct PartStats { long long bytes_terms = 0, bytes_parents = 0, bytes_moments = 0, bytes_keys = 0; int imports = 0, owned = 0; double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } pstats;   // ms: CUDA-event stage times of the exchange
   bool phase_timing = false;                    // mce_options.phase_timing
   int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
   long long big_scratch_cap = 6LL << 30;       // bytes of addend rows above which group splitting is skipped for a step
@@ -411,6 +411,7 @@ class Engine {
     for (int m = 0; m < NSHAPE; m++) gtb[m + 1] = gtb[m] + gN[m];
     const long long nl = tl.t_begin[NSHAPE], gtot = gtb[NSHAPE];
     pstats = PartStats();
+    be.ev_record(12);
     // 1. reduction keys of the local terms, all ranks' keys per shape, splitters
     unsigned long long* kloc = (unsigned long long*)ptKeys.ensure(sizeof(unsigned long long) * (size_t)(nl + 4));
     unsigned long long* kall = (unsigned long long*)ptAllKeys.ensure(sizeof(unsigned long long) * (size_t)(gtot + 4));
@@ -431,6 +432,7 @@ class Engine {
       be.sort_pairs(kall + gtb[m], ksrt + gtb[m], dmy0 + gtb[m], dmy1 + gtb[m], (int)gN[m]);
       be.launch(KPartSplit{ksrt + gtb[m], (int)gN[m], W, split_d + m * PART_MAXW}, W - 1, 128, sizeof(int) * 130);
     }
+    be.ev_record(13);
     // 2. destination of every local term, send counts
     unsigned char* dest = (unsigned char*)ptDest.ensure((size_t)nl + 16);
     int* cnt_d = (int*)ptCnt.ensure(sizeof(int) * 2 * NSHAPE * PART_MAXW); int* cur_d = cnt_d + NSHAPE * PART_MAXW;
@@ -443,6 +445,7 @@ class Engine {
     for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = hc[m * PART_MAXW + h];
     const std::vector<long long> cm = allgather_ll(mine);                 // cm[(src * NSHAPE + m) * W + dst]
     auto C = [&](int src, int m, int dst) { return cm[((size_t)src * NSHAPE + m) * W + dst]; };
+    be.ev_record(14);
     // 3. pack, exchange
     std::vector<long long> sbase(NSHAPE + 1, 0), rbase(NSHAPE + 1, 0), nrecv(NSHAPE, 0), run_off((size_t)NSHAPE * PART_MAXW, 0);
     for (int m = 0; m < NSHAPE; m++) {
@@ -468,6 +471,7 @@ class Engine {
       pstats.bytes_terms += (nrecv[m] - C(R, m, R)) * RB;
     }
     be.xchg_end();
+    be.ev_record(15);
     // 4. owned terms in canonical order
     TermView tv; memset(&tv, 0, sizeof(tv));
     long long nt = 0, tA = 0, tpq = 0;
@@ -492,6 +496,7 @@ class Engine {
       be.launch(KPartCountOld{gks + tb, n, nold_d + m}, 1, 32, 0);
       be.launch(KPartUnpack{d, m, tv, recvb + rbase[m], ord + tb, gidx}, (n + PART_TB - 1) / PART_TB, 128, 0);
     }
+    be.ev_record(16);
     // 5. import list: distinct (parent shape, home rank, alive rank) of the owned terms; every term learns its import index
     unsigned long long* ik = (unsigned long long*)ptIKey.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
     unsigned long long* iks = (unsigned long long*)ptIKeyS.ensure(sizeof(unsigned long long) * (size_t)(nt + 4));
@@ -515,6 +520,7 @@ class Engine {
     be.d2h(nold.data(), nold_d, sizeof(int) * NSHAPE);
     for (int m = 0; m < NSHAPE; m++) tv.n_old[m] = nold[m];
     const int n_import = seg[NSHAPE * W];
+    be.ev_record(17);
     // 6. requests to the home ranks, parent records back
     for (int m = 0; m < NSHAPE; m++) for (int h = 0; h < W; h++) mine[(size_t)m * W + h] = seg[m * W + h + 1] - seg[m * W + h];
     const std::vector<long long> rq = allgather_ll(mine);                 // rq[(requester * NSHAPE + m) * W + home]
@@ -539,6 +545,7 @@ class Engine {
     }
     unsigned char* prs = (unsigned char*)ptPRecS.ensure((size_t)psb[NSHAPE] + 64);
     unsigned char* prr = (unsigned char*)ptPRecR.ensure((size_t)prb[NSHAPE] + 64);
+    be.ev_record(18);
     for (int m = 1; m < NSHAPE; m++) if (nreq[m] > 0)
       be.launch(KImportPack{pg.v, ws, with_tp ? 1 : 0, m, d, lay[m], reqb + rqb[m], pg.gpos.template as<int>(), prs + psb[m]}, (int)nreq[m], 64, 0);
     be.xchg_begin();
@@ -550,6 +557,7 @@ class Engine {
       pstats.bytes_parents += (nimp[m] - Q(R, m, R)) * B;
     }
     be.xchg_end();
+    be.ev_record(19);
     // 7. the import store: a generation store of its own, addressed like the local one
     std::vector<int> per(NSHAPE, 0);
     for (int m = 0; m < NSHAPE; m++) per[m] = (int)nimp[m];
@@ -567,7 +575,9 @@ class Engine {
     int* igpos = (int*)ptIgpos.ensure(sizeof(int) * ((size_t)n_import + 4));
     for (int m = 1; m < NSHAPE; m++) if (nimp[m] > 0)
       be.launch(KImportUnpack{imp.v, *iws, with_tp ? 1 : 0, m, d, lay[m], prr + prb[m], seg[m * W], igpos}, (int)nimp[m], 64, 0);
+    be.ev_record(20);
     pstats.imports = n_import; pstats.owned = (int)nt;
+    for (int i = 0; i < 8; i++) pstats.ms[i] = be.ev_elapsed(12 + i, 13 + i);     // keys+splitters, destinations, term exchange, unpack, import list, requests, parent pack+exchange, import store
     *tvx = tv;
   }
 

@@ -162,6 +162,8 @@ typedef struct { const void* send; void* recv; const long long* soff; const long
 typedef struct {
   int rank, world, owned_terms, imported_parents, local_parents, pad_;
   long long bytes_terms, bytes_parents, bytes_moments, bytes_keys;   /* received from other ranks during the last step */
+  double ms_stage[8];   /* CUDA-event times of the exchange stages of the last step: keys + splitters, destinations, term pack + exchange,
+                           unpack, import list, requests, parent-record pack + exchange, import store */
 } mce_shard_stats;
 typedef int (*mce_exchange_fn)(void* ctx, int op, void* base, long long n);
 int mce_shard_unique_id(int device, void* id128);

@@ -53,7 +53,7 @@ struct EmuBackend {
   void memset(void* p, int v, size_t n) { ::memset(p, v, n); }
   double tic() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
   double toc(double t0) { return tic() - t0; }
-  double ev_t[12] = {0};
+  double ev_t[24] = {0};
   void ev_record(int i) { ev_t[i] = tic(); }
   void ev_record_side(int i) { ev_t[i] = tic(); }
   double ev_elapsed(int i0, int i1) { return ev_t[i1] - ev_t[i0]; }

@@ -25,6 +25,9 @@ python tools/gen_scenarios.py tests/golden      # again: the deep-declared varia
 $R tests/golden/lti3_deep.mces         tests/golden/lti3_deep.ref.mced         --full-upto 4    # max_shape 22
 $R tests/golden/lti4_2pnoise_deep.mces tests/golden/lti4_2pnoise_deep.ref.mced --full-upto 3    # max_shape 18
 $R tests/golden/lti3_3msmts_deep.mces  tests/golden/lti3_3msmts_deep.ref.mced  --full-upto 5    # max_shape 18
+# the example's sliding-window depth (5 time steps = 15 MUs): recorded with foo_steps = 5, golden for MUs 1..13 (19 minutes on one thread)
+[ -f tests/golden/leo7_w5.mces ] || oracle/_ref/ref_gen_leo7 tests/golden/leo7_w5.mces 5
+[ -f tests/golden/leo7_w5.ref.mced ] || $R tests/golden/leo7_w5.mces tests/golden/leo7_w5.ref.mced --full-upto 0 --max-steps 13
 # the 8-thread reference (shipping default NUM_CPUS=8), informational: counts and moments only
 oracle/_ref/ref_run_cpu8 tests/golden/leo7.mces tests/golden/leo7.ref8.mced --full-upto 0
 ls -la tests/golden
