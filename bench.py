@@ -333,7 +333,7 @@ def gpu_arm(args):
         gt_bytes_per_launch = sum(a["gt_bytes"] for a in acc) / max(1, sum(a["gt_launch"] for a in acc))
         achieved = gt_bytes_per_launch / (gt_ms_per_launch * 1e-3) / 1e9 if gt_ms_per_launch > 0 else 0.0
         traffic = None
-        tf = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        tf = os.path.join(ROOT, "profiles", "traffic_r02.json")      # ncu pass of tools/gpu_profile.sh on this build (not measured in this run)
         if os.path.exists(tf):
             try:
                 traffic = json.load(open(tf)).get("gtable_dram_bytes_per_launch")
@@ -354,7 +354,7 @@ def gpu_arm(args):
                 "clocks": sampler.summary(),
                 "roofline": {"bound": "hbm", "kernel": "KGTable (child B-table + G-table build per reduction group)", "achieved": achieved,
                              "peak": peaks["hbm_gbs"], "peak_source": which, "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                             "traffic": traffic, "bytes_per_launch_algorithmic": gt_bytes_per_launch, "ms_per_launch": gt_ms_per_launch},
+                             "traffic": traffic, "traffic_source": "profiles/traffic_r02.json (ncu dram__bytes_read + dram__bytes_write over every KGTable launch of one cold pass, tools/gpu_profile.sh)" if traffic else None, "bytes_per_launch_algorithmic": gt_bytes_per_launch, "ms_per_launch": gt_ms_per_launch},
                 "timed_region_wall_s": region_s}
         line.update(secondary)
         if "one_gpu_same_window" in secondary:
