@@ -185,7 +185,7 @@ class Engine {
     // every other kernel whose shared memory grows with the deepest shape of the window, at that shape
     const int cgen = cell_count_general(max_shape, d);
     const size_t need_mu = KMsmtUpdate2::smem_bytes(max_shape, d), need_ftr = KFtrRoundTiled::smem_bytes(max_shape, d);
-    const size_t need_tp = max_shape <= 16 ? KTpDce2::smem_bytes((1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1, 128, d)
+    const size_t need_tp = max_shape <= 16 ? KTpDce2T<2>::smem_bytes((1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1, 128, d)
                                            : KTpDce::smem_bytes(next_pow2(DCE_STORAGE_MULT * cgen), next_pow2(cgen + 1), 128);
     const size_t worst = need_mu > need_ftr ? (need_mu > need_tp ? need_mu : need_tp) : (need_ftr > need_tp ? need_ftr : need_tp);
     if (worst > 227 * 1024) {
@@ -682,7 +682,15 @@ class Engine {
         const int nth = 128;
         if (max_shape <= 16) {
           const int NWt = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
-          be.launch(KTpDce2{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2::smem_bytes(NWt, nth, d));
+          switch (d) {        // the vertex solver is specialised per state dimension (its d x d systems live in registers)
+            case 2: be.launch(KTpDce2T<2>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<2>::smem_bytes(NWt, nth, d)); break;
+            case 3: be.launch(KTpDce2T<3>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<3>::smem_bytes(NWt, nth, d)); break;
+            case 4: be.launch(KTpDce2T<4>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<4>::smem_bytes(NWt, nth, d)); break;
+            case 5: be.launch(KTpDce2T<5>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<5>::smem_bytes(NWt, nth, d)); break;
+            case 6: be.launch(KTpDce2T<6>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<6>::smem_bytes(NWt, nth, d)); break;
+            case 7: be.launch(KTpDce2T<7>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<7>::smem_bytes(NWt, nth, d)); break;
+            default: be.launch(KTpDce2T<8>{sp, pg.v, ws, NWt, diag, tp0}, tp1 - tp0, nth, KTpDce2T<8>::smem_bytes(NWt, nth, d)); break;
+          }
         } else {
           be.launch(KTpDce{sp, pg.v, ws, vis_cap, acc_cap, diag, tp0}, tp1 - tp0, nth, KTpDce::smem_bytes(vis_cap, acc_cap, nth));
         }

@@ -15,21 +15,83 @@
 
 namespace mce {
 
+// Vertex of d hyperplanes with the reference's acceptance tests (cell_enumeration.hpp:741-776: PLU with partial pivoting, reject when
+// singular or cond_1 > 1e12 from the explicit inverse) for a COMPILE-TIME dimension: every loop is unrolled and every array index is
+// static, so the d x d system, the permutation and the right-hand sides live in registers (no shared-memory matrix, no local memory) and
+// the d independent columns of the inverse give the scheduler instruction-level parallelism.  Same operations in the same order as
+// solve_vertex / solve_vertex_s (mce_kern_group.h), which stay the readable restatement and serve the max_shape > 16 kernel.
+#if defined(__CUDA_ARCH__)
+#define MCE_UNROLL _Pragma("unroll")
+#else
+#define MCE_UNROLL
+#endif
+template <int D>
+MCE_HD bool solve_vertex_r(const double* sA, const int* combo, const double* b_pert, double* vertex) {
+  double M[D][D], bc[D];
+  MCE_UNROLL for (int j = 0; j < D; j++) {
+    const double* row = sA + combo[j] * D;
+    MCE_UNROLL for (int l = 0; l < D; l++) M[j][l] = row[l];
+    bc[j] = b_pert[combo[j]];
+  }
+  double norm_val = -1;
+  MCE_UNROLL for (int i = 0; i < D; i++) { double v = 0; MCE_UNROLL for (int j = 0; j < D; j++) v += fabs(M[j][i]); if (v > norm_val) norm_val = v; }
+  int P[D];
+  MCE_UNROLL for (int j = 0; j < D; j++) {
+    double pivot = PLU_EPS; int pi = -1;
+    MCE_UNROLL for (int i = j; i < D; i++) { const double v = M[i][j]; if (fabs(v) > fabs(pivot)) { pivot = v; pi = i; } }
+    if (pi == -1) return false;
+    MCE_UNROLL for (int i = j + 1; i < D; i++)
+      if (i == pi) { MCE_UNROLL for (int q = 0; q < D; q++) { const double t = M[j][q]; M[j][q] = M[i][q]; M[i][q] = t; } }
+    P[j] = pi;
+    const double piv = M[j][j];
+    MCE_UNROLL for (int k = j + 1; k < D; k++) {
+      const double temp = M[k][j] / piv;
+      M[k][j] = temp;
+      MCE_UNROLL for (int q = j + 1; q < D; q++) M[k][q] -= temp * M[j][q];
+    }
+  }
+  int Preg[D], P_T[D];                               // perm_transpose with static indices
+  MCE_UNROLL for (int i = 0; i < D; i++) Preg[i] = i;
+  MCE_UNROLL for (int i = 0; i < D; i++) {
+    MCE_UNROLL for (int k = 0; k < D; k++) if (k == P[i] && k != i) { const int t = Preg[i]; Preg[i] = Preg[k]; Preg[k] = t; }
+  }
+  MCE_UNROLL for (int i = 0; i < D; i++) { MCE_UNROLL for (int k = 0; k < D; k++) if (k == Preg[i]) P_T[k] = i; }
+  double inv_norm = -1;
+  MCE_NOUNROLL for (int c = 0; c <= D; c++) {        // columns of the inverse, then the right-hand side: one solve body
+    if (c == D && norm_val * inv_norm > COND_EPS) return false;
+    double w[D];
+    MCE_UNROLL for (int k = 0; k < D; k++) {
+      double v = 0;
+      MCE_UNROLL for (int i = 0; i < D; i++) if (P_T[i] == k) v = (c == D) ? bc[i] : (i == c ? 1.0 : 0.0);
+      w[k] = v;
+    }
+    MCE_UNROLL for (int i = 0; i < D; i++) { double sol = w[i]; MCE_UNROLL for (int j = 0; j < i; j++) sol -= M[i][j] * w[j]; w[i] = sol; }
+    MCE_UNROLL for (int i = D - 1; i >= 0; i--) { double sol = w[i]; MCE_UNROLL for (int j = D - 1; j > i; j--) sol -= M[i][j] * w[j]; w[i] = sol / M[i][i]; }
+    if (c < D) { double v = 0; MCE_UNROLL for (int j = 0; j < D; j++) v += fabs(w[j]); if (v > inv_norm) inv_norm = v; }
+    else { MCE_UNROLL for (int j = 0; j < D; j++) vertex[j] = w[j]; }
+  }
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------
 // K2 for max_shape <= 16: DCE-TP with bitmaps.  The visited set F[2^m] of cell_enumeration.hpp:735 is a 2^m-bit
 // bitmap (atomicOr tells the first visitor), "restriction is a parent cell" (ce:790-798) is a bit test in the
 // parent's key bitmap, "the opposite was accepted too" (ce:816-852) a bit test in the accepted bitmap, and the
 // surviving half is enumerated in ascending key order from that bitmap -- no hash table, no sort.
 // ---------------------------------------------------------------------------------------------
-struct KTpDce2 {
-  static constexpr int kMaxThreads = 128, kMinBlocks = 6;
+template <int D>
+struct KTpDce2T {
+  // the vertex systems live in registers (solve_vertex_r: 2 D^2 registers for the matrix alone).  Measured at D = 7 on the LEO7 window (MU 10, 9.9 M vertices):
+  // 2 / 3 / 4 / 5 / 6 CTAs per SM = 5.5 / 4.4 / 4.0 / 4.4 / 4.6 ms -- occupancy beats a spill-free matrix -- against 5.3 ms for the shared-memory solver
+  static constexpr int kMaxThreads = 128, kMinBlocks = D <= 4 ? 8 : (D <= 7 ? 4 : 3);
   StepParams sp; GenView gen; ParentWs ws; int NW /* 2^max_shape / 32 */; int* diag;
-  int r0 = 0;                           // first parent of this launch (term-level sharding: a rank takes a range of parents)
-  static MCE_HD size_t smem_bytes(int NW, int nthreads, int d) {
-    return sizeof(double) * (MAXM * MAXD + (size_t)d * d * nthreads) + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
+  int r0 = 0;                           // first parent of this launch
+  static MCE_HD size_t smem_bytes(int NW, int nthreads, int) {
+    return sizeof(double) * (MAXM * MAXD) + sizeof(unsigned) * (3 * (size_t)NW + 2 * (size_t)nthreads + 8) + sizeof(unsigned short) * ((size_t)NW + 16 + 1024);
   }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int r = r0 + c.block(), d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
+    constexpr int d = D;
+    const int r = r0 + c.block(), gid = gen.alive[r], phc = gen_m(gen, gid), m = ws.m_tp[r], pcells = gen.cells[gid];
     const unsigned* pkeys = gen_keys(gen, gid, phc);
     unsigned* out = ws.tpB + (long long)r * ws.tpB_stride;
     if (m == phc) {                       // Gamma fully coaligned: B is unchanged (est:680-685)
@@ -45,8 +107,7 @@ struct KTpDce2 {
       return;
     }
     double* sA = (double*)c.smem();
-    double* sAc = sA + MAXM * MAXD;                      // [d*d][nthreads] one vertex system per thread
-    unsigned* bmVis = (unsigned*)(sAc + (size_t)d * d * c.nthreads());      // visited sign vectors (m bits)
+    unsigned* bmVis = (unsigned*)(sA + MAXM * MAXD);     // visited sign vectors (m bits)
     unsigned* bmAcc = bmVis + NW;                        // accepted sign vectors
     unsigned* bmPar = bmAcc + NW;                        // parent keys (phc bits)
     unsigned* niv = bmPar + NW;
@@ -70,19 +131,24 @@ struct KTpDce2 {
         cmask[tid] = 0;
         const long long ci = base + tid;
         if (ci >= ncombo) return;
-        int combo[MAXD]; double bc[MAXD], vertex[MAXD];
-        double* Ac = sAc + tid;            // this thread's d x d system, element e at Ac[e * NT]
-        unrank_combo(ci, m, d, combo);
-        unsigned cm = 0;
-        for (int j = 0; j < d; j++) {
-          for (int l = 0; l < d; l++) Ac[(j * d + l) * NT] = sA[combo[j] * d + l];
-          bc[j] = sp.b_pert[combo[j]]; cm |= (1u << combo[j]);
+        int combo[D]; double vertex[D];
+        {                                  // unrank_combo with static indices
+          long long idx = ci; int x = 0;
+          MCE_UNROLL for (int i = 0; i < D; i++) {
+            for (;; x++) { const long long cnt = (long long)binom_u64(m - 1 - x, D - 1 - i); if (idx < cnt) break; idx -= cnt; }
+            combo[i] = x++;
+          }
         }
-        if (!solve_vertex_s(Ac, NT, bc, vertex, d)) return;
+        unsigned cm = 0;
+        MCE_UNROLL for (int j = 0; j < D; j++) cm |= (1u << combo[j]);
+        if (!solve_vertex_r<D>(sA, combo, sp.b_pert, vertex)) return;
         unsigned sgn = 0;
         for (int ac = 0; ac < m; ac++) {
           if ((cm >> ac) & 1u) continue;
-          if ((dot_lr(sA + ac * d, vertex, d) - sp.b_pert[ac]) < 0) sgn |= (1u << ac);
+          const double* row = sA + ac * D;
+          double dot = 0;
+          MCE_UNROLL for (int l = 0; l < D; l++) dot += row[l] * vertex[l];
+          if ((dot - sp.b_pert[ac]) < 0) sgn |= (1u << ac);
         }
         niv[tid] = sgn; cmask[tid] = cm;
       });
