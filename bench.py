@@ -348,7 +348,9 @@ def gpu_arm(args):
                 "detail": {"ms_per_mu_mean": 1e3 * ev_s / (args.steps * len(sc.rec)),
                            "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
                            "parallelism": ("one window partitioned over %d gpus: terms routed to the owners of their reduction keys (NCCL send/recv), parent tables fetched from their home ranks" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
-                           "moments": "reference serial order (bit-exact)" if not term_sharded or args.moments == "ordered" else "per-rank serial sums added in rank order (last bits depend on N)", "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
+                           "moments": "reference serial order (bit-exact)" if not term_sharded or args.moments == "ordered" else (
+                               "Re fz bit-exact (exact scan of the serial chain over all ranks' slots => counts, keys and G bit-exact); Im fz, mean, covariance: per-rank serial sums added in rank order" if args.moments == "hybrid"
+                               else "per-rank serial sums added in rank order (last bits depend on N)"), "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
                 "e2e": {"value": child / wall_s, "unit": "child terms/s", "h2d_bytes_per_step": a0["h2d"], "d2h_bytes_per_step": a0["d2h"]},
                 "gpu_launches": int(sum(a["launches"] for a in acc)),
                 "clocks": sampler.summary(),
@@ -385,7 +387,9 @@ if __name__ == "__main__":
     ap.add_argument("--shard", default="terms", choices=["windows", "terms"],
                     help="N > 1: ONE window partitioned over the GPUs (default, strong scaling) or one independent window per GPU (weak scaling)")
     ap.add_argument("--window", type=int, default=0, choices=[0, 4, 5], help="time steps of the window: 4 (12 MUs) or 5 (15 MUs); 0 = 4 at N = 1, 5 for a partitioned window")
-    ap.add_argument("--moments", default="ordered", choices=["ordered", "allreduce"], help="partitioned window: moment sums in the reference's order (bit-exact) or per-rank sums added in rank order")
+    ap.add_argument("--moments", default="hybrid", choices=["ordered", "hybrid", "allreduce"],
+                    help="partitioned window: every moment sum in the reference's order on every rank (ordered: all bit-exact, the chain does not scale); Re fz by an exact scan over all ranks' slots "
+                         "and the other sums per rank (hybrid, default: every count, key and G bit-exact); or all sums per rank (allreduce)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)

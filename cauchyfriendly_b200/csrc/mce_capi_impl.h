@@ -185,6 +185,11 @@ int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, co
   h->e->be.make_current();
   try { return h->e->debug_moment_sums(n, d, g, y, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
+int mce_debug_sum_scan(mce_handle* h, long long n, const double* g, double* out) {
+  if (!h || n < 0 || !out || (n > 0 && !g)) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
+  try { return h->e->debug_sum_scan(n, g, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
 int mce_debug_capture(mce_handle* h, int enable) { if (!h) return MCE_ERR_BAD_ARG; h->e->capture = enable != 0; return 0; }
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd, int* meta, uint8_t* cmap, int8_t* csmap, int* F) {
   if (!h || !n_terms) return MCE_ERR_BAD_ARG;
@@ -232,7 +237,7 @@ int mce_shard_init_callback(mce_handle* h, int rank, int world, mce_exchange_fn 
 }
 
 int mce_shard_set_moments_mode(mce_handle* h, int mode) {
-  if (!h || mode < 0 || mode > 1) return MCE_ERR_BAD_ARG;
+  if (!h || mode < 0 || mode > 2) return MCE_ERR_BAD_ARG;
   h->e->moments_mode = mode;
   return 0;
 }

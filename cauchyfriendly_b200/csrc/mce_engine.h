@@ -125,7 +125,9 @@ class Engine {
   DevBuf<BE> ptIKey, ptIKeyS, ptIIdx, ptIIdxS, ptFlag, ptPos, ptIList, ptRList, ptSeg, ptNImp, ptReq, ptPRecS, ptPRecR, ptIgpos, ptBxG, ptSKey, ptSAll, ptHost, ptGg;
   DevBuf<BE> iwsSgn, iwsXor, iwsTpB, iwsTpBc, txA, txp, txq, txb, txmeta, txcmap;
   std::vector<int> g_alive_per_shape;           // survivors per shape over all ranks
-  int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order
+  int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order;
+                                                // 2: like 1, but Re fz -- the one sum that feeds back into the filter -- is the exact scan over ALL slots (KSumScan)
+  int scan_restarts = 0;
   struct PartStats { long long bytes_terms = 0, bytes_parents = 0, bytes_moments = 0, bytes_keys = 0; int imports = 0, owned = 0; double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } pstats;   // ms: CUDA-event stage times of the exchange
   bool phase_timing = false;                    // mce_options.phase_timing
   int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
@@ -384,18 +386,18 @@ class Engine {
   // Ordered moments (moments_mode 0): every slot's (g, y) is placed at its canonical position of the global slot list and the
   // list is combined over the ranks (each word has one non-zero contributor, so the integer sum is the value); every rank then
   // adds ALL slots in the reference's order.  Returns the global slot count; *g_out / *y_out point at the combined list.
-  long long part_gather_slots(const SlotView& sl, const GenStore& pg, cplx** g_out, double** y_out) {
+  long long part_gather_slots(const SlotView& sl, const GenStore& pg, cplx** g_out, double** y_out, bool with_y = true) {
     KSlotScatter k; memset(&k, 0, sizeof(k));
     long long ng_slots = 0; int base = 0;
     for (int m = 0; m < NSHAPE; m++) { k.gslot_begin[m] = ng_slots; k.gshape_base[m] = base; ng_slots += (long long)g_alive_per_shape[m] * (sl.MT[m] + 1); base += g_alive_per_shape[m]; }
-    const size_t words = (size_t)ng_slots * (2 + 2 * d);
+    const size_t words = (size_t)ng_slots * (2 + (with_y ? 2 * d : 0));
     double* buf = (double*)ptGg.ensure(sizeof(double) * (words + 8));
     be.memset(buf, 0, sizeof(double) * words);
-    k.sl = sl; k.d = d; k.gpos = pg.gpos.template as<int>(); k.g_out = (cplx*)buf; k.y_out = buf + 2 * ng_slots;
+    k.sl = sl; k.d = d; k.gpos = pg.gpos.template as<int>(); k.g_out = (cplx*)buf; k.y_out = with_y ? buf + 2 * ng_slots : nullptr;
     if (sl.n_slots > 0) be.launch(k, (int)((sl.n_slots + 127) / 128), 128, 0);
     be.xchg_begin(); be.xchg_allreduce_u32(buf, words * 2); be.xchg_end();
     pstats.bytes_moments = (long long)(sizeof(double) * words);
-    *g_out = (cplx*)buf; *y_out = buf + 2 * ng_slots;
+    *g_out = (cplx*)buf; if (y_out) *y_out = buf + 2 * ng_slots;
     return ng_slots;
   }
 
@@ -737,8 +739,10 @@ class Engine {
     // its CTAs are placed on idle SMs, so the main stream is drained first (measured: 8.4 ms instead of 11.6 ms at 1.1 M slots).
     // partitioned estimator, ordered moments: the sums run over ALL ranks' slots in the reference's order (bit-exact)
     const cplx* mom_g = sl.g; const double* mom_y = sl.y; long long mom_n = nslots;
+    const cplx* scan_g = nullptr; long long scan_n = 0;
     if (part) {
       if (moments_mode == 0) { cplx* gg; double* gy; mom_n = part_gather_slots(sl, pg, &gg, &gy); mom_g = gg; mom_y = gy; stats.slots = mom_n; }
+      if (moments_mode == 2) { cplx* gg; scan_n = part_gather_slots(sl, pg, &gg, nullptr, false); scan_g = gg; stats.slots = scan_n; }
     }
     be.ev_record(6);
     be.sync();
@@ -753,6 +757,7 @@ class Engine {
     } else {
       be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
+    if (scan_g) be.launch_side(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
     be.ev_record_side(5);
     auto finish_moments = [&]() {
       std::vector<double> raw(2 * nq);
@@ -767,6 +772,10 @@ class Engine {
           double acc = 0;
           for (int h = 0; h < W; h++) { double v; memcpy(&v, &all[(size_t)h * 2 * nq + i], sizeof(double)); acc += v; }
           raw[i] = acc;
+        }
+        if (moments_mode == 2) {                // Re fz as the reference's chain over ALL slots gives it, bit for bit
+          double sc2[2]; be.d2h(sc2, mom + 2 * nq, sizeof(sc2));
+          raw[0] = sc2[0]; scan_restarts = (int)sc2[1];
         }
       }
       finalize_moments(raw.data(), true);
@@ -1254,6 +1263,19 @@ class Engine {
     if (n > 0 && dd > 0) be.h2d(yy, y, sizeof(double) * (size_t)n * 2 * dd);
     be.launch(KMomentsSerial{gg, yy, n, dd, mom}, nq, 512, KMomentsSerial::smem_bytes(dd));
     be.d2h(out, mom, sizeof(double) * 2 * nq);
+    return 0;
+  }
+
+  // Test hook: KSumScan over the real parts of n complex values; out[0] = the serial-order sum, out[1] = restarts of the scan.
+  int debug_sum_scan(long long n, const double* g, double* out) {
+    cplx* gg = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(n + 8));
+    double* mom = (double*)momOut.ensure(sizeof(double) * 4 * (1 + d + d * d) + 16);
+    if (n > 0) be.h2d(gg, g, sizeof(cplx) * (size_t)n);
+    be.ev_record(10);
+    be.launch(KSumScan{gg, n, mom}, 1, 1024, KSumScan::smem_bytes(1024));
+    be.ev_record(11);
+    be.d2h(out, mom, sizeof(double) * 2);
+    cpdf_ms = be.ev_elapsed(10, 11);          // device time of the kernel, read back through mce_cpdf_last_ms
     return 0;
   }
 

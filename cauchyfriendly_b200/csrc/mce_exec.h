@@ -38,6 +38,41 @@ struct DevCtx {
   __device__ __forceinline__ unsigned atomic_or(unsigned* p, unsigned v) { return atomicOr(p, v); }
   __device__ __forceinline__ unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
   __device__ __forceinline__ int load_relaxed(const int* p) { return *(const volatile int*)p; }
+  __device__ __forceinline__ int atomic_min(int* p, int v) { return atomicMin(p, v); }
+  // Block-wide inclusive scan of n == nthreads() elements held in shared memory, in place: x[k] <- op(x[0], ..., x[k]) folded left to right with an
+  // ASSOCIATIVE op(earlier, later).  Warp shuffles inside a warp, one warp over the warp totals; `scratch` holds nthreads() / 32 elements.
+  // Called from block-uniform code (outside par); ends with a barrier.
+  template <class T, class Op>
+  __device__ __forceinline__ void block_scan(T* x, T* scratch, Op op) {
+    const int tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = ((int)blockDim.x + 31) >> 5;
+    T v = x[tid];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      T o = v;
+      unsigned long long* w = (unsigned long long*)&o;
+#pragma unroll
+      for (int i = 0; i < (int)(sizeof(T) / 8); i++) w[i] = __shfl_up_sync(0xffffffffu, w[i], off);
+      if (lane >= off) v = op(o, v);
+    }
+    if (lane == 31) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+      T t = scratch[lane < nw ? lane : 0];
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        T o = t;
+        unsigned long long* w = (unsigned long long*)&o;
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(T) / 8); i++) w[i] = __shfl_up_sync(0xffffffffu, w[i], off);
+        if (lane >= off && lane < nw) t = op(o, t);
+      }
+      if (lane < nw) scratch[lane] = t;
+    }
+    __syncthreads();
+    if (warp > 0) v = op(scratch[warp - 1], v);
+    x[tid] = v;
+    __syncthreads();
+  }
   // 16-byte asynchronous global -> shared copy (LDGSTS); the data is visible after cp_async_wait() + a barrier
   __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);

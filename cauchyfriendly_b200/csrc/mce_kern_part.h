@@ -358,7 +358,7 @@ struct KSurvRank {                        // gpos[a] = survivors of lower shapes
 
 // ---- ordered moments: every slot's (g, y) goes to its canonical position of the global slot list ----
 struct KSlotScatter {
-  SlotView sl; int d; const int* gpos; cplx* g_out; double* y_out;
+  SlotView sl; int d; const int* gpos; cplx* g_out; double* y_out;      // y_out == nullptr: only g (the exact scan of Re fz needs nothing else)
   long long gslot_begin[NSHAPE]; int gshape_base[NSHAPE];
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
@@ -369,7 +369,7 @@ struct KSlotScatter {
       const int r = sl.par_begin[ms] + (int)(ls / per), t = (int)(ls % per);
       const long long gs = gslot_begin[ms] + (long long)(gpos[r] - gshape_base[ms]) * per + t;
       g_out[gs] = sl.g[s];
-      for (int i = 0; i < 2 * d; i++) y_out[gs * 2 * d + i] = sl.y[s * 2 * d + i];
+      if (y_out) for (int i = 0; i < 2 * d; i++) y_out[gs * 2 * d + i] = sl.y[s * 2 * d + i];
     });
   }
 };

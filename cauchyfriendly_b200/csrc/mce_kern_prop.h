@@ -605,6 +605,151 @@ struct KMomentsSerial {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// ONE serial-order sum as a parallel scan, bit-identical to  acc = 0; for (k) acc += x[k]  (used for Re fz of a partitioned estimator:
+// the only moment sum that feeds back into the filter, G_SCALE_FACTOR = 1 / (2 pi Re fz), est:349).
+// While a running sum s stays inside one binade, s <- fl(s + a) is integer arithmetic on its 53-bit significand S in units of ulp(s): the exact
+// a / ulp = V + f rounds to V, V + 1, or -- on a tie, f = 1/2 -- to whichever makes the RESULT even (IEEE round-to-nearest-even).  So an addend
+// is a map  S -> S + d[S & 1]  with two precomputed integers (d[0] == d[1] unless it is a tie), and such maps compose associatively:
+//     (g o f)[p] = f[p] + g[(p + f[p]) & 1].
+// A tile of addends is reduced by a block scan of maps; every prefix value is then checked to lie in [2^52 + 1, 2^53 - 2] (then every exact
+// partial sum was inside the binade and the integer model held).  At the first element that fails -- the sum crosses a binade or zero, a
+// non-finite or oversized addend, a zero / subnormal running sum -- the valid prefix is kept, a few elements are added by the literal loop,
+// and the scan restarts behind them with the new binade.  Chains that hover around zero restart at every other element (Im fz does: that is
+// why the full set of moment sums stays a dependent chain); Re fz changes binade once per ~1000 addends.
+// ---------------------------------------------------------------------------------------------
+struct MomMap { long long d0, d1; };
+MCE_HD MomMap mom_identity() { MomMap m; m.d0 = 0; m.d1 = 0; return m; }
+MCE_HD MomMap mom_compose(const MomMap& f, const MomMap& g) {      // first f, then g
+  MomMap h;
+  h.d0 = f.d0 + ((f.d0 & 1) ? g.d1 : g.d0);
+  h.d1 = f.d1 + (((f.d1 + 1) & 1) ? g.d1 : g.d0);
+  return h;
+}
+MCE_HD long long mom_apply(const MomMap& f, long long S) { return S + ((S & 1) ? f.d1 : f.d0); }
+struct MomState { long long S; int E, sign, ok; double scale; };
+MCE_HD MomState mom_state(double s) {
+  union { double d; unsigned long long u; } v; v.d = s;
+  MomState st; st.E = (int)((v.u >> 52) & 0x7ffull); st.sign = (int)(v.u >> 63);
+  st.S = (long long)((v.u & 0xfffffffffffffull) | (1ull << 52));
+  st.ok = (st.E >= 64 && st.E <= 2046) ? 1 : 0;                  // normal, finite and 1 / ulp(s) representable (zero, tiny, inf, nan take the literal loop)
+  union { double d; unsigned long long u; } sc; sc.u = ((unsigned long long)(st.ok ? 2098 - st.E : 1023) << 52) | ((unsigned long long)st.sign << 63);   // +-2^(1075 - E)
+  st.scale = sc.d;
+  return st;
+}
+MCE_HD double mom_value(const MomState& st, long long S) {       // S in [2^52, 2^53)
+  union { double d; unsigned long long u; } v;
+  v.u = ((unsigned long long)st.sign << 63) | ((unsigned long long)st.E << 52) | ((unsigned long long)S & 0xfffffffffffffull);
+  return v.d;
+}
+// The map of addend `a` for a running sum in the binade / sign of `st`; false when the integer model cannot hold for it.
+// q = a / ulp(s) is an exact scaling by a power of two (st.scale); rint(q) is the nearest integer with ties to even, which is the increment for
+// an EVEN significand (the result must be even on a tie); for an odd one the tie goes to the other neighbour.  |q| >= 2^52 (the sum would leave the
+// binade), infinities and NaNs fail the single comparison.  A subnormal product only arises for |q| << 1/2 and rounds to 0 either way.
+MCE_HD bool mom_classify(double a, const MomState& st, MomMap* m) {
+  const double q = a * st.scale;                                  // signed so that it ADDS to the significand
+  *m = mom_identity();
+  if (!(fabs(q) < 4503599627370496.0)) return false;              // 2^52
+  const double d0 = rint(q), r = q - d0;                          // r is exact
+  const long long D0 = (long long)d0;
+  m->d0 = D0;
+  m->d1 = (fabs(r) == 0.5) ? D0 + (r > 0 ? 1 : -1) : D0;
+  return true;
+}
+MCE_HD bool mom_in_binade(long long S) { return S >= (1ll << 52) + 1 && S <= (1ll << 53) - 2; }
+
+constexpr int SS_SERIAL = 32;           // elements added by the literal loop behind a failed check
+constexpr int SS_E = 8;                 // consecutive elements per thread of one tile
+struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re + ... (n addends) in order; out[1] = restarts (as a double, statistics)
+  const cplx* x; long long n; double* out;
+  static MCE_HD size_t smem_bytes(int nthreads) {
+    return sizeof(double) * (2 * (size_t)nthreads * SS_E + 2) + sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(long long) * (size_t)nthreads + sizeof(int) * 8 + 64;
+  }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int NT = c.nthreads(), TILE = NT * SS_E;
+    double* vals = (double*)c.smem();                 // [2][TILE] addends of this tile and the next
+    double* sv = vals + 2 * (size_t)TILE;             // [0] running sum
+    MomMap* maps = (MomMap*)(sv + 2);                 // [NT] thread maps (inclusive scan in place), then [32] scan scratch
+    long long* Ss = (long long*)(maps + NT + 32);     // [NT] significand in front of every thread's first element
+    int* ctl = (int*)(Ss + NT);                       // [0] first failing element, [1] done, [2] next start, [3] restarts
+    const long long ntiles = (n + TILE - 1) / TILE;
+    c.par([&](int tid) {
+      if (tid == 0) { sv[0] = 0; ctl[3] = 0; }
+      for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
+    });
+    for (long long t = 0; t < ntiles; t++) {
+      const int cnt = (int)((n - t * TILE) < TILE ? (n - t * TILE) : TILE);
+      const double* a = vals + (t & 1) * (size_t)TILE;
+      int pos = 0;
+      for (;;) {
+        const double s = c.uniform(sv[0]);
+        const MomState st = mom_state(s);
+        union { double dd; unsigned long long u; } sb; sb.dd = s;
+        const bool zero = sb.u == 0ull;               // +0: addends of +-0 leave it unchanged ((+0) + (-0) = +0)
+        // A: the maps of the own elements, composed; the next tile's loads are issued first and stored last, so they fly meanwhile
+        c.par([&](int tid) {
+          double nx[SS_E];
+          const bool pre = pos == 0 && t + 1 < ntiles;
+          if (pre) for (int e = 0; e < SS_E; e++) { const long long k = (t + 1) * TILE + (long long)tid * SS_E + e; nx[e] = (k < n) ? x[k].re : 0.0; }
+          MomMap m = mom_identity(); int bad = 0;
+          for (int e = 0; e < SS_E; e++) {
+            const int k = tid * SS_E + e;
+            if (k < pos || k >= cnt) continue;
+            MomMap me = mom_identity();
+            if (zero) bad |= !(a[k] == 0.0);
+            else if (!st.ok || !mom_classify(a[k], st, &me)) bad = 1;
+            m = mom_compose(m, me);
+          }
+          maps[tid] = m;
+          if (bad) Ss[tid] = -1; else Ss[tid] = 0;
+          if (tid == 0) ctl[0] = 0x7fffffff;
+          if (pre) { double* nb = vals + ((t + 1) & 1) * (size_t)TILE; for (int e = 0; e < SS_E; e++) nb[tid * SS_E + e] = nx[e]; }
+        });
+        c.block_scan(maps, maps + NT, [](const MomMap& f, const MomMap& g) { return mom_compose(f, g); });
+        // B: every prefix value must stay inside the binade; the first element that fails is the restart point
+        c.par([&](int tid) {
+          const bool bad = Ss[tid] < 0;
+          long long S = tid == 0 ? st.S : mom_apply(maps[tid - 1], st.S);
+          Ss[tid] = S;
+          for (int e = 0; e < SS_E; e++) {
+            const int k = tid * SS_E + e;
+            if (k < pos || k >= cnt) continue;
+            bool fail;
+            if (zero) fail = !(a[k] == 0.0);
+            else {
+              MomMap me = mom_identity();
+              fail = !st.ok || !mom_classify(a[k], st, &me);
+              S = mom_apply(me, S);
+              fail = fail || !mom_in_binade(S);
+            }
+            if (fail) { c.atomic_min(&ctl[0], k); break; }
+          }
+          (void)bad;
+        });
+        // C: the new running sum, or a few literal additions behind the failing element
+        c.par([&](int tid) {
+          if (tid != 0) return;
+          const int v = ctl[0];
+          if (v == 0x7fffffff) { if (!zero && cnt > pos) sv[0] = mom_value(st, mom_apply(maps[NT - 1], st.S)); ctl[1] = 1; return; }
+          double acc = s;
+          if (!zero && v > pos) {                         // the valid prefix: walk the owning thread's elements up to v - 1
+            const int tv = v / SS_E;
+            long long S = Ss[tv];
+            for (int k = tv * SS_E; k < v; k++) { if (k < pos) continue; MomMap me = mom_identity(); mom_classify(a[k], st, &me); S = mom_apply(me, S); }
+            acc = mom_value(st, S);
+          }
+          const int e = v + SS_SERIAL < cnt ? v + SS_SERIAL : cnt;
+          for (int i = v; i < e; i++) acc += a[i];
+          sv[0] = acc; ctl[2] = e; ctl[1] = (e >= cnt) ? 1 : 0; ctl[3] += 1;
+        });
+        if (c.uniform(ctl[1])) break;
+        pos = c.uniform(ctl[2]);
+      }
+    }
+    c.par([&](int tid) { if (tid == 0) { out[0] = sv[0]; out[1] = (double)ctl[3]; } });
+  }
+};
+
 constexpr int MOM_CHUNK = 4096;   // slots per block of the partial-moment reduction
 struct KMomentsPartial {          // partial[block][2*(d + d*d)] = sum over the block's slots of (g*y_j, -g*y_j*y_k)
   const cplx* g; const double* y; long long n; int d; double* partial;

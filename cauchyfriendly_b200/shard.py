@@ -7,7 +7,9 @@ makes identical step calls.  Every term lives on one rank; moments and counts co
 transport="nccl": the library opens libnccl.so.2 itself and issues grouped send/recv, all-gathers and all-reduces on its own
 CUDA stream; torch.distributed is only used to ship the 128-byte NCCL id from rank 0.  transport="callback": the library hands
 every exchange to Python, which runs it over `dist` (used by the CPU tests with the gloo backend and host memory).
-moments: "ordered" (bit-identical to one GPU) or "allreduce" (per-rank sums added in rank order; scales)."""
+moments: "ordered" (every sum bit-identical to one GPU), "hybrid" (Re fz -- the sum that feeds back into the filter -- bit-identical through an exact
+scan over all ranks' slots, the other sums per rank and added in rank order: every count, key and G stays bit-identical, mean / covariance move in the
+last digits) or "allreduce" (all sums per rank; fz moves in the last bits and deep steps can lose or gain a term)."""
 import ctypes as ct
 
 import numpy as np
@@ -23,7 +25,7 @@ def init_term_sharding(handle, dist, lib=None, transport="nccl", device=-1, mome
     rank, world = dist.get_rank(), dist.get_world_size()
     if world == 1:
         return
-    if lib.mce_shard_set_moments_mode(handle, {"ordered": 0, "allreduce": 1}[moments]) != 0:
+    if lib.mce_shard_set_moments_mode(handle, {"ordered": 0, "allreduce": 1, "hybrid": 2}[moments]) != 0:
         raise RuntimeError("mce_shard_set_moments_mode failed")
     if transport == "nccl":
         buf = ct.create_string_buffer(128)

@@ -181,6 +181,9 @@ int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, 
  * n caller-supplied slots, every real accumulator in slot order exactly like the dependent chain of cauchy_estimator.hpp:307-338.
  * g: n complex values, y: n x d complex values (d may be 0: only fz), out: 2 * (1 + d + d*d) doubles. */
 int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, const double* y, double* out);
+/* Test hook for the exact scan of one serial-order sum (csrc/mce_kern_prop.h: KSumScan, used for Re fz of a partitioned estimator):
+ * out[0] = g[0].re + g[1].re + ... added in order, bit for bit; out[1] = how often the scan fell back to the literal loop. */
+int mce_debug_sum_scan(mce_handle* h, long long n, const double* g /* n complex */, double* out /*[2]*/);
 int mce_debug_capture(mce_handle* h, int enable);
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,
                         int* meta /*[n][8]*/, uint8_t* cmap /*[n][32]*/, int8_t* csmap /*[n][32]*/, int* F /*[n]*/);

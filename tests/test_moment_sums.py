@@ -51,6 +51,36 @@ def _check(lib):
         s.close()
 
 
+def _check_scan(lib):
+    """KSumScan (Re fz of a partitioned estimator): the scan of rounding maps equals the dependent chain on every adversarial sequence."""
+    sc = read_scenario(os.path.join(ROOT, "tests", "golden", "lti3.mces"))
+    s = Session(lib, sc)
+    dp = ct.POINTER(ct.c_double)
+    restarts = {}
+    try:
+        for name, a in cases().items():
+            g = np.zeros((len(a), 2)); g[:, 0] = a; g[:, 1] = 12345.0
+            g = np.ascontiguousarray(g)
+            out = np.zeros(2)
+            assert lib.mce_debug_sum_scan(s.h, len(a), g.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
+            want = serial_sum(a)
+            assert out[0].tobytes() == np.float64(want).tobytes(), "%s: scan %r != serial chain %r" % (name, out[0], want)
+            restarts[name] = int(out[1])
+    finally:
+        s.close()
+    assert restarts["long_positive"] < 200 and restarts["all_zero"] == 0, restarts      # the scan path really carries the friendly chains
+    assert restarts["binade_walk"] > 50, restarts                                        # ... and the literal loop the hostile ones
+
+
+def test_sum_scan_equals_the_serial_chain_emulated():
+    _check_scan(load_emu())
+
+
+@pytest.mark.gpu
+def test_sum_scan_equals_the_serial_chain_gpu():
+    _check_scan(load_product())
+
+
 def test_moment_kernel_equals_the_serial_chain_emulated():
     _check(load_emu())
 

@@ -38,6 +38,19 @@ def skip(n):       # the post-coalignment term lists are a debug capture of the 
     return "/muc/m" in n or ("/ftr/m" in n and n.split("/")[-1] in ("A", "p", "b", "cells", "keys", "G", "encB") and int(n.split("/")[0][1:]) > full)
 if mode == "ordered":
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=skip)
+elif mode == "hybrid":
+    # Re fz bit-exact (exact scan over all ranks' slots) => G_SCALE_FACTOR and with it every count, key, hyperplane and G value bit-exact;
+    # the other sums are rank-ordered partials: Im fz, mean and covariance move in the last digits (the covariance sums are ill-conditioned)
+    import numpy as np
+    d = sc.d
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=lambda n: skip(n) or n.endswith("/moments"))
+    for n in gold:
+        if n.endswith("/moments"):
+            a, b = gold[n], got[n]
+            if a[0].real.tobytes() != b[0].real.tobytes():
+                probs.append("%s: Re fz is not bit-identical (%r vs %r)" % (n, a[0].real, b[0].real))
+            if np.max(np.abs(a[1:1 + d] - b[1:1 + d])) > 1e-9 * np.max(np.abs(a[1:1 + d])) or np.max(np.abs(a[1 + d:] - b[1 + d:])) > 1e-4 * np.max(np.abs(a[1 + d:])):
+                probs.append("%s: mean / covariance differ beyond the reordering noise" % n)
 else:
     # rank-ordered partial sums: fz (hence every G) moves in the last bits, cells that cancel move more; the discrete results
     # (counts, keys, hyperplanes) are compared exactly, fz and the mean to 1e-9, G through its digest to 1e-6
@@ -65,7 +78,8 @@ dist.barrier(); dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("case,world,moments", [("lti3:8:5", 2, "ordered"), ("lti4_2msmts:8:5", 2, "ordered"), ("leo7:6:4", 2, "ordered"),
-                                                ("lti3:8:5", 3, "ordered"), ("lti3:5:5", 3, "allreduce"), ("homing3:7:4", 2, "ordered")])
+                                                ("lti3:8:5", 3, "ordered"), ("lti3:5:5", 3, "allreduce"), ("homing3:7:4", 2, "ordered"),
+                                                ("leo7:7:4", 3, "hybrid"), ("lti3:8:5", 2, "hybrid")])
 def test_partitioned_estimator_matches_golden_on_every_rank(case, world, moments, tmp_path):
     from harness import load_emu
     load_emu(rebuild=True)
