@@ -990,6 +990,7 @@ class Engine {
         const int lo = g0, hi = g1, gshift = 0;
         const int Hm = cell_count_central_half(m, d);
         int nth = Hm <= 32 ? 32 : (Hm <= 64 ? 64 : 128);
+        { static const char* ev = getenv("MCE_G2_NT"); if (ev && max_shape <= 16) { const int v = atoi(ev); if (v == 32 || v == 64 || v == 128) nth = v < nth ? v : nth; } }
         if (max_shape <= 16) {
           const int NW = (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1;
           const int ix = phase * NSHAPE + m;
@@ -1000,13 +1001,13 @@ class Engine {
             ba.rows = brows + rows_base[ix]; ba.flags = bflags + flags_base[ix]; ba.keys = bkeys + keys_base[ix]; ba.row_stride = Hm;
           }
           const int* ord = order_all + tv.t_begin[m]; const int* gst = gstart_all + gstart_off[m];
-          const size_t smb = KGTable2::smem_bytes(Hcap, NW);
-          KGTable2 k{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
+          const size_t smb = KGTable2::smem_bytes(Hm, NW);      // per-cell arrays sized by this shape's largest table: what is left of the SM's 256 KB is L1 for the parent tables
+          KGTable2 k{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
           be.launch(k, hi - lo, nth, smb);
           if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
-            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
-            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
-            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hcap, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
+            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
           }
         } else {
           KGTable k{sp, pv, ng.v, gws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};

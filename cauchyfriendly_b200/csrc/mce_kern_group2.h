@@ -218,7 +218,8 @@ struct KTpDce2T {
   }
 };
 
-constexpr int G2_CHUNK = 32;      // members staged per chunk
+constexpr int G2_CHUNK = 16;      // members staged per chunk
+constexpr int G2_M = 16;          // this kernel serves max_shape <= 16
 
 // The "member is not negligible" flag is raised by whichever thread finds a qualifying cell and only ever read to skip a test:
 // an intended benign race (every writer stores 1).  Building with -DMCE_RACECHECK turns both sides into atomics so that
@@ -234,18 +235,20 @@ constexpr int G2_CHUNK = 32;      // members staged per chunk
 struct Group2Member {              // everything the kernel needs to know about one member, gathered in one parallel phase
   int ti, parent, gidp, phc, pc, own_cells;
   long long rk_off;                // parent's rank structure inside prev.rbm / prev.rpf
+  const cplx* pG;                  // the parent's table and rank structure, resolved once per member (eval_cell runs per cell)
+  const unsigned* bmP; const unsigned short* pfP;
   unsigned hflag, enc_lhp, csneg, mask, kflip;
   unsigned char z, is_child, has_cmap, pbc;
   unsigned char skip;              // certified negligible from the parent's largest |G| alone: no cell needs evaluating
   double c, d, psq;
-  unsigned char ksrc[MAXM];
+  unsigned char ksrc[G2_M];
 };
 
 struct Group2Sm {
   int cnt, owner, pad0, pad1;
-  unsigned sgbits[2][MAXM];        // per-row orientation bits of a staged member (update_btable's sigma); slot = member index & 1
+  unsigned sgbits[2][G2_M];        // per-row orientation bits of a staged member (update_btable's sigma); slot = member index & 1
   int flag[G2_CHUNK];              // per member: some cell is not negligible
-  double q[2][MAXM];
+  double q[2][G2_M];
   Group2Member mem[G2_CHUNK];
 };
 
@@ -260,7 +263,7 @@ MCE_HD double flip_sign(double x, unsigned neg) {
 
 // exclusive prefix popcounts of a bitmap; *total (may be null) receives the number of set bits
 template <class Ctx> MCE_KERNEL_FN MCE_NOINLINE void bm_prefix_any(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) {
-  if (nw <= 64) {               // one phase: word w sums the popcounts below it
+  if (nw <= 64 && nw <= c.nthreads()) {               // one phase: word w sums the popcounts below it
     c.par([&](int tid) {
       if (tid >= nw) return;
       int s = 0;
@@ -358,7 +361,7 @@ struct KGTable2T {
   BigArgs big;
   int gid_shift = 0;            // slot of group gi in the new generation = gid_begin[m] + gi + gid_shift (sharded layouts pad each phase)
   static MCE_HD size_t smem_bytes(int HC, int NW) {
-    return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + 1024) * sizeof(unsigned short) + 64;
+    return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + kMaxThreads) * sizeof(unsigned short) + 64;
   }
 
   template <class Ctx> MCE_KERNEL_FN void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const { bm_prefix_any(c, bm, pf, nw, total); }
@@ -379,6 +382,7 @@ struct KGTable2T {
     e->ti = ti; e->parent = me.parent; e->gidp = gidp; e->phc = phc; e->pc = prev.cells[gidp];
     e->own_cells = sp.with_tp ? ws.tpB_cells[me.parent] : e->pc;
     e->rk_off = gen_rk_off(prev, gidp, phc);
+    e->pG = gen_G(prev, gidp, phc); e->bmP = prev.rbm + e->rk_off; e->pfP = prev.rpf + e->rk_off;
     e->hflag = me.hflag; e->enc_lhp = me.enc_lhp; e->csneg = me.csneg; e->mask = ws.sgnmask[me.parent];   // bxor is read when needed (it can change)
     e->z = me.z; e->is_child = me.flags & 1; e->has_cmap = (me.flags >> 1) & 1; e->pbc = me.pbc;
     e->c = me.c_val; e->d = me.d_val;
@@ -426,7 +430,7 @@ struct KGTable2T {
   // G of one cell of the staged member, flattening.hpp:129-247
   MCE_HDN MCE_NOINLINE cplx eval_cell(const double* q, const Group2Member* e, int* flag, unsigned key) const {
     const int phc = e->phc;
-    const unsigned* bmP = prev.rbm + e->rk_off; const unsigned short* pfP = prev.rpf + e->rk_off;
+    const unsigned* bmP = e->bmP; const unsigned short* pfP = e->pfP;
     // ygi = sum over non-H-orthogonal rows of q_k s_k, in row order (flat:137-154).  sm->q holds +0.0 for the H-orthogonal
     // rows (adding +0.0 never changes a running sum that started at +0.0), so the loop is branch-free; s_k flips the sign bit.
     double ygi = 0;
@@ -450,7 +454,7 @@ struct KGTable2T {
       }
       lm = (z < phc) ? (lp | (1 << z)) : lp;
     }
-    const cplx* pG = gen_G(prev, e->gidp, phc);
+    const cplx* pG = e->pG;
     const cplx gp = lookup(e, pG, bmP, pfP, lp ^ (int)e->enc_lhp);
     const cplx gm = lookup(e, pG, bmP, pfP, lm ^ (int)e->enc_lhp);
     const cplx vp = make_cplx(ygi + e->d, e->c), vm = make_cplx(ygi - e->d, e->c);
