@@ -10,7 +10,7 @@ MAXM = 32
 
 class MceOptions(ct.Structure):
     _fields_ = [("device", ct.c_int), ("tr_search_order", ct.c_int * 12), ("print_basic_info", ct.c_int),
-                ("fast_moments", ct.c_int), ("group_split_threshold", ct.c_int), ("phase_timing", ct.c_int), ("reserved", ct.c_int * 5)]
+                ("fast_moments", ct.c_int), ("group_split_threshold", ct.c_int), ("phase_timing", ct.c_int), ("lean_group_kernel", ct.c_int), ("reserved", ct.c_int * 4)]
 
 
 class MceMoments(ct.Structure):
@@ -25,7 +25,7 @@ class MceStepStats(ct.Structure):
                                              "bytes_step_algorithmic", "kernel_launches")] + \
                [("ftr_rounds_max", ct.c_int), ("diag_unmodelled_alias", ct.c_int), ("diag_hash_overflow", ct.c_int),
                 ("ev_step_ms", ct.c_double), ("ev_gtable_ms", ct.c_double), ("gtable_launches", ct.c_longlong),
-                ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_ftr_ms", ct.c_double), ("ev_mu_ms", ct.c_double)]
+                ("cells_parents", ct.c_longlong), ("cells_survivors", ct.c_longlong), ("split_groups", ct.c_longlong), ("ev_moments_ms", ct.c_double), ("ev_ftr_ms", ct.c_double), ("ev_mu_ms", ct.c_double), ("gtable_lean_launches", ct.c_longlong)]
 
 
 class MceAllToAllV(ct.Structure):      # mce_alltoallv_args

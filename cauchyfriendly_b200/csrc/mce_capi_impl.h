@@ -35,6 +35,7 @@ mce_handle* mce_create(int d, int cmcc, int pncc, int p, int steps, const double
   if (!e) { g_mce_error = "mce_create: out of memory"; return nullptr; }
   e->fast_moments = opts->fast_moments != 0;
   e->phase_timing = opts->phase_timing != 0;
+  e->lean_groups = opts->lean_group_kernel != 0;
   e->big_T = opts->group_split_threshold == 0 ? mce::BIG_T : (opts->group_split_threshold < 0 ? 0x7fffffff : opts->group_split_threshold);
   if (!e->be.init(opts->device, &berr)) { g_mce_error = "mce_create: " + berr; delete e; return nullptr; }
   mce_handle* h = new mce_handle; h->e = e;
@@ -170,7 +171,7 @@ int mce_get_step_stats(mce_handle* h, mce_step_stats* out) {
   out->ms_ftr = s.ms_ftr; out->ms_gtable = s.ms_gtable; out->ms_compact = s.ms_compact;
   out->parents = s.parents; out->slots = s.slots; out->terms_after_muc = s.terms_after_muc; out->groups = s.groups; out->survivors = s.survivors;
   out->bytes_gtable_algorithmic = s.bytes_gtable; out->bytes_step_algorithmic = s.bytes_step; out->kernel_launches = s.launches;
-  out->ev_step_ms = s.ev_step_ms; out->ev_gtable_ms = s.ev_gtable_ms; out->gtable_launches = s.gtable_launches;
+  out->ev_step_ms = s.ev_step_ms; out->ev_gtable_ms = s.ev_gtable_ms; out->gtable_launches = s.gtable_launches; out->gtable_lean_launches = s.gtable_lean_launches;
   out->cells_parents = s.cells_parents; out->cells_survivors = s.cells_survivors; out->split_groups = s.big_groups; out->ev_moments_ms = s.ev_moments_ms; out->ev_ftr_ms = s.ev_ftr_ms; out->ev_mu_ms = s.ev_mu_ms;
   out->ftr_rounds_max = s.ftr_rounds_max; out->diag_unmodelled_alias = s.diag_alias; out->diag_hash_overflow = s.diag_hash;
   return 0;

@@ -34,7 +34,7 @@ struct StepStats {
   long long bytes_gtable = 0, bytes_step = 0, launches = 0;
   int ftr_rounds_max = 0, diag_alias = 0, diag_hash = 0;
   double ev_step_ms = 0, ev_gtable_ms = 0, ev_mu_ms = 0, ev_moments_ms = 0, ev_ftr_ms = 0;   // CUDA-event durations on the stream
-  long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0;
+  long long cells_parents = 0, cells_survivors = 0, gtable_launches = 0, gtable_lean_launches = 0;
   int big_groups = 0;
 };
 
@@ -130,6 +130,7 @@ class Engine {
   int scan_restarts = 0;
   struct PartStats { long long bytes_terms = 0, bytes_parents = 0, bytes_moments = 0, bytes_keys = 0; int imports = 0, owned = 0; double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0}; } pstats;   // ms: CUDA-event stage times of the exchange
   bool phase_timing = false;                    // mce_options.phase_timing
+  bool lean_groups = false;                     // mce_options.lean_group_kernel
   int big_T = BIG_T;                            // groups with more members are split (mce_options.group_split_threshold)
   long long big_scratch_cap = 6LL << 30;       // bytes of addend rows above which group splitting is skipped for a step
   // debug capture
@@ -176,12 +177,12 @@ class Engine {
     if (d < 2 || d > MAXD) { *why = "state dimension must be in [2, 8]"; return false; }
     if (max_shape > MAXM - 1) { *why = "max hyperplane count exceeds 31 (reference cap, est:231-235)"; return false; }
     if (pncc > MAXPN) { *why = "pncc > 4 not supported"; return false; }
-    // the group kernel keeps one table (keys + two complex values per cell) in shared memory
+    // the group kernel keeps one table in shared memory: keys + two complex values per cell, or -- lean variant, used where that does not fit -- keys + one
     const int Hcap = cell_count_central_half(max_shape, d);
-    const size_t need = max_shape <= 16 ? KGTable2::smem_bytes(Hcap, (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1)
+    const size_t need = max_shape <= 16 ? KGTable2T<G2_NORMAL, true>::smem_bytes(Hcap, (1 << max_shape) / 32 > 1 ? (1 << max_shape) / 32 : 1)
                                         : KGTable::smem_bytes(next_pow2(Hcap < 4 ? 4 : Hcap));
     if (need > 227 * 1024) {
-      *why = "a window this deep gives tables of up to " + std::to_string(Hcap) + " cells; the group kernel holds a table in shared memory (227 KB, about 5500 cells)";
+      *why = "a window this deep gives tables of up to " + std::to_string(Hcap) + " cells; the group kernel holds a table in shared memory (227 KB, about 11000 cells for up to 16 hyperplanes, 5500 beyond)";
       return false;
     }
     // every other kernel whose shared memory grows with the deepest shape of the window, at that shape
@@ -1000,15 +1001,20 @@ class Engine {
             ba.groups = bgroups + big_slot_base[ix]; ba.parts = bparts + big_part_base[ix];
             ba.rows = brows + rows_base[ix]; ba.flags = bflags + flags_base[ix]; ba.keys = bkeys + keys_base[ix]; ba.row_stride = Hm;
           }
+          // the standard variant wherever its two value tables fit; the lean one (half the bytes per cell, ~10 % slower) beyond
+          const bool lean = lean_groups || KGTable2::smem_bytes(Hm, NW) > (size_t)(227 * 1024);
           const int* ord = order_all + tv.t_begin[m]; const int* gst = gstart_all + gstart_off[m];
-          const size_t smb = KGTable2::smem_bytes(Hm, NW);      // per-cell arrays sized by this shape's largest table: what is left of the SM's 256 KB is L1 for the parent tables
-          KGTable2 k{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift};
-          be.launch(k, hi - lo, nth, smb);
-          if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
-            be.launch(KGTable2T<G2_BIG_ROOT>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
-            be.launch(KGTable2T<G2_BIG_PARTS>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
-            be.launch(KGTable2T<G2_BIG_FINAL>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
-          }
+          auto launch_all = [&](auto lean_tag) {
+            constexpr bool L = decltype(lean_tag)::value;
+            const size_t smb = KGTable2T<G2_NORMAL, L>::smem_bytes(Hm, NW);      // per-cell arrays sized by this shape's largest table: what is left of the SM's 256 KB is L1 for the parent tables
+            be.launch(KGTable2T<G2_NORMAL, L>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, split ? big_T : 0x7fffffff, ba, gshift}, hi - lo, nth, smb);
+            if (nbg > 0) {       // root election, then the members in parts, then the ordered sums of the stored addends
+              be.launch(KGTable2T<G2_BIG_ROOT, L>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+              be.launch(KGTable2T<G2_BIG_PARTS, L>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbp, nth, smb);
+              be.launch(KGTable2T<G2_BIG_FINAL, L>{sp, pv, ng.v, gws, tv, m, lo, ord, gst, Hm, NW, aflag, diag, big_T, ba, gshift}, nbg, nth, smb);
+            }
+          };
+          if (lean) { launch_all(std::true_type{}); stats.gtable_lean_launches++; } else launch_all(std::false_type{});
         } else {
           KGTable k{sp, pv, ng.v, gws, tv, m, g0, order_all + tv.t_begin[m], gstart_all + gstart_off[m], HC2, aflag, diag};
           be.launch(k, g1 - g0, nth, gsm);

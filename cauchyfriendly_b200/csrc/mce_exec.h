@@ -39,6 +39,9 @@ struct DevCtx {
   __device__ __forceinline__ unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { return atomicCAS(p, cmp, v); }
   __device__ __forceinline__ int load_relaxed(const int* p) { return *(const volatile int*)p; }
   __device__ __forceinline__ int atomic_min(int* p, int v) { return atomicMin(p, v); }
+  // Per-thread value that lives across phases: a register here, one element per emulated thread in tests/emu.
+  template <class T> struct Priv { T v; __device__ __forceinline__ T& operator[](int) { return v; } };
+  template <class T> __device__ __forceinline__ Priv<T> priv() const { return Priv<T>(); }
   // Block-wide inclusive scan of n == nthreads() elements held in shared memory, in place: x[k] <- op(x[0], ..., x[k]) folded left to right with an
   // ASSOCIATIVE op(earlier, later).  Warp shuffles inside a warp, one warp over the warp totals; `scratch` holds nthreads() / 32 elements.
   // Called from block-uniform code (outside par); ends with a barrier.

@@ -220,6 +220,7 @@ struct KTpDce2T {
 
 constexpr int G2_CHUNK = 16;      // members staged per chunk
 constexpr int G2_M = 16;          // this kernel serves max_shape <= 16
+constexpr int G2_SLOTS = 3;       // staged q / orientation bits (the lean variant keeps three members in flight: pending, current, next)
 
 // The "member is not negligible" flag is raised by whichever thread finds a qualifying cell and only ever read to skip a test:
 // an intended benign race (every writer stores 1).  Building with -DMCE_RACECHECK turns both sides into atomics so that
@@ -246,9 +247,9 @@ struct Group2Member {              // everything the kernel needs to know about 
 
 struct Group2Sm {
   int cnt, owner, pad0, pad1;
-  unsigned sgbits[2][G2_M];        // per-row orientation bits of a staged member (update_btable's sigma); slot = member index & 1
+  unsigned sgbits[G2_SLOTS][G2_M];        // per-row orientation bits of a staged member (update_btable's sigma); slot = member index & 1
   int flag[G2_CHUNK];              // per member: some cell is not negligible
-  double q[2][G2_M];
+  double q[G2_SLOTS][G2_M];
   Group2Member mem[G2_CHUNK];
 };
 
@@ -348,7 +349,10 @@ MCE_HD bool is_skip_addend(const cplx& x) {
 // libgcc's full complex division, twice, out of line (the rare path of eval_cell)
 static MCE_HDN MCE_NOINLINE void g2_cdiv_pair_full(cplx u1, cplx v1, cplx u2, cplx v2, cplx* r1, cplx* r2) { *r1 = cdiv(u1, v1); *r2 = cdiv(u2, v2); }
 
-template <int MODE>
+// LEAN: no second value table in shared memory (16 + 4 instead of 32 + 4 bytes per cell): tables of up to ~11 000 cells fit (d = 7 with 16 hyperplanes:
+// 9 949), at the price of ~10 % more time on the tables both variants can hold (measured) -- the engine uses it where the
+// standard variant does not fit.
+template <int MODE, bool LEAN = false>
 struct KGTable2T {
   static constexpr int kMaxThreads = 128, kMinBlocks = 8;   // 64 registers: 8 CTAs (32 warps) per SM
   StepParams sp; GenView prev; GenView next; ParentWs ws; TermView tv;
@@ -361,7 +365,7 @@ struct KGTable2T {
   BigArgs big;
   int gid_shift = 0;            // slot of group gi in the new generation = gid_begin[m] + gi + gid_shift (sharded layouts pad each phase)
   static MCE_HD size_t smem_bytes(int HC, int NW) {
-    return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + 2 * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + kMaxThreads) * sizeof(unsigned short) + 64;
+    return ((sizeof(Group2Sm) + 15) & ~(size_t)15) + (size_t)HC * (sizeof(unsigned) + (LEAN ? 1 : 2) * sizeof(cplx)) + (size_t)NW * 2 * (sizeof(unsigned) + sizeof(unsigned short)) + 2 * (16 + kMaxThreads) * sizeof(unsigned short) + 64;
   }
 
   template <class Ctx> MCE_KERNEL_FN void bm_prefix(Ctx& c, const unsigned* bm, unsigned short* pf, int nw, int* total) const { bm_prefix_any(c, bm, pf, nw, total); }
@@ -674,6 +678,126 @@ struct KGTable2T {
     if (pend) { c.par([&](int tid) { do_pending(tid); }); pend = 0; }
   }
 
+  // ---- members [k_from, k_to), LEAN variant: the same sums without the member's value table.
+  //
+  // A member's table is only added when one of its cells is not negligible (flat:242-247), so its values cannot go into the root's
+  // sums before that is known -- but they need not be STORED either.  Every thread evaluates its first cell into a register; almost
+  // every accepted member raises its flag right there.  The barrier that ends the phase publishes the flag; the member's other
+  // cells are evaluated in the NEXT phase straight into the sums (same thread, same cells, so the order of the additions to a
+  // cell is the member order), together with the first cell of the next member.  While no flag is up, a thread goes on evaluating
+  // its further cells only to settle the negligibility test (the values are dropped; they are re-evaluated in the rare case that
+  // a late cell raises the flag).  One barrier per member, no second value table in shared memory.
+  struct MemberPlan {
+    int on, k, kk, sl; bool cj, own; unsigned sigma_n, maskT; const unsigned* bmT; const Group2Member* e;
+  };
+  // What member P does to root cell i: the member's cell with key Bk[i] ^ sigma_n, conjugated when cj (update_btable, ce:584-625:
+  // cell i of the member is cell i of the root).  An old term that keeps its own table (flat:291-314) only has the cells its
+  // (sorted) source table holds: a bit test in that table's rank bitmap.
+  MCE_HD bool member_has(const MemberPlan& P, unsigned key) const {
+    if (!P.own) return true;
+    const unsigned b = key ^ P.maskT;
+    return ((P.bmT[b >> 5] >> (b & 31)) & 1u) != 0;
+  }
+  template <class Ctx> MCE_KERNEL_FN void members_phase_lean(Ctx& c, Ws& w, int nB, int rsel, int k_from, int k_to, cplx* rows, int* rflags, int row_stride) const {
+    Group2Sm* sm = w.sm; cplx* acc = w.acc; unsigned* Bk = w.Bk; unsigned* bmA = w.bmA;
+    const int ncomb = w.ncomb, nwM = w.nwM, NT = c.nthreads(); const unsigned rev_m = w.rev_m, top_m = w.top_m;
+    const int* members = w.members;
+    auto v0 = c.template priv<cplx>();   // the member's first cell of this thread, waiting for the flag
+    auto load_chunk = [&](int tid) {
+      if (tid < G2_CHUNK) { sm->flag[tid] = 0; if (w.cbase + tid < ncomb) load_member(&sm->mem[tid], members[w.cbase + tid]); }
+    };
+    MemberPlan pend; pend.on = 0;          // accepted member whose cells (but the first) are still to be evaluated
+    auto do_rest = [&](int tid) {
+      if (!pend.on) return;
+      cplx* row = rows ? rows + (long long)pend.k * row_stride : nullptr;
+      MCE_NOUNROLL for (int i = tid; i < nB; i += NT) {
+        const unsigned key = Bk[i] ^ pend.sigma_n;
+        if (!member_has(pend, key)) { if (row) row[i] = skip_addend(); continue; }
+        cplx g = (i == tid) ? v0[tid] : eval_cell(sm->q[pend.sl], pend.e, &sm->flag[pend.kk], key);
+        if (pend.cj) g = cconj(g);
+        if (row) row[i] = g; else acc[i] = cadd(acc[i], g);
+      }
+      if (row && tid == 0) rflags[pend.k] = 1;
+    };
+    // One phase body serves every case (the rest of the pending member, then the first cells of member `cur` when cur.on): the code of the
+    // two evaluation loops exists once -- the kernel is instruction-cache bound as soon as they are duplicated.
+    bool staged = false;                 // the member's q / sgbits already sit in slot nsl
+    bool own_ready = false;              // member k keeps its own table and the scratch bitmap / counter are prepared for it
+    int last_sl = 0, nsl = 1;            // slot of the last evaluated member; slot the next member was staged into
+    enum { AFTER_NONE = 0, AFTER_RELOAD = 1, AFTER_OWN = 2, AFTER_END = 3 };
+    MemberPlan cur; cur.on = 0;
+    const unsigned* src = nullptr; int nT = 0;
+    int k = k_from;
+    for (;;) {
+      int after = AFTER_NONE;
+      bool next_here = false;
+      const Group2Member* et = nullptr; const Group2Member* en = nullptr;
+      cur.on = 0;
+      if (k >= k_to) { if (!pend.on) break; after = AFTER_END; }
+      else if (k - w.cbase >= G2_CHUNK || k < w.cbase) after = AFTER_RELOAD;     // the phase below finishes the pending member (and is the barrier in front of the reload)
+      else {
+        const int kk = k - w.cbase;
+        et = &sm->mem[kk];
+        if (et->skip) { staged = false; ++k; continue; }       // certified negligible (load_member): contributes nothing, costs nothing
+        const bool own = !(et->is_child || et->own_cells != nB);
+        if (own && !own_ready) after = AFTER_OWN;                // the scratch bitmap may still serve the pending member: finish that one first
+        else {
+          const int sl = staged ? nsl : (last_sl + 1) % G2_SLOTS;
+          if (!staged) c.par([&](int tid) { stage_qs(sm, et, sl, rsel, tid); });
+          nsl = (sl + 1) % G2_SLOTS;
+          next_here = (k + 1 < k_to) && (kk + 1 < G2_CHUNK);     // member k+1 is in the loaded chunk: stage it during this phase
+          en = et + 1;
+          const unsigned sigma_raw = sigma_of(sm, sl);
+          cur.on = 1; cur.k = k; cur.kk = kk; cur.sl = sl; cur.e = et;
+          cur.cj = (sigma_raw & top_m) != 0;
+          cur.sigma_n = cur.cj ? (sigma_raw ^ rev_m) : sigma_raw;
+          cur.own = own; cur.maskT = 0; cur.bmT = nullptr;
+          if (own) { unsigned mask; parent_B_src(et->parent, &src, &nT, &mask); cur.bmT = sp.with_tp ? bmA : prev.rbm + et->rk_off; cur.maskT = mask; }
+        }
+      }
+      c.par([&](int tid) {
+        do_rest(tid);                      // consumes the previous member's v0 before this member's first cell replaces it
+        if (!cur.on) return;
+        int matched = 0;
+        MCE_NOUNROLL for (int i = tid; i < nB; i += NT) {
+          const unsigned key = Bk[i] ^ cur.sigma_n;
+          if (!member_has(cur, key)) continue;
+          matched++;
+          if (i != tid && G2_FLAG_READ(&sm->flag[cur.kk])) { if (cur.own) continue; break; }   // accepted: the other cells wait for the next phase
+          const cplx g = eval_cell(sm->q[cur.sl], et, &sm->flag[cur.kk], key);
+          if (i == tid) v0[tid] = g;
+        }
+        if (cur.own && matched) c.atomic_add(&sm->cnt, matched);
+        if (!et->is_child && !cur.own && tid == 0) c.atomic_add(diag, 1);     // flat:516-539 also rewrites the parent's B memory: not modelled
+        if (next_here) stage_qs(sm, en, nsl, rsel, tid);
+      });
+      pend.on = 0;
+      if (cur.on) {
+        bool accepted = sm->flag[cur.kk] != 0;
+        if (!accepted && cur.own && sm->cnt != nT) {
+          // cells of the member's table without a counterpart in the root's: they take part in the negligibility test all the same
+          c.par([&](int tid) {
+            MCE_NOUNROLL for (int j = tid; j < nT; j += NT) { if (G2_FLAG_READ(&sm->flag[cur.kk])) break; (void)eval_cell(sm->q[cur.sl], et, &sm->flag[cur.kk], src[j] ^ cur.maskT); }
+          });
+          accepted = sm->flag[cur.kk] != 0;
+        }
+        if (accepted) pend = cur;
+        last_sl = cur.sl; staged = next_here; own_ready = false;
+        ++k;
+      } else if (after == AFTER_RELOAD) {
+        w.cbase = k; c.par([&](int tid) { load_chunk(tid); }); staged = false;
+      } else if (after == AFTER_OWN) {
+        // old term with its own table: cell i of its B_mu is position i of its (sorted) source table; root cell i takes the cell with the
+        // same key, when the table has it (flat:291-314).  On TP steps B_mu comes from the DCE-TP table, not from the G-table keys: bitmap over tpB
+        unsigned mask;
+        parent_B_src(et->parent, &src, &nT, &mask);
+        c.par([&](int tid) { if (tid == 0) sm->cnt = 0; if (sp.with_tp) { MCE_NOUNROLL for (int i = tid; i < nwM; i += NT) bmA[i] = 0; } });
+        if (sp.with_tp) c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nT; i += NT) { const unsigned b = src[i]; c.atomic_or(&bmA[b >> 5], 1u << (b & 31)); } });
+        own_ready = true;
+      } else break;
+    }
+  }
+
   // ---- write the surviving term; rank of a key in the bitmap of the final keys = its sorted position (flat:251-252) ----
   template <class Ctx> MCE_KERNEL_FN void emit(Ctx& c, Ws& w, int nB, int rsel) const {
     const int d = sp.d, nwM = w.nwM, gid_out = w.gid_out;
@@ -702,7 +826,7 @@ struct KGTable2T {
     w.sm = (Group2Sm*)base;
     w.acc = (cplx*)(base + ((sizeof(Group2Sm) + 15) & ~(size_t)15));
     w.Gm = w.acc + HC;
-    w.Bk = (unsigned*)(w.Gm + HC);
+    w.Bk = (unsigned*)(w.Gm + (LEAN ? 0 : HC));
     w.bmP = w.Bk + HC;             // parent-table rank structure of the staged member
     w.bmA = w.bmP + NW;            // scratch bitmap: parent B_mu / TP table / final keys
     w.pfP = (unsigned short*)(w.bmA + NW);
@@ -725,7 +849,8 @@ struct KGTable2T {
         c.par([&](int tid) { if (tid == 0) { alive_flag[w.gid_out] = 0; next.cells[w.gid_out] = 0; next.g_m[w.gid_out] = (unsigned char)m; } });
         return;
       }
-      members_phase(c, w, nB, rsel, k + 1, w.ncomb, (cplx*)nullptr, (int*)nullptr, 0);
+      if (LEAN) members_phase_lean(c, w, nB, rsel, k + 1, w.ncomb, (cplx*)nullptr, (int*)nullptr, 0);
+      else members_phase(c, w, nB, rsel, k + 1, w.ncomb, (cplx*)nullptr, (int*)nullptr, 0);
       emit(c, w, nB, rsel);
       return;
     }
@@ -750,7 +875,8 @@ struct KGTable2T {
       if (from >= hi) return;
       c.par([&](int tid) { MCE_NOUNROLL for (int i = tid; i < nB; i += c.nthreads()) w.Bk[i] = keys[i]; });
       w.cbase = from + 1;                        // forces the first iteration to load its chunk
-      members_phase(c, w, nB, rsel, from, hi, rows, rflags, big.row_stride);
+      if (LEAN) members_phase_lean(c, w, nB, rsel, from, hi, rows, rflags, big.row_stride);
+      else members_phase(c, w, nB, rsel, from, hi, rows, rflags, big.row_stride);
       return;
     }
     // G2_BIG_FINAL: root table + every stored addend, in member order (the order fixes the floating-point sums)

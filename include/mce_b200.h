@@ -45,7 +45,10 @@ typedef struct mce_options {
                                  -1 = never split.  The results do not depend on it.                          */
   int phase_timing;           /* 1: fill the per-phase ms_* fields of mce_step_stats (adds a stream synchronisation
                                  after every phase of a step); 0 (default): only the CUDA-event totals are measured */
-  int reserved[5];
+  int lean_group_kernel;      /* 1: every group runs the lean variant of the G-table kernel (no second value table in shared
+                                 memory; the engine otherwise uses it only for tables the standard variant cannot hold).
+                                 The results do not depend on it.                                             */
+  int reserved[4];
 } mce_options;
 
 /* Fills `o` with the defaults (device -1, identity search order). */
@@ -140,6 +143,7 @@ typedef struct mce_step_stats {
   double ev_moments_ms;                 /* CUDA-event time of the moment sums on the side stream                  */
   double ev_ftr_ms;                     /* CUDA-event time of the term reduction (sorts, rounds, group lists)      */
   double ev_mu_ms;                      /* CUDA-event time from the start of the step to the end of the measurement update */
+  long long gtable_lean_launches;       /* group-kernel launches that ran the lean variant                          */
 } mce_step_stats;
 int mce_get_step_stats(mce_handle* h, mce_step_stats* out);
 

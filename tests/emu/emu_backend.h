@@ -36,6 +36,8 @@ struct EmuCtx {
   unsigned atomic_cas(unsigned* p, unsigned cmp, unsigned v) { unsigned o = *p; if (o == cmp) *p = v; return o; }
   int load_relaxed(const int* p) { return *p; }
   int atomic_min(int* p, int v) { int o = *p; if (v < o) *p = v; return o; }
+  template <class T> struct Priv { std::vector<T> v; T& operator[](int t) { return v[t]; } };
+  template <class T> Priv<T> priv() const { return Priv<T>{std::vector<T>(nthreads_)}; }
   template <class T, class Op> void block_scan(T* x, T*, Op op) { for (int k = 1; k < nthreads_; k++) x[k] = op(x[k - 1], x[k]); }
   void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
   void cp_async_wait() {}

@@ -37,7 +37,7 @@ def load_product():
 
 
 class Session:
-    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0, phase_timing=False):
+    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0, phase_timing=False, lean=False):
         self.lib, self.sc = lib, sc
         o = MceOptions()
         lib.mce_default_options(ct.byref(o))
@@ -48,6 +48,7 @@ class Session:
         o.fast_moments = int(fast_moments)
         o.group_split_threshold = int(split)
         o.phase_timing = int(phase_timing)
+        o.lean_group_kernel = int(lean)
         self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
         self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
         if not self.h:
@@ -125,9 +126,9 @@ def _ssum(a):
 
 
 def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0,
-                 on_create=None, device=-1):
+                 on_create=None, device=-1, lean=False):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device)
+    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device, lean=lean)
     if on_create is not None:
         on_create(s)
     out = {}
@@ -155,6 +156,7 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
             out[sp + "/gscale"] = np.array([mo.g_scale_factor])
             out[sp + "/stats"] = np.array([st.ms_total, st.ms_tp, st.ms_mu, st.ms_moments, st.ms_regroup, st.ms_ftr, st.ms_gtable, st.ms_compact,
                                            st.ftr_rounds_max, st.diag_unmodelled_alias, st.diag_hash_overflow, st.kernel_launches, st.split_groups])
+            out[sp + "/lean_launches"] = np.array([st.gtable_lean_launches], np.int64)
             full = (k + 1) <= full_upto
             if not mo.skip_post_mu:
                 cnt = s.counts(False)

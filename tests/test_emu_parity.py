@@ -13,7 +13,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 CASES = {"lti3": (8, 5), "lti2": (10, 6), "lti4": (6, 4), "lti3_3msmts": (12, 7), "lti4_2pnoise": (5, 3), "lti4_2msmts": (9, 5),
          "syn2": (12, 3), "syn3": (8, 3), "syn5": (5, 3), "syn7": (4, 2), "syn8": (4, 2), "leo7": (6, 3), "leo5": (7, 4), "homing3": (8, 5),
          # declared deeper than replayed: max_shape > 16 routes through KTpDce / KGTable (sort + hash variants)
-         "homing_real": (8, 5), "lti3_deep": (8, 4), "lti4_2pnoise_deep": (5, 3), "lti3_3msmts_deep": (12, 5)}
+         "homing_real": (8, 5), "leo7_deep16": (6, 3), "lti3_deep": (8, 4), "lti4_2pnoise_deep": (5, 3), "lti3_3msmts_deep": (12, 5)}
 
 
 def _upto(d, k):
@@ -44,6 +44,19 @@ def test_split_reduction_groups_match_golden(emu, name, steps, full, split):
     gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
     got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, split=split)
     assert max(got["s%d/stats" % k][12] for k in range(2, steps + 1)) > 0, "no group was split"
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
+    assert not probs, "\n".join(probs[:20])
+
+
+@pytest.mark.parametrize("name,steps,full,split", [("lti3", 8, 5, 0), ("lti3", 8, 5, 3), ("leo7", 6, 3, 0), ("lti4_2msmts", 8, 5, 0), ("homing3", 8, 5, 0), ("syn2", 10, 3, 2)])
+def test_lean_group_kernel_matches_golden(emu, name, steps, full, split):
+    """The lean variant of the G-table kernel (one value table in shared memory instead of two; taken by the engine for tables the standard
+    variant cannot hold) forced onto every group, with and without split groups."""
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
+    got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, split=split, lean=True)
+    assert max(got["s%d/lean_launches" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
     assert not probs, "\n".join(probs[:20])

@@ -21,7 +21,7 @@ GOLDEN_CASES = {"lti3": (11, 5), "lti2": (10, 6), "lti4": (8, 4), "lti3_3msmts":
                 # the 1-thread reference needs 19 minutes for them), counts / key digests / moments per step
                 "leo7_w5": (13, 0),
                 # declared deeper than replayed: max_shape > 16 routes through KTpDce / KGTable (sort + hash variants)
-                "homing_real": (8, 5), "lti3_deep": (9, 4), "lti4_2pnoise_deep": (6, 3), "lti3_3msmts_deep": (12, 5)}
+                "homing_real": (8, 5), "leo7_deep16": (8, 3), "lti3_deep": (9, 4), "lti4_2pnoise_deep": (6, 3), "lti3_3msmts_deep": (12, 5)}
 
 
 @pytest.fixture(scope="module")
@@ -60,6 +60,20 @@ def test_gpu_matches_reference_golden(lib, name):
             assert abs(int(got[n][2]) - int(gold[n][2])) <= 256, "%s: %s vs %s" % (n, got[n], gold[n])      # total cells of the shape
         skip = lambda n: _skip(n) or n in known
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=skip)
+    assert not probs, "\n".join(probs[:25])
+
+
+@pytest.mark.parametrize("name,steps,full,split", [("lti3", 10, 5, 0), ("lti3", 8, 5, 3), ("leo7", 11, 3, 0), ("lti4_2msmts", 10, 5, 0), ("homing3", 8, 5, 0), ("syn5", 7, 3, 0)])
+def test_gpu_lean_group_kernel_matches_reference_golden(lib, name, steps, full, split):
+    """The lean variant of the G-table kernel (no second value table in shared memory: the variant the engine takes for tables of more than
+    ~6 300 cells, e.g. 7 states with 16 hyperplanes) forced onto every group, split groups included: every array as in the golden dumps."""
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = read_dump(os.path.join(GOLD, name + ".ref.mced"))
+    gold = {n: v for n, v in gold.items() if n == "header" or int(n.split("/")[0][1:]) <= steps}
+    got = run_scenario(lib, sc, full_upto=full, max_steps=steps, capture=full > 0, split=split, lean=True)
+    assert max(got["s%d/lean_launches" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=_skip)
     assert not probs, "\n".join(probs[:25])
 
 

@@ -14,7 +14,7 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 # scenario -> number of steps replayed on the CPU (kept small enough for a few-minute CPU suite)
 CASES = {"lti3": 9, "lti2": 10, "lti4": 7, "lti3_3msmts": 15, "lti4_2pnoise": 6, "lti4_2msmts": 11,
          "syn2": 12, "syn3": 9, "syn4": 7, "syn5": 6, "syn6": 5, "syn7": 5, "syn8": 4, "leo7": 8, "leo5": 9, "homing3": 8,
-         "homing_real": 8, "lti3_deep": 9, "lti4_2pnoise_deep": 6, "lti3_3msmts_deep": 12}
+         "homing_real": 8, "leo7_deep16": 8, "lti3_deep": 9, "lti4_2pnoise_deep": 6, "lti3_3msmts_deep": 12}
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -132,7 +132,9 @@ def homing3():
 # (est:97) exceeds 16 and the engine takes its max_shape > 16 kernels (sort/hash G-table and DCE-TP variants; the bitmap
 # kernels serve max_shape <= 16 only) while the replayed prefix stays cheap for the CPU reference.  The reference supports
 # up to 31 hyperplanes (est:231-235).  name -> (source scenario, declared steps, records kept)
-DEEP = {"lti3_deep": ("lti3", 20, 9), "lti4_2pnoise_deep": ("lti4_2pnoise", 8, 6), "lti3_3msmts_deep": ("lti3_3msmts", 16, 12)}
+DEEP = {"lti3_deep": ("lti3", 20, 9), "lti4_2pnoise_deep": ("lti4_2pnoise", 8, 6), "lti3_3msmts_deep": ("lti3_3msmts", 16, 12),
+        # 7 states with 16 hyperplanes declared (tables of up to 9 949 cells: accepted since the lean group kernel exists), first 8 MUs replayed
+        "leo7_deep16": ("leo7", 10, 8)}
 
 
 def deepen(outdir, name):

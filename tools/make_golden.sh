@@ -25,6 +25,7 @@ python tools/gen_scenarios.py tests/golden      # again: the deep-declared varia
 $R tests/golden/lti3_deep.mces         tests/golden/lti3_deep.ref.mced         --full-upto 4    # max_shape 22
 $R tests/golden/lti4_2pnoise_deep.mces tests/golden/lti4_2pnoise_deep.ref.mced --full-upto 3    # max_shape 18
 $R tests/golden/lti3_3msmts_deep.mces  tests/golden/lti3_3msmts_deep.ref.mced  --full-upto 5    # max_shape 18
+$R tests/golden/leo7_deep16.mces       tests/golden/leo7_deep16.ref.mced       --full-upto 3    # d = 7, max_shape 16
 # the example's sliding-window depth (5 time steps = 15 MUs): recorded with foo_steps = 5, golden for MUs 1..13 (19 minutes on one thread)
 [ -f tests/golden/leo7_w5.mces ] || oracle/_ref/ref_gen_leo7 tests/golden/leo7_w5.mces 5
 [ -f tests/golden/leo7_w5.ref.mced ] || $R tests/golden/leo7_w5.mces tests/golden/leo7_w5.ref.mced --full-upto 0 --max-steps 13
