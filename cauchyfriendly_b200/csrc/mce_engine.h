@@ -758,7 +758,10 @@ class Engine {
     } else {
       be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
-    if (scan_g) be.launch_side(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
+    if (scan_g) {       // one CTA; on the window's last step nothing else waits on the main stream, so it runs there, beside the rank's own chains
+      if (skip_post_mu) be.launch(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
+      else be.launch_side(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
+    }
     be.ev_record_side(5);
     auto finish_moments = [&]() {
       std::vector<double> raw(2 * nq);

@@ -198,103 +198,10 @@ struct KTimeProp {
 };
 
 // ---------------------------------------------------------------------------------------------
-// K3+K4: measurement update, moment contribution and MU coalignment; one thread per (parent, slot).
-// Launched once per old shape `ms` (all parents of a region share MT = ms + npn).
-// ---------------------------------------------------------------------------------------------
-struct KMsmtUpdate {
-  StepParams sp; GenView gen; ParentWs ws; SlotView sl; int ms;
-  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    c.par([&](int tid) {
-      const int MT = sl.MT[ms], spp = MT + 1;
-      const long long ls = (long long)c.block() * c.nthreads() + tid;
-      const int npar = sl.par_begin[ms + 1] - sl.par_begin[ms];
-      if (ls >= (long long)npar * spp) return;
-      const int r = sl.par_begin[ms] + (int)(ls / spp), s = (int)(ls % spp);
-      const long long slot = sl.slot_begin[ms] + ls;
-      const int d = sp.d, gid = gen.alive[r], phc = gen_m(gen, gid);
-      int m; const double *Ap, *pp, *bp;
-      if (sp.with_tp) { m = ws.m_tp[r]; Ap = ws.A + (long long)r * sp.max_shape * d; pp = ws.p + (long long)r * sp.max_shape; bp = ws.b + (long long)r * d; }
-      else { m = phc; Ap = gen_A(gen, gid, phc, d); pp = gen_p(gen, gid, phc); bp = gen_b(gen, gid, d); }
-      SlotMeta me; me.newm = 0; me.pbc = (unsigned char)m; me.z = 0; me.flags = 0; me.hflag = 0; me.enc_lhp = 0; me.csneg = 0; me.parent = r; me.pad_ = 0; me.c_val = 0; me.d_val = 0;
-      double* yout = sl.y + slot * 2 * d;
-      const int t = (s == 0) ? m : s - 1;
-      // --- msmt_update, cauchy_term.hpp:104-134: mu_l = a_l / (H a_l), rho_l = p_l |H a_l| ---
-      double mu[(MAXM + 1) * MAXD], rho[MAXM + 1];
-      unsigned F_int = 0, sgn = 0;
-      if (t <= m) {
-        for (int l = 0; l < m; l++) {
-          double* mu_l = mu + l * d;
-          for (int i = 0; i < d; i++) mu_l[i] = Ap[l * d + i];
-          const double H_mu = dot_lr(sp.H, mu_l, d), a = fabs(H_mu);
-          if (a < MU_EPS) rho[l] = pp[l];
-          else {
-            const double sc = 1.0 / H_mu;
-            for (int i = 0; i < d; i++) mu_l[i] *= sc;
-            rho[l] = pp[l] * a; F_int |= (1u << l);
-            if (!(H_mu > 0)) sgn |= (1u << l);
-          }
-        }
-        rho[m] = sp.gamma; for (int i = 0; i < d; i++) mu[m * d + i] = 0; F_int |= (1u << m);
-      }
-      if (t > m || (s != 0 && t >= m) || !((F_int >> t) & 1u)) {        // no such child (row H-orthogonal, or parent has fewer rows than MT)
-        sl.g[slot] = make_cplx(0, 0);
-        for (int j = 0; j < 2 * d; j++) yout[j] = 0;
-        sl.meta[slot] = me;
-        return;
-      }
-      const double zeta = sp.msmt - dot_lr(sp.H, bp, d);
-      // --- child t, cauchy_term.hpp:158-211 ---
-      double cA[MAXM * MAXD], cp[MAXM], cq[MAXM], cb[MAXD];
-      const double* mu_t = mu + t * d;
-      for (int i = 0; i < d; i++) cb[i] = bp[i] + zeta * mu_t[i];
-      unsigned hofs = 0; int l = 0;
-      for (int _l = 0; _l < m + 1; _l++) {
-        if (_l == t) continue;
-        const double* mu_l = mu + _l * d;
-        cp[l] = rho[_l];
-        if ((F_int >> _l) & 1u) for (int i = 0; i < d; i++) cA[l * d + i] = mu_l[i] - mu_t[i];
-        else { for (int i = 0; i < d; i++) cA[l * d + i] = mu_l[i]; hofs |= (1u << l); }
-        l++;
-      }
-      // enc_lhp, cauchy_term.hpp:217-228
-      unsigned enc_lhp = sgn;
-      if (phc < m) enc_lhp &= (1u << phc) - 1u;
-      me.z = (unsigned char)t; me.flags = (s == 0) ? 0 : 1; me.hflag = hofs; me.enc_lhp = enc_lhp; me.c_val = zeta; me.d_val = rho[t];
-      // --- moment contribution, cauchy_estimator.hpp:307-338 (summed by KMoments) ---
-      const unsigned* pkeys = gen_keys(gen, gid, phc); const cplx* pG = gen_G(gen, gid, phc);
-      const long long rko = sp.max_shape <= 16 ? gen_rk_off(gen, gid, phc) : 0;
-      sl.g[slot] = eval_g_yei(cA, cp, cb, m, d, hofs, zeta, rho[t], sp.root_point, false, phc, t, enc_lhp, pkeys, pG, gen.cells[gid], yout,
-                              sp.max_shape <= 16 ? gen.rbm + rko : nullptr, sp.max_shape <= 16 ? gen.rpf + rko : nullptr);
-      if (s == 0) {
-        unsigned e = sgn;                                   // parent B ^= enc_sgn_AH, half-normalised (term:229-250)
-        if (e & (1u << (m - 1))) e ^= (m >= 32 ? 0xffffffffu : ((1u << m) - 1u));
-        ws.sgnmask[r] = e; ws.bxor[r] = 0;
-      }
-      if (sp.skip_post_mu) { me.newm = (unsigned char)m; sl.meta[slot] = me; return; }
-      // --- normalise / coalign (cauchy_estimator.hpp:719-731) and store the slot ---
-      int newm = m; unsigned csneg = 0;
-      unsigned char* cmap = sl.cmap + slot * MAXM;
-      if (s == 0) normalize_rows(cA, cp, cq, m, d, true);
-      else {
-        newm = mu_coalign_rows(cA, cp, cq, m, d, &hofs, cmap, &csneg);
-        if (newm < m) me.flags |= 2;
-      }
-      me.newm = (unsigned char)newm; me.hflag = hofs; me.csneg = csneg;
-      double* Ao = sl.A + sl.A_off[ms] + ls * (long long)MT * d; double* po = sl.p + sl.pq_off[ms] + ls * MT; double* qo = sl.q + sl.pq_off[ms] + ls * MT;
-      double* bo = sl.b + slot * d;
-      for (int i = 0; i < newm * d; i++) Ao[i] = cA[i];
-      for (int i = 0; i < newm; i++) { po[i] = cp[i]; qo[i] = cq[i]; }
-      for (int i = 0; i < d; i++) bo[i] = cb[i];
-      sl.meta[slot] = me;
-    });
-  }
-};
-
-// ---------------------------------------------------------------------------------------------
 // K3+K4, cooperative version: a CTA takes MU_PB parents at a time and keeps their mu rows and all their children in shared
 // memory; the work is spread as (parent, row), (parent, child, row) and (parent, child) items, so no thread holds a
-// hyperplane array of its own (KMsmtUpdate keeps ~5 KB per thread in local memory, which turns into HBM traffic).
-// Arithmetic and its order are those of KMsmtUpdate / the reference, item by item.
+// hyperplane array of its own (a thread per (parent, child) keeps ~5 KB in local memory, which turns into HBM traffic: round 1's first kernel).
+// Arithmetic and its order are those of the reference (term:84-310), item by item.
 // ---------------------------------------------------------------------------------------------
 constexpr int MU_PB = 4;      // one warp per parent: 32 * MU_PB threads per CTA
 // (child s, element l) items of one parent walked by a lane with stride 32, without integer divisions
