@@ -92,7 +92,10 @@ struct CauchyEstimator
         p0_init = (double*) malloc(d * sizeof(double)); memcpy(p0_init, _p0, d * sizeof(double));
         b0_init = (double*) malloc(d * sizeof(double)); memcpy(b0_init, _b0, d * sizeof(double));
         terms_dp = (CauchyTerm**) calloc(shape_range, sizeof(CauchyTerm*));
-        B_dense = NULL; auto_mirror = false;
+        B_dense = NULL;
+        // Programs compiled UNCHANGED against this header (the Swig shim, the reference's tests) cannot set a member: MCE_AUTO_MIRROR=1 in the
+        // environment switches the mirror on for them, so that the reference's readers of terms_dp (cpdf_ndim.hpp, cauchy_prediction.hpp) find the terms.
+        { const char* am = getenv("MCE_AUTO_MIRROR"); auto_mirror = (am != NULL && atoi(am) != 0); }
         childterms_workspace.init(shape_range-1, d);
         first_term_live = false;
         seed_first_term();

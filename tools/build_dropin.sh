@@ -23,9 +23,23 @@ for t in cauchy_estimator leo_satellite_7state_gps window_manager homing_missile
   echo "built build/dropin/$t"
 done
 # the device cpdf dispatcher checked against the reference's own CPU cpdf code over the host mirror (tests/dropin/cpdf1d_dropin.cpp)
-# ... the Swig shim driven from C++ (tests/dropin/pycauchy_dropin.cpp) and the window bank with logging (winbank_dropin.cpp)
+# ... the Swig shim driven from C++ (tests/dropin/pycauchy_dropin.cpp), the window bank with logging (winbank_dropin.cpp) and the
+# relative-system readers of cauchy_prediction.hpp over two estimators (rsys_dropin.cpp)
 for t in cpdf1d_dropin pycauchy_dropin winbank_dropin; do
   g++ -O3 -w -ffp-contract=off -I"$OV/include" -I"$ROOT/include" "$OV/tests/$t.cpp" -o "$ROOT/build/dropin/$t" \
+      -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
+  echo "built build/dropin/$t"
+done
+# Two estimators in one program (rsys_dropin.cpp): the constructor draws root_point / b_pert with libc rand() once per helper thread (est:125-150), so the
+# second estimator's draws depend on NUM_CPUS.  The golden comes from the NUM_CPUS = 1 reference; this program is therefore built from a second overlay whose
+# cauchy_constants.hpp says NUM_CPUS = 1 (generated exactly like oracle/Makefile does; everything else is the overlay above).
+OV1=$ROOT/build/overlay_cpu1
+rm -rf "$OV1" && cp -a "$OV" "$OV1"
+rm "$OV1/include/cauchy_constants.hpp"
+sed 's/^const int NUM_CPUS = [0-9]*;/const int NUM_CPUS = 1;/' "$REF/include/cauchy_constants.hpp" > "$OV1/include/cauchy_constants.hpp"
+grep -q 'const int NUM_CPUS = 1;' "$OV1/include/cauchy_constants.hpp"
+for t in rsys_dropin; do
+  g++ -O3 -w -ffp-contract=off -I"$OV1/include" -I"$ROOT/include" "$OV1/tests/$t.cpp" -o "$ROOT/build/dropin/$t" \
       -L"$ROOT/cauchyfriendly_b200" -lmce_b200 -Wl,-rpath,'$ORIGIN/../../cauchyfriendly_b200' -lm -lpthread
   echo "built build/dropin/$t"
 done

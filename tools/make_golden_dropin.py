@@ -5,6 +5,7 @@ same sources compiled against include/cauchy_estimator.hpp + libmce_b200.so (too
 
   ex_pycauchy_cpu1.txt   stdout of tests/dropin/pycauchy_dropin.cpp (the Swig shim pycauchy.hpp driven from C++)
   ex_leo5_cpu1.txt       counts + moments printed by src/leo_satellite_5state.cpp (BASELINE.json configs[2])
+  ex_rsys_cpu1.txt       the result lines of tests/dropin/rsys_dropin.cpp: the relative-system readers of cauchy_prediction.hpp over two estimators
   winbank_cpu1/          log files of the 8-window bank on the inputs of src/window_manager.cpp (tests/dropin/winbank_dropin.cpp)
   homing_cpu1/           log files of src/homing_missile.cpp (BASELINE.json configs[1]; closed loop, 8 windows, 99 steps) with
                          time() pinned to the author's seed 1658778374 by tests/dropin/fixed_time.c (LD_PRELOAD)
@@ -38,6 +39,8 @@ def parsed_example(text):
 def main():
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(GOLD, "ex_pycauchy_cpu1.txt"), "w").write(run([os.path.join(REF, "ex_pycauchy_cpu1")], td))
+        from test_rsys_dropin import result_lines
+        open(os.path.join(GOLD, "ex_rsys_cpu1.txt"), "w").write("\n".join(result_lines(run([os.path.join(REF, "ex_rsys_cpu1")], td))) + "\n")
         wb = os.path.join(td, "wb")
         os.makedirs(wb)
         run([os.path.join(REF, "ex_winbank_cpu1"), wb], td)
