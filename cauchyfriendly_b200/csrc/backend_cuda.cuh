@@ -196,6 +196,7 @@ struct CudaBackend {
     if (!evs[i]) MCE_CUDA_CHECK(cudaEventCreate(&evs[i]));
     MCE_CUDA_CHECK(cudaEventRecord(evs[i], side));
   }
+  void ev_wait(int i) { MCE_CUDA_CHECK(cudaEventSynchronize(evs[i])); }      // host waits for a recorded event
   double ev_elapsed(int i0, int i1) {
     float ms = 0;
     MCE_CUDA_CHECK(cudaEventSynchronize(evs[i1]));

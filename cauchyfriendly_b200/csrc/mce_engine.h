@@ -125,6 +125,7 @@ class Engine {
   DevBuf<BE> ptIKey, ptIKeyS, ptIIdx, ptIIdxS, ptFlag, ptPos, ptIList, ptRList, ptSeg, ptNImp, ptReq, ptPRecS, ptPRecR, ptIgpos, ptBxG, ptSKey, ptSAll, ptHost, ptGg;
   DevBuf<BE> iwsSgn, iwsXor, iwsTpB, iwsTpBc, txA, txp, txq, txb, txmeta, txcmap;
   std::vector<int> g_alive_per_shape;           // survivors per shape over all ranks
+  long long early_scale_slots = 400000;         // steps with at least this many slots take G_SCALE_FACTOR from the exact scan of Re fz (mce_options.early_scale_min_slots)
   int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order;
                                                 // 2: like 1, but Re fz -- the one sum that feeds back into the filter -- is the exact scan over ALL slots (KSumScan)
   int scan_restarts = 0;
@@ -745,10 +746,15 @@ class Engine {
       if (moments_mode == 0) { cplx* gg; double* gy; mom_n = part_gather_slots(sl, pg, &gg, &gy); mom_g = gg; mom_y = gy; stats.slots = mom_n; }
       if (moments_mode == 2) { cplx* gg; scan_n = part_gather_slots(sl, pg, &gg, nullptr, false); scan_g = gg; stats.slots = scan_n; }
     }
+    // Large steps: the G-table build only needs G_SCALE_FACTOR = 1 / (2 pi Re fz), and Re fz alone is available early -- KSumScan adds that one chain
+    // as an exact parallel scan, 3x faster than the dependent chain (bit-identical; checked against the chain's own Re fz below).  The G-table kernels
+    // then start as soon as the term reduction is done, and the 2 (1 + d + d^2) serial chains finish beside them instead of in front of them.
+    const bool early_scale = !part && !skip_post_mu && !fast_moments && nslots >= early_scale_slots;
     be.ev_record(6);
     be.sync();
     be.side_begin();
     be.ev_record_side(4);
+    if (early_scale) { be.launch_side(KSumScan{sl.g, nslots, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024)); be.ev_record_side(9); }
     if (fast_moments && !part) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
@@ -763,6 +769,14 @@ class Engine {
       else be.launch_side(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
     }
     be.ev_record_side(5);
+    double early_refz = 0, chain_refz = 0;
+    auto early_gscale = [&]() {        // Re fz from the scan -> the scale of the new G values
+      double sc2[2];
+      be.ev_wait(9);
+      be.d2h(sc2, mom + 2 * nq, sizeof(sc2));
+      early_refz = sc2[0]; scan_restarts = (int)sc2[1];
+      sp.gscale = (1.0 / (2.0 * M_PI)) / early_refz;       // finalize_moments' expression
+    };
     auto finish_moments = [&]() {
       std::vector<double> raw(2 * nq);
       be.side_join();
@@ -782,6 +796,7 @@ class Engine {
           raw[0] = sc2[0]; scan_restarts = (int)sc2[1];
         }
       }
+      chain_refz = raw[0];
       finalize_moments(raw.data(), true);
       sp.gscale = G_SCALE_FACTOR;
     };
@@ -945,7 +960,7 @@ class Engine {
     stats.ms_ftr = toc(tph); tph = tic();
 
     // ---- K7/K8: child B-tables and G-tables, one CTA per reduction group ----
-    finish_moments();            // G_SCALE_FACTOR = 1 / (2 pi Re fz) scales every new G (flat:227)
+    if (early_scale) early_gscale(); else finish_moments();            // G_SCALE_FACTOR = 1 / (2 pi Re fz) scales every new G (flat:227)
     stats.ms_moments += toc(tph); tph = tic();
     // one D2H brings the root counts of every shape (KCountRoots) and the split-group counters (KBigGroups)
     std::vector<unsigned long long> h64(3 * 2 * NSHAPE, 0); std::vector<int> h32(2 * 2 * NSHAPE, 0), cr(2 * NSHAPE, 0);
@@ -1027,6 +1042,10 @@ class Engine {
       if (part && phase == 0) part_bxor_sync(gws);      // phase 1 reads the re-orientation masks phase 0 wrote, on whichever rank
     }
     be.ev_record(3);
+    if (early_scale) {           // the full set of sums, finished beside the G-table kernels; its Re fz must be the scan's, bit for bit
+      finish_moments();
+      if (memcmp(&early_refz, &chain_refz, sizeof(double)) != 0) { error = "the exact scan of Re fz disagrees with the serial chain"; return -7; }
+    }
     stats.ev_gtable_ms = be.ev_elapsed(2, 3); stats.ev_ftr_ms = be.ev_elapsed(7, 8);
     stats.groups = total_groups;
     stats.ms_gtable = toc(tph); tph = tic();

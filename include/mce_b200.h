@@ -32,7 +32,8 @@ enum {
   MCE_ERR_CUDA = -3,
   MCE_ERR_STATE = -4,     /* e.g. stepping past num_estimation_steps (the reference exit(1)s, est:1220-1225) */
   MCE_ERR_CAPACITY = -5,
-  MCE_ERR_FTR = -6        /* the term-reduction rounds did not reach a fixed point (cannot happen for finite inputs) */
+  MCE_ERR_FTR = -6,       /* the term-reduction rounds did not reach a fixed point (cannot happen for finite inputs) */
+  MCE_ERR_SCAN = -7       /* the exact scan of Re fz (early G_SCALE_FACTOR of large steps) disagreed with the serial chain: internal error */
 };
 
 typedef struct mce_options {
@@ -48,7 +49,10 @@ typedef struct mce_options {
   int lean_group_kernel;      /* 1: every group runs the lean variant of the G-table kernel (no second value table in shared
                                  memory; the engine otherwise uses it only for tables the standard variant cannot hold).
                                  The results do not depend on it.                                             */
-  int reserved[4];
+  int early_scale_min_slots;  /* steps with at least this many (parent + child) slots take G_SCALE_FACTOR from an exact parallel scan of
+                                 Re fz, so that the G-table kernels start while the serial moment chains still run; 0 = default
+                                 (400000), -1 = never.  The results do not depend on it.                      */
+  int reserved[3];
 } mce_options;
 
 /* Fills `o` with the defaults (device -1, identity search order). */

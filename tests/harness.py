@@ -37,7 +37,7 @@ def load_product():
 
 
 class Session:
-    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0, phase_timing=False, lean=False):
+    def __init__(self, lib, sc, print_basic_info=False, device=-1, fast_moments=False, split=0, phase_timing=False, lean=False, early_scale=0):
         self.lib, self.sc = lib, sc
         o = MceOptions()
         lib.mce_default_options(ct.byref(o))
@@ -49,6 +49,7 @@ class Session:
         o.group_split_threshold = int(split)
         o.phase_timing = int(phase_timing)
         o.lean_group_kernel = int(lean)
+        o.early_scale_min_slots = int(early_scale)
         self._keep = [np.ascontiguousarray(x, np.float64) for x in (sc.A0, sc.p0, sc.b0, sc.root_point, np.concatenate([sc.b_pert, np.zeros(MAXM)]))]
         self.h = lib.mce_create(sc.d, sc.cmcc, sc.pncc, sc.p, sc.steps, *[_dp(x) for x in self._keep], ct.byref(o))
         if not self.h:
@@ -126,9 +127,9 @@ def _ssum(a):
 
 
 def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0,
-                 on_create=None, device=-1, lean=False):
+                 on_create=None, device=-1, lean=False, early_scale=0):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device, lean=lean)
+    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device, lean=lean, early_scale=early_scale)
     if on_create is not None:
         on_create(s)
     out = {}

@@ -60,3 +60,15 @@ def test_lean_group_kernel_matches_golden(emu, name, steps, full, split):
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
     assert not probs, "\n".join(probs[:20])
+
+
+@pytest.mark.parametrize("name,steps,full", [("lti3", 8, 5), ("leo7", 6, 3), ("homing3", 8, 5), ("lti4_2pnoise", 5, 3), ("lti3_deep", 8, 4)])
+def test_early_scale_from_the_exact_scan_matches_golden(emu, name, steps, full):
+    """Large steps take G_SCALE_FACTOR from the exact scan of Re fz (KSumScan) and finish the serial moment chains beside the G-table kernels; with the
+    threshold at one slot every step does.  The engine itself checks the scan against the chain bit for bit (MCE_ERR_SCAN)."""
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
+    got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, early_scale=1)
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
+    assert not probs, "\n".join(probs[:20])

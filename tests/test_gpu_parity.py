@@ -77,6 +77,19 @@ def test_gpu_lean_group_kernel_matches_reference_golden(lib, name, steps, full, 
     assert not probs, "\n".join(probs[:25])
 
 
+@pytest.mark.parametrize("name,steps,full", [("lti3", 10, 5), ("leo7", 9, 3), ("homing3", 8, 5), ("lti3_deep", 9, 4)])
+def test_gpu_early_scale_from_the_exact_scan_matches_reference_golden(lib, name, steps, full):
+    """G_SCALE_FACTOR from the exact scan of Re fz on EVERY step (threshold one slot; by default steps of 400 000 slots and more, e.g. MU 11 of the
+    LEO7 window in test_gpu_matches_reference_golden): all arrays as in the golden dumps; the engine checks scan == chain bit for bit itself."""
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = read_dump(os.path.join(GOLD, name + ".ref.mced"))
+    gold = {n: v for n, v in gold.items() if n == "header" or int(n.split("/")[0][1:]) <= steps}
+    got = run_scenario(lib, sc, full_upto=full, max_steps=steps, capture=full > 0, early_scale=1)
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=_skip)
+    assert not probs, "\n".join(probs[:25])
+
+
 @pytest.mark.parametrize("name,steps", [("lti3", 8), ("syn4", 7), ("lti4_2msmts", 10), ("leo7", 7)])
 def test_gpu_matches_live_oracle_full_state(lib, name, steps, tmp_path):
     """Every term, coalignment map, FTR flag, key and G value of every step against the oracle run on this box."""

@@ -7,6 +7,7 @@ timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -12
 echo "=== timings"
 timeout 600 python tools/time_scenario.py leo7 2 2>&1 | tail -34
 timeout 300 python tools/time_scenario.py lti3 2 2>&1 | tail -15
+timeout 300 python tools/time_scenario.py leo7_w5 2 2>&1 | tail -18
 echo "=== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$R.json 2> gpurun_out/bench_$R.err; tail -2 gpurun_out/bench_$R.err; cat gpurun_out/bench_$R.json
 echo "=== bench reference arm"
