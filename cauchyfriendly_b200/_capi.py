@@ -43,7 +43,7 @@ EXCHANGE_FN = ct.CFUNCTYPE(ct.c_int, ct.c_void_p, ct.c_int, ct.c_void_p, ct.c_lo
 # every symbol include/mce_b200.h declares
 SYMBOLS = ["mce_default_options", "mce_create", "mce_destroy", "mce_step", "mce_get_moments", "mce_shape_range",
            "mce_get_terms_per_shape", "mce_set_master_step", "mce_reset", "mce_reinitialize_start_statistics", "mce_set_first_term", "mce_shift_b",
-           "mce_deterministic_time_prop", "mce_export_shape", "mce_cpdf_grid_count", "mce_marginal_1d_points", "mce_marginal_1d_grid", "mce_marginal_2d_points", "mce_marginal_2d_grid", "mce_cpdf_last_ms", "mce_get_step_stats", "mce_debug_div_selftest", "mce_debug_moment_sums", "mce_debug_sum_scan", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback", "mce_shard_set_moments_mode", "mce_shard_export_gpos", "mce_shard_get_stats",
+           "mce_deterministic_time_prop", "mce_export_shape", "mce_cpdf_grid_count", "mce_marginal_1d_points", "mce_marginal_1d_grid", "mce_marginal_2d_points", "mce_marginal_2d_grid", "mce_cpdf_last_ms", "mce_get_step_stats", "mce_debug_div_selftest", "mce_debug_moment_sums", "mce_debug_sum_scan", "mce_debug_export_slots", "mce_debug_capture", "mce_debug_muc_shape", "mce_shard_unique_id", "mce_shard_init", "mce_shard_init_callback", "mce_shard_set_moments_mode", "mce_shard_export_gpos", "mce_shard_get_stats",
            "mce_last_error", "mce_version"]
 
 
@@ -76,6 +76,8 @@ def bind(lib):
     lib.mce_cpdf_last_ms.restype = ct.c_double
     lib.mce_debug_capture.argtypes = [ct.c_void_p, ct.c_int]
     lib.mce_debug_sum_scan.argtypes = [ct.c_void_p, ct.c_longlong, dp, dp]
+    lib.mce_debug_export_slots.argtypes = [ct.c_void_p, ct.c_longlong, dp, dp]
+    lib.mce_debug_export_slots.restype = ct.c_longlong
     lib.mce_debug_moment_sums.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_int, dp, dp, dp]
     lib.mce_debug_div_selftest.argtypes = [ct.c_void_p, ct.c_longlong, ct.c_ulonglong, ct.POINTER(ct.c_ulonglong)]
     lib.mce_shard_unique_id.argtypes = [ct.c_int, ct.c_void_p]

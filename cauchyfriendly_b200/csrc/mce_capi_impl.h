@@ -187,6 +187,11 @@ int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, co
   h->e->be.make_current();
   try { return h->e->debug_moment_sums(n, d, g, y, out); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
 }
+long long mce_debug_export_slots(mce_handle* h, long long cap, double* g, double* y) {
+  if (!h || cap < 0) return MCE_ERR_BAD_ARG;
+  h->e->be.make_current();
+  try { return h->e->debug_export_slots(cap, g, y); } catch (const std::exception& ex) { g_mce_error = ex.what(); return MCE_ERR_CUDA; }
+}
 int mce_debug_sum_scan(mce_handle* h, long long n, const double* g, double* out) {
   if (!h || n < 0 || !out || (n > 0 && !g)) return MCE_ERR_BAD_ARG;
   h->e->be.make_current();

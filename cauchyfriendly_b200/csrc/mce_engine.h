@@ -714,7 +714,7 @@ class Engine {
       rank += n; nslots += (long long)n * (MT + 1); offA += (long long)n * (MT + 1) * MT * d; offpq += (long long)n * (MT + 1) * MT;
     }
     sl.par_begin[NSHAPE] = rank; sl.slot_begin[NSHAPE] = nslots; sl.n_slots = nslots;
-    stats.slots = nslots;
+    stats.slots = nslots; last_nslots = nslots;
     sl.meta = (SlotMeta*)slmeta.ensure(sizeof(SlotMeta) * (size_t)(nslots + 1));
     sl.g = (cplx*)slg.ensure(sizeof(cplx) * (size_t)(nslots + 8));
     sl.y = (double*)sly.ensure(sizeof(double) * (size_t)(nslots + 1) * 2 * d);
@@ -1293,6 +1293,15 @@ class Engine {
     be.launch(KMomentsSerial{gg, yy, n, dd, mom}, nq, 512, KMomentsSerial::smem_bytes(dd));
     be.d2h(out, mom, sizeof(double) * 2 * nq);
     return 0;
+  }
+
+  // Test hook: the per-slot moment inputs of the LAST step (g[n] complex, y[n][d] complex: what the moment kernels add up), valid until the next step.
+  long long last_nslots = 0;
+  long long debug_export_slots(long long cap, double* g, double* y) {
+    const long long n = last_nslots < cap ? last_nslots : cap;
+    if (n > 0 && g) be.d2h(g, slg.p, sizeof(cplx) * (size_t)n);
+    if (n > 0 && y) be.d2h(y, sly.p, sizeof(double) * (size_t)n * 2 * d);
+    return last_nslots;
   }
 
   // Test hook: KSumScan over the real parts of n complex values; out[0] = the serial-order sum, out[1] = restarts of the scan.

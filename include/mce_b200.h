@@ -192,6 +192,9 @@ int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, co
 /* Test hook for the exact scan of one serial-order sum (csrc/mce_kern_prop.h: KSumScan, used for Re fz of a partitioned estimator):
  * out[0] = g[0].re + g[1].re + ... added in order, bit for bit; out[1] = how often the scan fell back to the literal loop. */
 int mce_debug_sum_scan(mce_handle* h, long long n, const double* g /* n complex */, double* out /*[2]*/);
+/* Test hook: the per-slot moment inputs of the last step (g: n complex, y: n x d complex; either may be NULL), at most `cap` slots are copied;
+ * returns the slot count of that step.  The moment kernels add exactly these values (cauchy_estimator.hpp:307-338). */
+long long mce_debug_export_slots(mce_handle* h, long long cap, double* g, double* y);
 int mce_debug_capture(mce_handle* h, int enable);
 int mce_debug_muc_shape(mce_handle* h, int m, int* n_terms, double* A, double* p, double* q, double* b, double* cd /*[n][2]*/,
                         int* meta /*[n][8]*/, uint8_t* cmap /*[n][32]*/, int8_t* csmap /*[n][32]*/, int* F /*[n]*/);

@@ -157,7 +157,7 @@ def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode
             out[sp + "/gscale"] = np.array([mo.g_scale_factor])
             out[sp + "/stats"] = np.array([st.ms_total, st.ms_tp, st.ms_mu, st.ms_moments, st.ms_regroup, st.ms_ftr, st.ms_gtable, st.ms_compact,
                                            st.ftr_rounds_max, st.diag_unmodelled_alias, st.diag_hash_overflow, st.kernel_launches, st.split_groups])
-            out[sp + "/lean_launches"] = np.array([st.gtable_lean_launches], np.int64)
+            out[sp + "/lean/stats"] = np.array([st.gtable_lean_launches], np.int64)
             full = (k + 1) <= full_upto
             if not mo.skip_post_mu:
                 cnt = s.counts(False)

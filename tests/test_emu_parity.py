@@ -56,7 +56,7 @@ def test_lean_group_kernel_matches_golden(emu, name, steps, full, split):
     sc = read_scenario(os.path.join(GOLD, name + ".mces"))
     gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
     got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, split=split, lean=True)
-    assert max(got["s%d/lean_launches" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
+    assert max(got["s%d/lean/stats" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
     assert not probs, "\n".join(probs[:20])

@@ -71,7 +71,7 @@ def test_gpu_lean_group_kernel_matches_reference_golden(lib, name, steps, full, 
     gold = read_dump(os.path.join(GOLD, name + ".ref.mced"))
     gold = {n: v for n, v in gold.items() if n == "header" or int(n.split("/")[0][1:]) <= steps}
     got = run_scenario(lib, sc, full_upto=full, max_steps=steps, capture=full > 0, split=split, lean=True)
-    assert max(got["s%d/lean_launches" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
+    assert max(got["s%d/lean/stats" % k][0] for k in range(2, steps + 1)) > 0, "the lean variant did not run"
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=_skip)
     assert not probs, "\n".join(probs[:25])
