@@ -117,6 +117,7 @@ class Engine {
   double cpdf_ms = 0;                          // device time of the last marginal_1d_points call (CUDA events)
   DevBuf<BE> slA, slp, slq, slb, slmeta, slcmap, slg, sly;
   DevBuf<BE> tvA, tvp, tvq, tvb, tvmeta, tvcmap, slotOfTerm;
+  DevBuf<BE> sumTiles;
   DevBuf<BE> rankCounts, rankTotals, momPartial, momOut, scratchI0, scratchI1, scratchI2, scratchI3, scratchK0, scratchK1;
   DevBuf<BE> ftrF, ftrWide, grpOrder, grpStart, aliveFlag, diagBuf, unkBuf, initBuf;
   DevBuf<BE> bigGroups, bigParts, bigCnt, bigRows, bigFlags, bigKeys;
@@ -159,7 +160,7 @@ class Engine {
     DevBuf<BE>* all[] = {&gen[0].g_m, &gen[0].cells, &gen[0].alive, &gen[0].A, &gen[0].p, &gen[0].b, &gen[0].keys, &gen[0].G, &gen[0].rbm, &gen[0].rpf, &gen[1].rbm, &gen[1].rpf, &gen[0].gmax, &gen[1].gmax,
                          &gen[1].g_m, &gen[1].cells, &gen[1].alive, &gen[1].A, &gen[1].p, &gen[1].b, &gen[1].keys, &gen[1].G,
                          &wsA, &wsp, &wsb, &wsm, &wsSgn, &wsXor, &wsTpB, &wsTpBc, &slA, &slp, &slq, &slb, &slmeta, &slcmap, &slg, &sly,
-                         &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut,
+                         &tvA, &tvp, &tvq, &tvb, &tvmeta, &tvcmap, &slotOfTerm, &rankCounts, &rankTotals, &momPartial, &momOut, &sumTiles,
                          &gen[0].gpos, &gen[1].gpos, &imp.g_m, &imp.cells, &imp.alive, &imp.A, &imp.p, &imp.b, &imp.keys, &imp.G, &imp.rbm, &imp.rpf, &imp.gmax, &imp.gpos,
                          &ptKeys, &ptAllKeys, &ptAllSorted, &ptIdx0, &ptIdx1, &ptSplit, &ptDest, &ptCnt, &ptRunOff, &ptSend, &ptRecv, &ptGk, &ptGkS, &ptOrd, &ptGidx, &ptNold,
                          &ptIKey, &ptIKeyS, &ptIIdx, &ptIIdxS, &ptFlag, &ptPos, &ptIList, &ptRList, &ptSeg, &ptNImp, &ptReq, &ptPRecS, &ptPRecR, &ptIgpos, &ptBxG, &ptSKey, &ptSAll, &ptHost, &ptGg,
@@ -383,6 +384,23 @@ class Engine {
     const int W = be.shard.world;
     std::vector<long long> soff(W, 0), scnt(W, bytes);
     be.xchg_alltoallv(send, soff.data(), scnt.data(), recv, roff.data(), rcnt.data());
+  }
+
+  // One serial-order sum (Re of n complex values), bit-identical to the dependent chain: tile summaries in parallel, then the exact walk (csrc/mce_kern_prop.h).
+  void launch_sum_scan(bool side, const cplx* g, long long n, double* out) {
+    const long long TILE = (long long)SS_NT * SS_E, ntiles = (n + TILE - 1) / TILE;
+    KSumScan k{g, n, out};
+    static const bool no_tiles = getenv("MCE_SCAN_NO_TILES") != nullptr;      // measurement switch (tools/scan_real.py)
+    if (ntiles >= 4 && !no_tiles) {
+      const size_t off = (sizeof(double) * (size_t)ntiles + 63) & ~(size_t)63;
+      unsigned char* buf = (unsigned char*)sumTiles.ensure(off + sizeof(SumTile) * (size_t)ntiles + 64);
+      double* tsum = (double*)buf; SumTile* tiles = (SumTile*)(buf + off);
+      KSumTileSums k1{g, n, tsum}; KSumTileMaps k2{g, n, tsum, tiles};
+      if (side) { be.launch_side(k1, (int)ntiles, SS_NT, KSumTileSums::smem_bytes(SS_NT)); be.launch_side(k2, (int)ntiles, SS_NT, KSumTileMaps::smem_bytes(SS_NT)); }
+      else { be.launch(k1, (int)ntiles, SS_NT, KSumTileSums::smem_bytes(SS_NT)); be.launch(k2, (int)ntiles, SS_NT, KSumTileMaps::smem_bytes(SS_NT)); }
+      k.tiles = tiles;
+    }
+    if (side) be.launch_side(k, 1, SS_NT, KSumScan::smem_bytes(SS_NT)); else be.launch(k, 1, SS_NT, KSumScan::smem_bytes(SS_NT));
   }
 
   // Ordered moments (moments_mode 0): every slot's (g, y) is placed at its canonical position of the global slot list and the
@@ -754,7 +772,7 @@ class Engine {
     be.sync();
     be.side_begin();
     be.ev_record_side(4);
-    if (early_scale) { be.launch_side(KSumScan{sl.g, nslots, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024)); be.ev_record_side(9); }
+    if (early_scale) { launch_sum_scan(true, sl.g, nslots, mom + 2 * nq); be.ev_record_side(9); }
     if (fast_moments && !part) {
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
@@ -765,8 +783,7 @@ class Engine {
       be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
     if (scan_g) {       // one CTA; on the window's last step nothing else waits on the main stream, so it runs there, beside the rank's own chains
-      if (skip_post_mu) be.launch(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
-      else be.launch_side(KSumScan{scan_g, scan_n, mom + 2 * nq}, 1, 1024, KSumScan::smem_bytes(1024));
+      launch_sum_scan(!skip_post_mu, scan_g, scan_n, mom + 2 * nq);
     }
     be.ev_record_side(5);
     double early_refz = 0, chain_refz = 0;
@@ -1310,9 +1327,9 @@ class Engine {
     double* mom = (double*)momOut.ensure(sizeof(double) * 4 * (1 + d + d * d) + 16);
     if (n > 0) be.h2d(gg, g, sizeof(cplx) * (size_t)n);
     be.ev_record(10);
-    be.launch(KSumScan{gg, n, mom}, 1, 1024, KSumScan::smem_bytes(1024));
+    launch_sum_scan(false, gg, n, mom);
     be.ev_record(11);
-    be.d2h(out, mom, sizeof(double) * 2);
+    be.d2h(out, mom, sizeof(double) * 3);
     cpdf_ms = be.ev_elapsed(10, 11);          // device time of the kernel, read back through mce_cpdf_last_ms
     return 0;
   }

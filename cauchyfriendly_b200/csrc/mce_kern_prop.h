@@ -567,10 +567,101 @@ MCE_HD bool mom_in_binade(long long S) { return S >= (1ll << 52) + 1 && S <= (1l
 
 constexpr int SS_SERIAL = 32;           // elements added by the literal loop behind a failed check
 constexpr int SS_E = 8;                 // consecutive elements per thread of one tile
-struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re + ... (n addends) in order; out[1] = restarts (as a double, statistics)
+constexpr int SS_NT = 1024;             // threads of the scan kernels: a tile is SS_NT * SS_E = 8192 addends
+
+// Tiles in parallel.  The map of a whole tile only depends on the binade and sign of the running sum while the tile is added, and those can be GUESSED: the plain
+// (unordered) sum of the tiles in front is within rounding noise of the true running sum.  KSumTileSums adds every tile up, KSumTileMaps composes every tile's map
+// under its guess and records, for both parities of the significand at the tile's start, the total offset and the smallest / largest prefix offset.  KSumScan then
+// walks the tiles in order with the EXACT running sum: a tile whose guess was right and whose prefixes all stay inside the binade (two comparisons) is applied in
+// O(1); any other tile -- the sum crosses a binade inside it, the guess was off, special values -- is added the slow way.  Nothing is ever assumed: a summary is only
+// used when the exact state proves the integer model held for every prefix of the tile, so the result is the serial chain's, bit for bit.
+struct SumTile { long long d[2], mn[2], mx[2]; int E, sign, ok, pad; };
+struct SumRange { long long mn[2], mx[2]; };
+struct KSumTileSums {                   // tsum[t] = plain sum of tile t (order irrelevant: it only feeds the guess)
+  const cplx* x; long long n; double* tsum;
+  static MCE_HD size_t smem_bytes(int nthreads) { return sizeof(double) * (size_t)nthreads + 64; }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    double* part = (double*)c.smem();
+    const long long base = (long long)c.block() * c.nthreads() * SS_E;
+    c.par([&](int tid) {
+      double acc = 0;
+      for (int e = 0; e < SS_E; e++) { const long long k = base + (long long)tid * SS_E + e; if (k < n) acc += x[k].re; }
+      part[tid] = acc;
+    });
+    for (int w = c.nthreads() >> 1; w >= 1; w >>= 1) c.par([&](int tid) { if (tid < w) part[tid] += part[tid + w]; });
+    c.par([&](int tid) { if (tid == 0) tsum[c.block()] = part[0]; });
+  }
+};
+struct KSumTileMaps {
+  const cplx* x; long long n; const double* tsum; SumTile* tiles;
+  static MCE_HD size_t smem_bytes(int nthreads) { return sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(SumRange) * ((size_t)nthreads + 32) + sizeof(double) * ((size_t)nthreads + 2) + sizeof(int) * 4 + 64; }
+  template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
+    const int NT = c.nthreads(), t = c.block();
+    MomMap* maps = (MomMap*)c.smem();                 // [NT] + [32] scan scratch
+    SumRange* rng = (SumRange*)(maps + NT + 32);      // [NT] + [32]
+    double* part = (double*)(rng + NT + 32);          // [NT] partial sums of the tiles in front, [NT] the guess
+    int* ctl = (int*)(part + NT + 2);
+    const long long base = (long long)t * NT * SS_E;
+    c.par([&](int tid) {
+      double acc = 0;
+      for (int u = tid; u < t; u += NT) acc += tsum[u];
+      part[tid] = acc;
+      if (tid == 0) ctl[0] = 0;
+    });
+    for (int w = NT >> 1; w >= 1; w >>= 1) c.par([&](int tid) { if (tid < w) part[tid] += part[tid + w]; });
+    const double guess = c.uniform(part[0]);
+    const MomState st = mom_state(guess);
+    if (!st.ok) { c.par([&](int tid) { if (tid == 0) { SumTile T; memset(&T, 0, sizeof(T)); tiles[t] = T; } }); return; }
+    c.par([&](int tid) {
+      MomMap m = mom_identity(); int bad = 0;
+      for (int e = 0; e < SS_E; e++) {
+        const long long k = base + (long long)tid * SS_E + e;
+        if (k >= n) break;
+        MomMap me = mom_identity();
+        if (!mom_classify(x[k].re, st, &me)) bad = 1;
+        m = mom_compose(m, me);
+      }
+      maps[tid] = m;
+      if (bad) ctl[0] = 1;                            // benign race: every writer stores 1
+    });
+    c.block_scan(maps, maps + NT, [](const MomMap& f, const MomMap& g) { return mom_compose(f, g); });
+    c.par([&](int tid) {                               // prefix offsets for both parities of the significand at the tile's start
+      const MomMap Q = tid == 0 ? mom_identity() : maps[tid - 1];
+      long long o[2] = {Q.d0, Q.d1};
+      SumRange r; r.mn[0] = r.mn[1] = 0x7fffffffffffffffll; r.mx[0] = r.mx[1] = -0x7fffffffffffffffll - 1;
+      for (int e = 0; e < SS_E; e++) {
+        const long long k = base + (long long)tid * SS_E + e;
+        if (k >= n) break;
+        MomMap me = mom_identity();
+        mom_classify(x[k].re, st, &me);
+        for (int pi = 0; pi < 2; pi++) {
+          o[pi] += ((pi + o[pi]) & 1) ? me.d1 : me.d0;
+          if (o[pi] < r.mn[pi]) r.mn[pi] = o[pi];
+          if (o[pi] > r.mx[pi]) r.mx[pi] = o[pi];
+        }
+      }
+      rng[tid] = r;
+    });
+    c.block_scan(rng, rng + NT, [](const SumRange& a, const SumRange& b) {
+      SumRange r;
+      for (int pi = 0; pi < 2; pi++) { r.mn[pi] = a.mn[pi] < b.mn[pi] ? a.mn[pi] : b.mn[pi]; r.mx[pi] = a.mx[pi] > b.mx[pi] ? a.mx[pi] : b.mx[pi]; }
+      return r;
+    });
+    c.par([&](int tid) {
+      if (tid != 0) return;
+      SumTile T;
+      T.d[0] = maps[NT - 1].d0; T.d[1] = maps[NT - 1].d1;
+      for (int pi = 0; pi < 2; pi++) { T.mn[pi] = rng[NT - 1].mn[pi]; T.mx[pi] = rng[NT - 1].mx[pi]; }
+      T.E = st.E; T.sign = st.sign; T.ok = ctl[0] ? 0 : 1; T.pad = 0;
+      tiles[t] = T;
+    });
+  }
+};
+struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re + ... (n addends) in order; out[1] = restarts, out[2] = tiles taken from their summaries (statistics)
   const cplx* x; long long n; double* out;
+  const SumTile* tiles = nullptr;       // summaries of KSumTileMaps (same tile size), or null: every tile the slow way
   static MCE_HD size_t smem_bytes(int nthreads) {
-    return sizeof(double) * (2 * (size_t)nthreads * SS_E + 2) + sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(long long) * (size_t)nthreads + sizeof(int) * 8 + 64;
+    return sizeof(double) * (2 * (size_t)nthreads * SS_E + 2) + sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(long long) * ((size_t)nthreads + 2) + sizeof(int) * 8 + 64;
   }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     const int NT = c.nthreads(), TILE = NT * SS_E;
@@ -578,13 +669,38 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
     double* sv = vals + 2 * (size_t)TILE;             // [0] running sum
     MomMap* maps = (MomMap*)(sv + 2);                 // [NT] thread maps (inclusive scan in place), then [32] scan scratch
     long long* Ss = (long long*)(maps + NT + 32);     // [NT] significand in front of every thread's first element
-    int* ctl = (int*)(Ss + NT);                       // [0] first failing element, [1] done, [2] next start, [3] restarts
+    long long* tnext = Ss + NT;                       // [0] first tile the fast path could not take
+    int* ctl = (int*)(Ss + NT + 2);                   // [0] first failing element, [1] done, [2] next start, [3] restarts, [4] tiles applied from their summaries
     const long long ntiles = (n + TILE - 1) / TILE;
     c.par([&](int tid) {
-      if (tid == 0) { sv[0] = 0; ctl[3] = 0; }
-      for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
+      if (tid == 0) { sv[0] = 0; ctl[3] = 0; ctl[4] = 0; }
+      if (!tiles) for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
     });
     for (long long t = 0; t < ntiles; t++) {
+      if (tiles) {
+        // every consecutive tile whose summary the exact running sum validates is applied in O(1) by one thread; the first one that is not is added below
+        c.par([&](int tid) {
+          if (tid != 0) return;
+          double s = sv[0]; long long tt = t;
+          const long long LO = (1ll << 52) + 1, HI = (1ll << 53) - 2;
+          while (tt < ntiles) {
+            const SumTile T = tiles[tt];
+            const MomState st = mom_state(s);
+            if (!(T.ok && st.ok && st.E == T.E && st.sign == T.sign)) break;
+            const int pi = (int)(st.S & 1);
+            if (!(T.mn[pi] >= LO - st.S && T.mx[pi] <= HI - st.S)) break;      // written so that garbage offsets cannot overflow the comparison
+            s = mom_value(st, st.S + T.d[pi]);
+            tt++;
+          }
+          sv[0] = s; tnext[0] = tt; ctl[4] += (int)(tt - t);
+        });
+        t = c.uniform(tnext[0]);
+        if (t >= ntiles) break;
+        c.par([&](int tid) {
+          double* buf = vals + (t & 1) * (size_t)TILE;
+          for (int e = 0; e < SS_E; e++) { const long long k = t * TILE + (long long)tid * SS_E + e; buf[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
+        });
+      }
       const int cnt = (int)((n - t * TILE) < TILE ? (n - t * TILE) : TILE);
       const double* a = vals + (t & 1) * (size_t)TILE;
       int pos = 0;
@@ -596,7 +712,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
         // A: the maps of the own elements, composed; the next tile's loads are issued first and stored last, so they fly meanwhile
         c.par([&](int tid) {
           double nx[SS_E];
-          const bool pre = pos == 0 && t + 1 < ntiles;
+          const bool pre = !tiles && pos == 0 && t + 1 < ntiles;
           if (pre) for (int e = 0; e < SS_E; e++) { const long long k = (t + 1) * TILE + (long long)tid * SS_E + e; nx[e] = (k < n) ? x[k].re : 0.0; }
           MomMap m = mom_identity(); int bad = 0;
           for (int e = 0; e < SS_E; e++) {
@@ -653,7 +769,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
         pos = c.uniform(ctl[2]);
       }
     }
-    c.par([&](int tid) { if (tid == 0) { out[0] = sv[0]; out[1] = (double)ctl[3]; } });
+    c.par([&](int tid) { if (tid == 0) { out[0] = sv[0]; out[1] = (double)ctl[3]; out[2] = (double)ctl[4]; } });
   }
 };
 

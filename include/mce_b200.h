@@ -190,8 +190,9 @@ int mce_debug_div_selftest(mce_handle* h, long long n, unsigned long long seed, 
  * g: n complex values, y: n x d complex values (d may be 0: only fz), out: 2 * (1 + d + d*d) doubles. */
 int mce_debug_moment_sums(mce_handle* h, long long n, int d, const double* g, const double* y, double* out);
 /* Test hook for the exact scan of one serial-order sum (csrc/mce_kern_prop.h: KSumScan, used for Re fz of a partitioned estimator):
- * out[0] = g[0].re + g[1].re + ... added in order, bit for bit; out[1] = how often the scan fell back to the literal loop. */
-int mce_debug_sum_scan(mce_handle* h, long long n, const double* g /* n complex */, double* out /*[2]*/);
+ * out[0] = g[0].re + g[1].re + ... added in order, bit for bit; out[1] = how often the scan fell back to the literal loop; out[2] = tiles (of 8192
+ * addends) applied in O(1) from the summaries computed in parallel (KSumTileSums / KSumTileMaps). */
+int mce_debug_sum_scan(mce_handle* h, long long n, const double* g /* n complex */, double* out /*[3]*/);
 /* Test hook: the per-slot moment inputs of the last step (g: n complex, y: n x d complex; either may be NULL), at most `cap` slots are copied;
  * returns the slot count of that step.  The moment kernels add exactly these values (cauchy_estimator.hpp:307-338). */
 long long mce_debug_export_slots(mce_handle* h, long long cap, double* g, double* y);

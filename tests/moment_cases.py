@@ -47,6 +47,21 @@ def cases(seed=0):
     out["binade_walk"] = np.where(np.arange(n) % 7 == 0, -0.9, 0.15) * (1.0 + rng.random(n) * 1e-12)
     out["long_random"] = rng.standard_normal(200000) + 0.01
     out["long_positive"] = rng.random(300000) * np.exp(rng.uniform(-20, 0, 300000))
+    # long sequences for the tiled scan (tiles of 8192 addends are summarised in parallel under a GUESSED binade and applied only when the exact sum agrees)
+    N = 150000
+    tt = np.where(rng.random(N) < 0.5, 2.0 ** -53, 2.0 ** -52) * rng.choice([1.0, 1.0, -1.0], N); tt[0] = 1.0
+    out["tiles_ties"] = tt                                               # half-ulp ties on a sum near 1: the parity maps carry across tiles
+    out["tiles_binade_growth"] = np.exp(np.linspace(-25, 3, N)) * rng.random(N)      # crosses ~40 binades, some inside tiles, some at their edges
+    edge = np.full(N, 2.0 ** -60); edge[0] = 1.0 - 2.0 ** -40; edge[8192 * 3 - 1] = 2.0 ** -40; edge[8192 * 7] = 2.0 ** -41
+    out["tiles_cross_at_edges"] = edge                                   # the sum reaches exactly 1.0 on the last addend of a tile
+    sw = rng.standard_normal(N) * 1e-6; sw[0] = 1.0; sw[N // 3] = -2.0; sw[2 * N // 3] = 2.5
+    out["tiles_sign_changes"] = sw
+    bo = np.where(np.arange(N) % 2 == 0, 0.75, -0.75) * (1.0 + rng.random(N) * 1e-9); bo[0] = 1.5
+    out["tiles_big_offsets"] = bo                                        # addends as large as the sum: offsets of 2^52 ulps, the guards against overflowing them
+    gi = rng.random(N) * 1e-3; gi[N // 2] = np.inf
+    out["tiles_inf_inside"] = gi
+    go = np.full(N, 2.0 ** -70); go[0] = 1.0 - 2.0 ** -53               # the exact sum stays below 1 for a long time while the unordered tile sums round to 1.0
+    out["tiles_guess_off"] = go
     out["short_3"] = np.array([1.0, 2.0 ** -53, 2.0 ** -53])
     out["empty"] = np.zeros(0)
     out["exact_tile"] = rng.random(1024)

@@ -56,20 +56,23 @@ def _check_scan(lib):
     sc = read_scenario(os.path.join(ROOT, "tests", "golden", "lti3.mces"))
     s = Session(lib, sc)
     dp = ct.POINTER(ct.c_double)
-    restarts = {}
+    restarts, fast = {}, {}
     try:
         for name, a in cases().items():
             g = np.zeros((len(a), 2)); g[:, 0] = a; g[:, 1] = 12345.0
             g = np.ascontiguousarray(g)
-            out = np.zeros(2)
+            out = np.zeros(3)
             assert lib.mce_debug_sum_scan(s.h, len(a), g.ctypes.data_as(dp), out.ctypes.data_as(dp)) == 0
             want = serial_sum(a)
             assert out[0].tobytes() == np.float64(want).tobytes(), "%s: scan %r != serial chain %r" % (name, out[0], want)
-            restarts[name] = int(out[1])
+            restarts[name] = int(out[1]); fast[name] = int(out[2])
     finally:
         s.close()
     assert restarts["long_positive"] < 200 and restarts["all_zero"] == 0, restarts      # the scan path really carries the friendly chains
     assert restarts["binade_walk"] > 50, restarts                                        # ... and the literal loop the hostile ones
+    # the tiled path: 300 000 friendly addends are 37 tiles, nearly all applied from their summaries; hostile data falls back and is still exact
+    assert fast["long_positive"] >= 30 and fast["tiles_ties"] >= 14, fast
+    assert fast["tiles_big_offsets"] == 0 and fast["tiles_guess_off"] == 0 and fast["tiles_inf_inside"] < 10, fast      # wrong guesses cost time, never bits
 
 
 def test_sum_scan_equals_the_serial_chain_emulated():
