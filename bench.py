@@ -349,7 +349,7 @@ def gpu_arm(args):
                            "heaviest_mu": {"mu": a0["heaviest"][1], "ms": a0["heaviest"][0], "terms_after_muc": a0["heaviest"][2], "survivors": a0["heaviest"][3]},
                            "parallelism": ("one window partitioned over %d gpus: terms routed to the owners of their reduction keys (NCCL send/recv), parent tables fetched from their home ranks" if term_sharded else "window-per-gpu x%d") % world, "l2": "flushed between timed iterations (256 MiB fill)",
                            "moments": "reference serial order (bit-exact)" if not term_sharded or args.moments == "ordered" else (
-                               "Re fz bit-exact (exact scan of the serial chain over all ranks' slots => counts, keys and G bit-exact); Im fz, mean, covariance: per-rank serial sums added in rank order" if args.moments == "hybrid"
+                               "Re fz bit-exact (exact scan of the serial chain over all ranks' slots => counts, keys and G bit-exact); Im fz, mean, covariance: per-rank two-level sums added in rank order" if args.moments == "hybrid"
                                else "per-rank serial sums added in rank order (last bits depend on N)"), "gtable_share_of_step": sum(a["gt_ms"] for a in acc) / (1e3 * ev_s)},
                 "e2e": {"value": child / wall_s, "unit": "child terms/s", "h2d_bytes_per_step": a0["h2d"], "d2h_bytes_per_step": a0["d2h"]},
                 "gpu_launches": int(sum(a["launches"] for a in acc)),

@@ -779,6 +779,13 @@ class Engine {
       be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
       be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
       be.launch_side(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
+    } else if (part && moments_mode == 2) {
+      // hybrid: the rank's own sums are added to the other ranks' in rank order anyway, so they need not be dependent chains: fixed-shape two-level reduction
+      // (deterministic for a given partition).  The one sum whose bits matter downstream, Re fz, comes from the exact scan over all ranks' slots.
+      const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
+      double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)(nblk > 0 ? nblk : 1) * 2 * nq + 64);
+      if (nblk > 0) be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial, 1}, nblk, 128, sizeof(double) * 2 * 128);
+      be.launch_side(KMomentsFinal{partial, nblk, nq, mom}, (2 * nq + 127) / 128, 128, 0);
     } else {
       be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }

@@ -774,10 +774,11 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
 };
 
 constexpr int MOM_CHUNK = 4096;   // slots per block of the partial-moment reduction
-struct KMomentsPartial {          // partial[block][2*(d + d*d)] = sum over the block's slots of (g*y_j, -g*y_j*y_k)
+struct KMomentsPartial {          // partial[block][2*(fz + d + d*d)] = sum over the block's slots of ([g,] g*y_j, -g*y_j*y_k)
   const cplx* g; const double* y; long long n; int d; double* partial;
+  int fz = 0;                     // 1: the normalisation sum (g itself) is quantity 0, so that KMomentsFinal writes the whole moment vector
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
-    const int nq = d + d * d;
+    const int nq = fz + d + d * d;
     double* sm = (double*)c.smem();                 // [nthreads][2] scratch per quantity
     const long long lo = (long long)c.block() * MOM_CHUNK;
     const long long hi = lo + MOM_CHUNK < n ? lo + MOM_CHUNK : n;
@@ -788,9 +789,11 @@ struct KMomentsPartial {          // partial[block][2*(d + d*d)] = sum over the 
           const cplx gv = g[i];
           const double* yy = y + i * 2 * d;
           cplx v;
-          if (qn < d) v = cmul(gv, make_cplx(yy[2 * qn], yy[2 * qn + 1]));
+          const int qm = qn - fz;
+          if (qm < 0) v = gv;
+          else if (qm < d) v = cmul(gv, make_cplx(yy[2 * qm], yy[2 * qm + 1]));
           else {
-            const int j = (qn - d) / d, k = (qn - d) % d;
+            const int j = (qm - d) / d, k = (qm - d) % d;
             v = cmul(cmul(gv, make_cplx(yy[2 * j], yy[2 * j + 1])), make_cplx(yy[2 * k], yy[2 * k + 1]));
             v.re = -v.re; v.im = -v.im;
           }

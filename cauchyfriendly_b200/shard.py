@@ -8,7 +8,7 @@ transport="nccl": the library opens libnccl.so.2 itself and issues grouped send/
 CUDA stream; torch.distributed is only used to ship the 128-byte NCCL id from rank 0.  transport="callback": the library hands
 every exchange to Python, which runs it over `dist` (used by the CPU tests with the gloo backend and host memory).
 moments: "ordered" (every sum bit-identical to one GPU), "hybrid" (Re fz -- the sum that feeds back into the filter -- bit-identical through an exact
-scan over all ranks' slots, the other sums per rank and added in rank order: every count, key and G stays bit-identical, mean / covariance move in the
+scan over all ranks' slots, the other sums per rank (two-level reductions) and added in rank order: every count, key and G stays bit-identical, mean / covariance move in the
 last digits) or "allreduce" (all sums per rank; fz moves in the last bits and deep steps can lose or gain a term)."""
 import ctypes as ct
 

@@ -49,8 +49,12 @@ elif mode == "hybrid":
             a, b = gold[n], got[n]
             if a[0].real.tobytes() != b[0].real.tobytes():
                 probs.append("%s: Re fz is not bit-identical (%r vs %r)" % (n, a[0].real, b[0].real))
-            if np.max(np.abs(a[1:1 + d] - b[1:1 + d])) > 1e-9 * np.max(np.abs(a[1:1 + d])) or np.max(np.abs(a[1 + d:] - b[1 + d:])) > 1e-4 * np.max(np.abs(a[1 + d:])):
-                probs.append("%s: mean / covariance differ beyond the reordering noise" % n)
+            # tolerance: 1e-8 of the largest mean entry, 1e-4 of the largest covariance entry.  These sums cancel 7 to 8 digits (partial sums of 1e5 against results of
+            # 1e-1), so ANY other order of the same addends moves them by ~1e-9 / ~1e-6; the reference's own 8-thread build is 8.5e-6 / 1.4e-1 away from its 1-thread
+            # build on this window (tests/test_oracle_golden.py prints the table)
+            if np.max(np.abs(a[1:1 + d] - b[1:1 + d])) > 1e-8 * np.max(np.abs(a[1:1 + d])) or np.max(np.abs(a[1 + d:] - b[1 + d:])) > 1e-4 * np.max(np.abs(a[1 + d:])):
+                probs.append("%s: mean / covariance differ beyond the reordering noise (mean %.2e, covariance %.2e of the largest entry)" % (
+                    n, np.max(np.abs(a[1:1 + d] - b[1:1 + d])) / np.max(np.abs(a[1:1 + d])), np.max(np.abs(a[1 + d:] - b[1 + d:])) / np.max(np.abs(a[1 + d:]))))
 else:
     # rank-ordered partial sums: fz (hence every G) moves in the last bits, cells that cancel move more; the discrete results
     # (counts, keys, hyperplanes) are compared exactly, fz and the mean to 1e-9, G through its digest to 1e-6
