@@ -10,7 +10,7 @@ MAXM = 32
 
 class MceOptions(ct.Structure):
     _fields_ = [("device", ct.c_int), ("tr_search_order", ct.c_int * 12), ("print_basic_info", ct.c_int),
-                ("fast_moments", ct.c_int), ("group_split_threshold", ct.c_int), ("phase_timing", ct.c_int), ("lean_group_kernel", ct.c_int), ("early_scale_min_slots", ct.c_int), ("reserved", ct.c_int * 3)]
+                ("fast_moments", ct.c_int), ("group_split_threshold", ct.c_int), ("phase_timing", ct.c_int), ("lean_group_kernel", ct.c_int), ("early_scale_min_slots", ct.c_int), ("fast_moments_min_slots", ct.c_int), ("reserved", ct.c_int * 2)]
 
 
 class MceMoments(ct.Structure):

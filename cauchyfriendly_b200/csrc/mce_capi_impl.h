@@ -36,6 +36,7 @@ mce_handle* mce_create(int d, int cmcc, int pncc, int p, int steps, const double
   e->fast_moments = opts->fast_moments != 0;
   e->phase_timing = opts->phase_timing != 0;
   e->lean_groups = opts->lean_group_kernel != 0;
+  e->fast_moments_slots = opts->fast_moments_min_slots <= 0 ? 300000 : opts->fast_moments_min_slots;
   e->early_scale_slots = opts->early_scale_min_slots == 0 ? 400000 : (opts->early_scale_min_slots < 0 ? (1ll << 62) : opts->early_scale_min_slots);
   e->big_T = opts->group_split_threshold == 0 ? mce::BIG_T : (opts->group_split_threshold < 0 ? 0x7fffffff : opts->group_split_threshold);
   if (!e->be.init(opts->device, &berr)) { g_mce_error = "mce_create: " + berr; delete e; return nullptr; }

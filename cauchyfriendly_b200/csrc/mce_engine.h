@@ -102,7 +102,7 @@ class Engine {
   StepStats stats;
   std::string error;
   bool finished = false;     // the window's last step has run: only reset() is valid now
-  bool fast_moments = false; // mean/covariance by a two-level tree instead of the reference's serial order (fz stays serial)
+  bool fast_moments = false; // every moment sum but Re fz by a two-level tree instead of the reference's serial order; Re fz by the exact scan (bit-identical)
 
   // ---- device state ----
   struct GenStore {
@@ -126,6 +126,7 @@ class Engine {
   DevBuf<BE> ptIKey, ptIKeyS, ptIIdx, ptIIdxS, ptFlag, ptPos, ptIList, ptRList, ptSeg, ptNImp, ptReq, ptPRecS, ptPRecR, ptIgpos, ptBxG, ptSKey, ptSAll, ptHost, ptGg;
   DevBuf<BE> iwsSgn, iwsXor, iwsTpB, iwsTpBc, txA, txp, txq, txb, txmeta, txcmap;
   std::vector<int> g_alive_per_shape;           // survivors per shape over all ranks
+  long long fast_moments_slots = 300000;        // mce_options.fast_moments_min_slots: below, the 114 dependent chains take < 1.5 ms and hide behind the term reduction: fast_moments keeps them (bit-exact)
   long long early_scale_slots = 400000;         // steps with at least this many slots take G_SCALE_FACTOR from the exact scan of Re fz (mce_options.early_scale_min_slots)
   int moments_mode = 0;                         // 0: every rank adds ALL slots in the reference's order (bit-exact); 1: per-rank serial sums added in rank order;
                                                 // 2: like 1, but Re fz -- the one sum that feeds back into the filter -- is the exact scan over ALL slots (KSumScan)
@@ -773,15 +774,11 @@ class Engine {
     be.side_begin();
     be.ev_record_side(4);
     if (early_scale) { launch_sum_scan(true, sl.g, nslots, mom + 2 * nq); be.ev_record_side(9); }
-    if (fast_moments && !part) {
-      const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
-      double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)nblk * 2 * (nq - 1) + 64);
-      be.launch_side(KMomentsSerial{sl.g, sl.y, nslots, 0, mom}, 1, 256, KMomentsSerial::smem_bytes(0));     // d = 0: only fz, in serial order
-      be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial}, nblk, 128, sizeof(double) * 2 * 128);
-      be.launch_side(KMomentsFinal{partial, nblk, nq - 1, mom + 2}, (2 * (nq - 1) + 127) / 128, 128, 0);
-    } else if (part && moments_mode == 2) {
-      // hybrid: the rank's own sums are added to the other ranks' in rank order anyway, so they need not be dependent chains: fixed-shape two-level reduction
-      // (deterministic for a given partition).  The one sum whose bits matter downstream, Re fz, comes from the exact scan over all ranks' slots.
+    if ((fast_moments && !part && nslots >= fast_moments_slots) || (part && moments_mode == 2)) {
+      // mce_options.fast_moments on one GPU / hybrid on a partitioned estimator: no dependent chain.  Every sum is a fixed-shape two-level reduction (deterministic
+      // for a given partition; a rank's sums are added to the other ranks' in rank order anyway) EXCEPT the one whose bits matter downstream: Re fz comes from the
+      // exact scan -- over all ranks' slots when partitioned -- so G_SCALE_FACTOR, and with it every count, key and G value, stays bit-identical.
+      if (!part) { scan_g = sl.g; scan_n = nslots; }
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)(nblk > 0 ? nblk : 1) * 2 * nq + 64);
       if (nblk > 0) be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial, 1}, nblk, 128, sizeof(double) * 2 * 128);
@@ -806,7 +803,8 @@ class Engine {
       be.side_join();
       stats.ev_moments_ms = be.ev_elapsed(4, 5); stats.ev_mu_ms = be.ev_elapsed(0, 6);
       be.d2h(raw.data(), mom, sizeof(double) * 2 * nq);
-      if (part && moments_mode != 0) {        // per-rank serial sums, added in rank order: the same result on every rank for a given world size
+      if (!part && fast_moments && nslots >= fast_moments_slots) { double sc2[2]; be.d2h(sc2, mom + 2 * nq, sizeof(sc2)); raw[0] = sc2[0]; scan_restarts = (int)sc2[1]; }
+      if (part && moments_mode != 0) {        // per-rank sums, added in rank order: the same result on every rank for a given world size
         std::vector<long long> mine(2 * nq);
         memcpy(mine.data(), raw.data(), sizeof(double) * 2 * nq);
         const std::vector<long long> all = allgather_ll(mine);

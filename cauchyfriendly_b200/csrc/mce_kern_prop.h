@@ -565,7 +565,8 @@ MCE_HD bool mom_classify(double a, const MomState& st, MomMap* m) {
 }
 MCE_HD bool mom_in_binade(long long S) { return S >= (1ll << 52) + 1 && S <= (1ll << 53) - 2; }
 
-constexpr int SS_SERIAL = 32;           // elements added by the literal loop behind a failed check
+constexpr int SS_SERIAL = 32;           // elements added by the literal loop behind a failed check ...
+constexpr int SS_SERIAL_MAX = 4096;     // ... doubling up to this while the scan keeps failing early
 constexpr int SS_E = 8;                 // consecutive elements per thread of one tile
 constexpr int SS_NT = 1024;             // threads of the scan kernels: a tile is SS_NT * SS_E = 8192 addends
 
@@ -673,7 +674,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
     int* ctl = (int*)(Ss + NT + 2);                   // [0] first failing element, [1] done, [2] next start, [3] restarts, [4] tiles applied from their summaries
     const long long ntiles = (n + TILE - 1) / TILE;
     c.par([&](int tid) {
-      if (tid == 0) { sv[0] = 0; ctl[3] = 0; ctl[4] = 0; }
+      if (tid == 0) { sv[0] = 0; ctl[3] = 0; ctl[4] = 0; ctl[5] = SS_SERIAL / 2; }
       if (!tiles) for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
     });
     for (long long t = 0; t < ntiles; t++) {
@@ -761,7 +762,12 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
             for (int k = tv * SS_E; k < v; k++) { if (k < pos) continue; MomMap me = mom_identity(); mom_classify(a[k], st, &me); S = mom_apply(me, S); }
             acc = mom_value(st, S);
           }
-          const int e = v + SS_SERIAL < cnt ? v + SS_SERIAL : cnt;
+          // Crossings come in clusters (the first thousands of addends of a real chain change binade every few elements): when the scan got nowhere, the literal
+          // run behind the failure doubles (5 ns per addend beats a 10 us scan pass that dies after a handful); a scan that carried a long stretch resets it.
+          int L = ctl[5];
+          L = (v - pos < 256) ? (L * 2 < SS_SERIAL_MAX ? L * 2 : SS_SERIAL_MAX) : SS_SERIAL;
+          ctl[5] = L;
+          const int e = v + L < cnt ? v + L : cnt;
           for (int i = v; i < e; i++) acc += a[i];
           sv[0] = acc; ctl[2] = e; ctl[1] = (e >= cnt) ? 1 : 0; ctl[3] += 1;
         });

@@ -40,8 +40,11 @@ typedef struct mce_options {
   int device;                 /* CUDA device ordinal; -1 = current device                                    */
   int tr_search_order[12];    /* TR_SEARCH_IDXS_ORDERING (cauchy_constants.hpp:66); {0,1,2,...} by default   */
   int print_basic_info;       /* reference quirk A.9(iii): when set, moments are re-evaluated after FTR      */
-  int fast_moments;           /* 0 (default): mean/covariance summed in the reference's serial order (bit-identical to
-                                 NUM_CPUS=1); 1: two-level tree reduction (deterministic, differs in the last bits)      */
+  int fast_moments;           /* 0 (default): every moment sum in the reference's serial order (bit-identical to NUM_CPUS=1: 114
+                                 dependent chains at d = 7, 5 ns per slot); 1: two-level tree reductions (deterministic; Im fz, mean
+                                 and covariance differ from the serial order by ~1e-9 / ~1e-6 of their largest entry), except Re fz,
+                                 which an exact parallel scan keeps bit-identical -- and with it G_SCALE_FACTOR and every count, key
+                                 and G value of the following steps                                                  */
   int group_split_threshold;  /* reduction groups with more members are split over several CTAs; 0 = default (192),
                                  -1 = never split.  The results do not depend on it.                          */
   int phase_timing;           /* 1: fill the per-phase ms_* fields of mce_step_stats (adds a stream synchronisation
@@ -52,7 +55,9 @@ typedef struct mce_options {
   int early_scale_min_slots;  /* steps with at least this many (parent + child) slots take G_SCALE_FACTOR from an exact parallel scan of
                                  Re fz, so that the G-table kernels start while the serial moment chains still run; 0 = default
                                  (400000), -1 = never.  The results do not depend on it.                      */
-  int reserved[3];
+  int fast_moments_min_slots; /* fast_moments applies to steps with at least this many slots (below, the dependent chains are cheap and
+                                 stay, bit-exact); 0 = default (300000)                                        */
+  int reserved[2];
 } mce_options;
 
 /* Fills `o` with the defaults (device -1, identity search order). */

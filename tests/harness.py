@@ -45,7 +45,8 @@ class Session:
             o.tr_search_order[i] = sc.tr_order[i]
         o.print_basic_info = int(print_basic_info)
         o.device = int(device)
-        o.fast_moments = int(fast_moments)
+        o.fast_moments = 1 if fast_moments else 0
+        o.fast_moments_min_slots = int(fast_moments) if int(fast_moments) > 1 else 0      # fast_moments=N > 1: the option with its slot threshold set to N
         o.group_split_threshold = int(split)
         o.phase_timing = int(phase_timing)
         o.lean_group_kernel = int(lean)
@@ -127,9 +128,9 @@ def _ssum(a):
 
 
 def run_scenario(lib, sc, full_upto=0, max_steps=None, capture=False, shift_mode="recorded", on_step=None, print_basic_info=False, split=0,
-                 on_create=None, device=-1, lean=False, early_scale=0):
+                 on_create=None, device=-1, lean=False, early_scale=0, fast_moments=False):
     """Returns {name: array} in the dump layout. capture=True adds the post-MUC term list / F arrays of full steps."""
-    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device, lean=lean, early_scale=early_scale)
+    s = Session(lib, sc, print_basic_info=print_basic_info, split=split, device=device, lean=lean, early_scale=early_scale, fast_moments=fast_moments)
     if on_create is not None:
         on_create(s)
     out = {}

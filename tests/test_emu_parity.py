@@ -72,3 +72,22 @@ def test_early_scale_from_the_exact_scan_matches_golden(emu, name, steps, full):
     got = {n: v for n, v in got.items() if n in gold}
     probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12})
     assert not probs, "\n".join(probs[:20])
+
+
+@pytest.mark.parametrize("name,steps,full", [("leo7", 6, 3), ("lti3", 8, 5)])
+def test_fast_moments_keep_every_discrete_result(emu, name, steps, full):
+    """mce_options.fast_moments: tree sums for every moment but Re fz, which the exact scan keeps bit-identical: counts, keys, hyperplanes and G values unchanged."""
+    import numpy as np
+    sc = read_scenario(os.path.join(GOLD, name + ".mces"))
+    gold = _upto(read_dump(os.path.join(GOLD, name + ".ref.mced")), steps)
+    got = run_scenario(emu, sc, full_upto=full, max_steps=steps, capture=True, fast_moments=2)       # threshold 2 slots: every step takes the tree + scan path
+    got = {n: v for n, v in got.items() if n in gold}
+    probs = compare_dumps(gold, got, float_rtol=0.0, float_names_rtol={r"fdigest$": 1e-12}, skip=lambda n: n.endswith("/moments"))
+    for n in gold:
+        if n.endswith("/moments") and not n.startswith("s1/"):
+            if gold[n][0].real.tobytes() != got[n][0].real.tobytes():
+                probs.append("%s: Re fz is not bit-identical" % n)
+            a, b, d = gold[n], got[n], sc.d
+            if np.max(np.abs(a[1:1 + d] - b[1:1 + d])) > 1e-8 * np.max(np.abs(a[1:1 + d])) or np.max(np.abs(a[1 + d:] - b[1 + d:])) > 1e-4 * np.max(np.abs(a[1 + d:])):
+                probs.append("%s: mean / covariance beyond the reordering noise" % n)
+    assert not probs, "\n".join(probs[:20])

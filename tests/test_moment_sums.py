@@ -69,7 +69,7 @@ def _check_scan(lib):
     finally:
         s.close()
     assert restarts["long_positive"] < 200 and restarts["all_zero"] == 0, restarts      # the scan path really carries the friendly chains
-    assert restarts["binade_walk"] > 50, restarts                                        # ... and the literal loop the hostile ones
+    assert 3 <= restarts["binade_walk"] < 40, restarts                                   # ... and the literal loop (in doubling runs) the hostile ones
     # the tiled path: 300 000 friendly addends are 37 tiles, nearly all applied from their summaries; hostile data falls back and is still exact
     assert fast["long_positive"] >= 30 and fast["tiles_ties"] >= 14, fast
     assert fast["tiles_big_offsets"] == 0 and fast["tiles_guess_off"] == 0 and fast["tiles_inf_inside"] < 10, fast      # wrong guesses cost time, never bits
