@@ -210,6 +210,10 @@ def gpu_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # stdout carries ONE JSON line: libraries that chat on it (NCCL prints its version on communicator creation) are sent to stderr, the line goes to the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local_rank)
@@ -389,7 +393,8 @@ def gpu_arm(args):
                                     "sample": "%s of the 12-MU window, one pass (%d child terms, %.1f s of step() time), %s" % (
                                         "all 12 MUs" if not args.short_cpu_baseline else "MUs 1..%d" % MATCHED_MUS,
                                         _child_terms(rows), ms / 1e3, "unmodified reference NUM_CPUS=8" if kind == "reference" else "plain-C oracle, 1 thread")}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     s.close()
     if dist:
         dist.destroy_process_group()
