@@ -387,16 +387,31 @@ class Engine {
     be.xchg_alltoallv(send, soff.data(), scnt.data(), recv, roff.data(), rcnt.data());
   }
 
+  // Hybrid moments: only Re g of every slot, packed, at its canonical position of the global slot list (8 bytes per slot to combine instead of 16 + 16 d).
+  long long part_gather_re(const SlotView& sl, const GenStore& pg, const double** re_out) {
+    KSlotScatter k; memset(&k, 0, sizeof(k));
+    long long ng_slots = 0; int base = 0;
+    for (int m = 0; m < NSHAPE; m++) { k.gslot_begin[m] = ng_slots; k.gshape_base[m] = base; ng_slots += (long long)g_alive_per_shape[m] * (sl.MT[m] + 1); base += g_alive_per_shape[m]; }
+    double* buf = (double*)ptGg.ensure(sizeof(double) * ((size_t)ng_slots + 8));
+    be.memset(buf, 0, sizeof(double) * (size_t)ng_slots);
+    k.sl = sl; k.d = d; k.gpos = pg.gpos.template as<int>(); k.re_out = buf;
+    if (sl.n_slots > 0) be.launch(k, (int)((sl.n_slots + 127) / 128), 128, 0);
+    be.xchg_begin(); be.xchg_allreduce_u32(buf, (size_t)ng_slots * 2); be.xchg_end();
+    pstats.bytes_moments = (long long)(sizeof(double) * (size_t)ng_slots);
+    *re_out = buf;
+    return ng_slots;
+  }
+
   // One serial-order sum (Re of n complex values), bit-identical to the dependent chain: tile summaries in parallel, then the exact walk (csrc/mce_kern_prop.h).
-  void launch_sum_scan(bool side, const cplx* g, long long n, double* out) {
+  void launch_sum_scan(bool side, const double* g, int stride, long long n, double* out) {
     const long long TILE = (long long)SS_NT * SS_E, ntiles = (n + TILE - 1) / TILE;
-    KSumScan k{g, n, out};
+    KSumScan k{g, stride, n, out};
     static const bool no_tiles = getenv("MCE_SCAN_NO_TILES") != nullptr;      // measurement switch (tools/scan_real.py)
     if (ntiles >= 4 && !no_tiles) {
       const size_t off = (sizeof(double) * (size_t)ntiles + 63) & ~(size_t)63;
       unsigned char* buf = (unsigned char*)sumTiles.ensure(off + sizeof(SumTile) * (size_t)ntiles + 64);
       double* tsum = (double*)buf; SumTile* tiles = (SumTile*)(buf + off);
-      KSumTileSums k1{g, n, tsum}; KSumTileMaps k2{g, n, tsum, tiles};
+      KSumTileSums k1{g, stride, n, tsum}; KSumTileMaps k2{g, stride, n, tsum, tiles};
       if (side) { be.launch_side(k1, (int)ntiles, SS_NT, KSumTileSums::smem_bytes(SS_NT)); be.launch_side(k2, (int)ntiles, SS_NT, KSumTileMaps::smem_bytes(SS_NT)); }
       else { be.launch(k1, (int)ntiles, SS_NT, KSumTileSums::smem_bytes(SS_NT)); be.launch(k2, (int)ntiles, SS_NT, KSumTileMaps::smem_bytes(SS_NT)); }
       k.tiles = tiles;
@@ -760,10 +775,10 @@ class Engine {
     // its CTAs are placed on idle SMs, so the main stream is drained first (measured: 8.4 ms instead of 11.6 ms at 1.1 M slots).
     // partitioned estimator, ordered moments: the sums run over ALL ranks' slots in the reference's order (bit-exact)
     const cplx* mom_g = sl.g; const double* mom_y = sl.y; long long mom_n = nslots;
-    const cplx* scan_g = nullptr; long long scan_n = 0;
+    const double* scan_g = nullptr; long long scan_n = 0; int scan_stride = 2;
     if (part) {
       if (moments_mode == 0) { cplx* gg; double* gy; mom_n = part_gather_slots(sl, pg, &gg, &gy); mom_g = gg; mom_y = gy; stats.slots = mom_n; }
-      if (moments_mode == 2) { cplx* gg; scan_n = part_gather_slots(sl, pg, &gg, nullptr, false); scan_g = gg; stats.slots = scan_n; }
+      if (moments_mode == 2) { scan_n = part_gather_re(sl, pg, &scan_g); scan_stride = 1; stats.slots = scan_n; }
     }
     // Large steps: the G-table build only needs G_SCALE_FACTOR = 1 / (2 pi Re fz), and Re fz alone is available early -- KSumScan adds that one chain
     // as an exact parallel scan, 3x faster than the dependent chain (bit-identical; checked against the chain's own Re fz below).  The G-table kernels
@@ -773,12 +788,12 @@ class Engine {
     be.sync();
     be.side_begin();
     be.ev_record_side(4);
-    if (early_scale) { launch_sum_scan(true, sl.g, nslots, mom + 2 * nq); be.ev_record_side(9); }
+    if (early_scale) { launch_sum_scan(true, (const double*)sl.g, 2, nslots, mom + 2 * nq); be.ev_record_side(9); }
     if ((fast_moments && !part && nslots >= fast_moments_slots) || (part && moments_mode == 2)) {
       // mce_options.fast_moments on one GPU / hybrid on a partitioned estimator: no dependent chain.  Every sum is a fixed-shape two-level reduction (deterministic
       // for a given partition; a rank's sums are added to the other ranks' in rank order anyway) EXCEPT the one whose bits matter downstream: Re fz comes from the
       // exact scan -- over all ranks' slots when partitioned -- so G_SCALE_FACTOR, and with it every count, key and G value, stays bit-identical.
-      if (!part) { scan_g = sl.g; scan_n = nslots; }
+      if (!part) { scan_g = (const double*)sl.g; scan_stride = 2; scan_n = nslots; }
       const int nblk = (int)((nslots + MOM_CHUNK - 1) / MOM_CHUNK);
       double* partial = (double*)momPartial.ensure(sizeof(double) * (size_t)(nblk > 0 ? nblk : 1) * 2 * nq + 64);
       if (nblk > 0) be.launch_side(KMomentsPartial{sl.g, sl.y, nslots, d, partial, 1}, nblk, 128, sizeof(double) * 2 * 128);
@@ -787,7 +802,7 @@ class Engine {
       be.launch_side(KMomentsSerial{mom_g, mom_y, mom_n, d, mom}, (nq + MOM_QB - 1) / MOM_QB, 512, KMomentsSerial::smem_bytes(d));
     }
     if (scan_g) {       // one CTA; on the window's last step nothing else waits on the main stream, so it runs there, beside the rank's own chains
-      launch_sum_scan(!skip_post_mu, scan_g, scan_n, mom + 2 * nq);
+      launch_sum_scan(!skip_post_mu, scan_g, scan_stride, scan_n, mom + 2 * nq);
     }
     be.ev_record_side(5);
     double early_refz = 0, chain_refz = 0;
@@ -1332,7 +1347,7 @@ class Engine {
     double* mom = (double*)momOut.ensure(sizeof(double) * 4 * (1 + d + d * d) + 16);
     if (n > 0) be.h2d(gg, g, sizeof(cplx) * (size_t)n);
     be.ev_record(10);
-    launch_sum_scan(false, gg, n, mom);
+    launch_sum_scan(false, (const double*)gg, 2, n, mom);
     be.ev_record(11);
     be.d2h(out, mom, sizeof(double) * 3);
     cpdf_ms = be.ev_elapsed(10, 11);          // device time of the kernel, read back through mce_cpdf_last_ms

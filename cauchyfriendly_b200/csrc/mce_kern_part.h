@@ -358,7 +358,8 @@ struct KSurvRank {                        // gpos[a] = survivors of lower shapes
 
 // ---- ordered moments: every slot's (g, y) goes to its canonical position of the global slot list ----
 struct KSlotScatter {
-  SlotView sl; int d; const int* gpos; cplx* g_out; double* y_out;      // y_out == nullptr: only g (the exact scan of Re fz needs nothing else)
+  SlotView sl; int d; const int* gpos; cplx* g_out; double* y_out;      // y_out == nullptr: only g
+  double* re_out;                                                        // != nullptr: only Re g, packed (all the exact scan of Re fz needs: half the bytes to combine)
   long long gslot_begin[NSHAPE]; int gshape_base[NSHAPE];
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     c.par([&](int tid) {
@@ -368,6 +369,7 @@ struct KSlotScatter {
       const long long ls = s - sl.slot_begin[ms];
       const int r = sl.par_begin[ms] + (int)(ls / per), t = (int)(ls % per);
       const long long gs = gslot_begin[ms] + (long long)(gpos[r] - gshape_base[ms]) * per + t;
+      if (re_out) { re_out[gs] = sl.g[s].re; return; }
       g_out[gs] = sl.g[s];
       if (y_out) for (int i = 0; i < 2 * d; i++) y_out[gs * 2 * d + i] = sl.y[s * 2 * d + i];
     });

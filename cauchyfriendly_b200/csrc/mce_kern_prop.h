@@ -579,14 +579,14 @@ constexpr int SS_NT = 1024;             // threads of the scan kernels: a tile i
 struct SumTile { long long d[2], mn[2], mx[2]; int E, sign, ok, pad; };
 struct SumRange { long long mn[2], mx[2]; };
 struct KSumTileSums {                   // tsum[t] = plain sum of tile t (order irrelevant: it only feeds the guess)
-  const cplx* x; long long n; double* tsum;
+  const double* x; int xs /* stride in doubles: 2 = real parts of a complex array, 1 = packed reals */; long long n; double* tsum;
   static MCE_HD size_t smem_bytes(int nthreads) { return sizeof(double) * (size_t)nthreads + 64; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     double* part = (double*)c.smem();
     const long long base = (long long)c.block() * c.nthreads() * SS_E;
     c.par([&](int tid) {
       double acc = 0;
-      for (int e = 0; e < SS_E; e++) { const long long k = base + (long long)tid * SS_E + e; if (k < n) acc += x[k].re; }
+      for (int e = 0; e < SS_E; e++) { const long long k = base + (long long)tid * SS_E + e; if (k < n) acc += x[k * xs]; }
       part[tid] = acc;
     });
     for (int w = c.nthreads() >> 1; w >= 1; w >>= 1) c.par([&](int tid) { if (tid < w) part[tid] += part[tid + w]; });
@@ -594,7 +594,7 @@ struct KSumTileSums {                   // tsum[t] = plain sum of tile t (order 
   }
 };
 struct KSumTileMaps {
-  const cplx* x; long long n; const double* tsum; SumTile* tiles;
+  const double* x; int xs; long long n; const double* tsum; SumTile* tiles;
   static MCE_HD size_t smem_bytes(int nthreads) { return sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(SumRange) * ((size_t)nthreads + 32) + sizeof(double) * ((size_t)nthreads + 2) + sizeof(int) * 4 + 64; }
   template <class Ctx> MCE_KERNEL_FN void run(Ctx& c) const {
     const int NT = c.nthreads(), t = c.block();
@@ -619,7 +619,7 @@ struct KSumTileMaps {
         const long long k = base + (long long)tid * SS_E + e;
         if (k >= n) break;
         MomMap me = mom_identity();
-        if (!mom_classify(x[k].re, st, &me)) bad = 1;
+        if (!mom_classify(x[k * xs], st, &me)) bad = 1;
         m = mom_compose(m, me);
       }
       maps[tid] = m;
@@ -634,7 +634,7 @@ struct KSumTileMaps {
         const long long k = base + (long long)tid * SS_E + e;
         if (k >= n) break;
         MomMap me = mom_identity();
-        mom_classify(x[k].re, st, &me);
+        mom_classify(x[k * xs], st, &me);
         for (int pi = 0; pi < 2; pi++) {
           o[pi] += ((pi + o[pi]) & 1) ? me.d1 : me.d0;
           if (o[pi] < r.mn[pi]) r.mn[pi] = o[pi];
@@ -659,7 +659,7 @@ struct KSumTileMaps {
   }
 };
 struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re + ... (n addends) in order; out[1] = restarts, out[2] = tiles taken from their summaries (statistics)
-  const cplx* x; long long n; double* out;
+  const double* x; int xs; long long n; double* out;
   const SumTile* tiles = nullptr;       // summaries of KSumTileMaps (same tile size), or null: every tile the slow way
   static MCE_HD size_t smem_bytes(int nthreads) {
     return sizeof(double) * (2 * (size_t)nthreads * SS_E + 2) + sizeof(MomMap) * ((size_t)nthreads + 32) + sizeof(long long) * ((size_t)nthreads + 2) + sizeof(int) * 8 + 64;
@@ -675,7 +675,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
     const long long ntiles = (n + TILE - 1) / TILE;
     c.par([&](int tid) {
       if (tid == 0) { sv[0] = 0; ctl[3] = 0; ctl[4] = 0; ctl[5] = SS_SERIAL / 2; }
-      if (!tiles) for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
+      if (!tiles) for (int e = 0; e < SS_E; e++) { const long long k = (long long)tid * SS_E + e; vals[tid * SS_E + e] = (k < n) ? x[k * xs] : 0.0; }
     });
     for (long long t = 0; t < ntiles; t++) {
       if (tiles) {
@@ -699,7 +699,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
         if (t >= ntiles) break;
         c.par([&](int tid) {
           double* buf = vals + (t & 1) * (size_t)TILE;
-          for (int e = 0; e < SS_E; e++) { const long long k = t * TILE + (long long)tid * SS_E + e; buf[tid * SS_E + e] = (k < n) ? x[k].re : 0.0; }
+          for (int e = 0; e < SS_E; e++) { const long long k = t * TILE + (long long)tid * SS_E + e; buf[tid * SS_E + e] = (k < n) ? x[k * xs] : 0.0; }
         });
       }
       const int cnt = (int)((n - t * TILE) < TILE ? (n - t * TILE) : TILE);
@@ -714,7 +714,7 @@ struct KSumScan {                       // ONE block; out[0] = x[0].re + x[1].re
         c.par([&](int tid) {
           double nx[SS_E];
           const bool pre = !tiles && pos == 0 && t + 1 < ntiles;
-          if (pre) for (int e = 0; e < SS_E; e++) { const long long k = (t + 1) * TILE + (long long)tid * SS_E + e; nx[e] = (k < n) ? x[k].re : 0.0; }
+          if (pre) for (int e = 0; e < SS_E; e++) { const long long k = (t + 1) * TILE + (long long)tid * SS_E + e; nx[e] = (k < n) ? x[k * xs] : 0.0; }
           MomMap m = mom_identity(); int bad = 0;
           for (int e = 0; e < SS_E; e++) {
             const int k = tid * SS_E + e;
