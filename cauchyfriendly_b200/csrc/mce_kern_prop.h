@@ -623,7 +623,7 @@ struct KSumTileMaps {
         m = mom_compose(m, me);
       }
       maps[tid] = m;
-      if (bad) ctl[0] = 1;                            // benign race: every writer stores 1
+      if (bad) c.atomic_or((unsigned*)&ctl[0], 1u);
     });
     c.block_scan(maps, maps + NT, [](const MomMap& f, const MomMap& g) { return mom_compose(f, g); });
     c.par([&](int tid) {                               // prefix offsets for both parities of the significand at the tile's start
@@ -916,8 +916,8 @@ struct KRegroup {
           const long long gt = tv.t_begin[m] + rank;
           double* bo = tv.b + gt * d; const double* bi = sl.b + slot * d;
           for (int i = 0; i < d; i++) bo[i] = bi[i];
-          const unsigned long long* ci = (const unsigned long long*)(sl.cmap + slot * MAXM); unsigned long long* co = (unsigned long long*)(tv.cmap + gt * MAXM);
-          if (me.flags & 2) for (int i = 0; i < MAXM / 8; i++) co[i] = ci[i];       // only coaligned children own a map (initcheck-clean)
+          const unsigned char* ci = sl.cmap + slot * MAXM; unsigned char* co = tv.cmap + gt * MAXM;
+          if (me.flags & 2) for (int i = 0; i < me.pbc; i++) co[i] = ci[i];         // only coaligned children own a map, of pbc entries (initcheck-clean)
           tv.meta[gt] = me; slot_of_term[gt] = slot;
         }
         desc[k] = e;
