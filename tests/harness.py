@@ -24,9 +24,19 @@ def _dp(a):
     return a.ctypes.data_as(ct.POINTER(ct.c_double)) if a is not None else None
 
 
+def _emu_stale(so):
+    """The emulation library is older than one of its sources (kernel headers, C ABI, the emulation backend)."""
+    if not os.path.exists(so):
+        return True
+    t = os.path.getmtime(so)
+    dirs = [os.path.join(ROOT, "cauchyfriendly_b200", "csrc"), os.path.join(ROOT, "tests", "emu"), os.path.join(ROOT, "include")]
+    return any(os.path.getmtime(os.path.join(d, f)) > t for d in dirs for f in os.listdir(d) if os.path.isfile(os.path.join(d, f)))
+
+
 def load_emu(rebuild=False):
+    """rebuild=True: make sure the library is up to date with its sources (a 20 s g++ run only when one of them changed)."""
     so = os.path.join(ROOT, "tests", "emu", "_build", "libmce_emu.so")
-    if rebuild or not os.path.exists(so):
+    if not os.path.exists(so) or (rebuild and _emu_stale(so)):
         subprocess.check_call([os.path.join(ROOT, "tests", "emu", "build.sh")])
     return bind(ct.CDLL(so))
 
