@@ -70,3 +70,31 @@ def test_create_without_gpu_reports_no_fallback(lib):
     h = lib.mce_create(d, 0, 1, 1, 5, dp(np.eye(d).ravel().copy()), dp(np.ones(d)), dp(np.zeros(d)), dp(np.ones(d) * 1.5), dp(np.zeros(64)), ct.byref(o))
     assert not h
     assert b"no CPU fallback" in lib.mce_last_error()
+
+
+def test_ctypes_mirrors_match_the_c_structs(tmp_path):
+    """The Python mirrors of the C ABI structs (cauchyfriendly_b200/_capi.py) have the size and the field offsets the C compiler gives include/mce_b200.h:
+    a field added to one side only would silently shift everything behind it."""
+    import ctypes as ct
+    import subprocess
+    from cauchyfriendly_b200 import _capi
+    src = tmp_path / "abi.c"
+    src.write_text("""#include <stdio.h>
+#include <stddef.h>
+#include "mce_b200.h"
+int main(void) {
+  printf("%zu %zu %zu %zu\\n", sizeof(mce_options), offsetof(mce_options, lean_group_kernel), offsetof(mce_options, fast_moments_min_slots), offsetof(mce_options, reserved));
+  printf("%zu %zu %zu\\n", sizeof(mce_moments), offsetof(mce_moments, g_scale_factor), offsetof(mce_moments, skip_post_mu));
+  printf("%zu %zu %zu\\n", sizeof(mce_step_stats), offsetof(mce_step_stats, ev_mu_ms), offsetof(mce_step_stats, gtable_lean_launches));
+  printf("%zu\\n", sizeof(mce_alltoallv_args));
+  return 0;
+}
+""")
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-I" + os.path.join(ROOT, "include"), str(src), "-o", exe])
+    rows = [[int(v) for v in line.split()] for line in subprocess.check_output([exe]).decode().splitlines()]
+    O, M, S = _capi.MceOptions, _capi.MceMoments, _capi.MceStepStats
+    assert rows[0] == [ct.sizeof(O), O.lean_group_kernel.offset, O.fast_moments_min_slots.offset, O.reserved.offset]
+    assert rows[1] == [ct.sizeof(M), M.g_scale_factor.offset, M.skip_post_mu.offset]
+    assert rows[2] == [ct.sizeof(S), S.ev_mu_ms.offset, S.gtable_lean_launches.offset]
+    assert rows[3] == [ct.sizeof(_capi.MceAllToAllV)]
